@@ -1,0 +1,180 @@
+/*
+ * gsplat_b200.h — C ABI of libgsplat_b200.so: the sm_100a implementation of the
+ * taichi_splatting render path (project -> SH -> tile map -> sort -> rasterize fwd/bwd).
+ *
+ * This is the drop-in boundary.  The reference's native boundary is only the three CUB
+ * wrappers of taichi_splatting/cuda_lib/module.cpp:14-18; its other kernels are Taichi-JIT
+ * and have no ABI, so each entry point below cites the reference kernel / wrapper it
+ * replaces.  Paths are relative to /root/reference/taichi_splatting/.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated;
+ *   - the caller owns all memory (inputs, outputs, workspaces); the library never allocates
+ *     device memory and keeps no pointer after returning;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises
+ *     the host; calls are re-entrant;
+ *   - return value: GS_OK (0) or a negative GsStatus; gs_last_error_string() describes the last
+ *     failure on the calling thread.  Nothing throws or exits across this boundary;
+ *   - `dtype` selects float (GS_F32) or double (GS_F64) for every `void*` floating tensor of
+ *     the call; the tile mapper is f32 only, like the reference (mapper/tile_mapper.py:12);
+ *   - tensors are dense row-major with the shapes stated.
+ */
+#ifndef GSPLAT_B200_H
+#define GSPLAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum GsStatus {
+  GS_OK = 0,
+  GS_ERR_INVALID = -1,     /* bad argument / shape */
+  GS_ERR_UNSUPPORTED = -2, /* configuration outside the implemented set */
+  GS_ERR_CUDA = -3,        /* a CUDA runtime call failed */
+  GS_ERR_WORKSPACE = -4    /* workspace too small */
+} GsStatus;
+
+typedef enum GsDtype { GS_F32 = 0, GS_F64 = 1 } GsDtype;
+
+int gs_abi_version(void);
+const char* gs_last_error_string(void);
+
+/* ------------------------------------------------------------------ projection
+ * replaces project_kernel + torch.nonzero + gather (perspective/projection.py:31-80, :146-149)
+ * and indexed_project_kernel.grad (:83-118, :164-185). */
+typedef struct GsProjectParams {
+  int32_t dtype;
+  int32_t image_width, image_height;
+  int64_t num_points;      /* N */
+  double near_plane, far_plane;
+  double blur_cov, clamp_margin, alpha_threshold;
+} GsProjectParams;
+
+size_t gs_project_fwd_workspace_bytes(const GsProjectParams* p);
+
+/* position (N,3) log_scaling (N,3) rotation (N,4 xyzw) alpha_logit (N,1) T_camera_world (4,4)
+ * projection (4: fx fy cx cy).  Outputs have capacity N; the first *num_visible rows are
+ * valid, in ascending gaussian index order (identical to nonzero()):
+ * points (N,7) depth (N,1) indexes (N) int64, num_visible: one int32 on the device. */
+int gs_project_fwd(const GsProjectParams* p, const void* position, const void* log_scaling,
+                   const void* rotation, const void* alpha_logit, const void* T_camera_world,
+                   const void* projection, void* points, void* depth, int64_t* indexes,
+                   int32_t* num_visible, void* workspace, size_t workspace_bytes, void* stream);
+
+/* grad_points (V,7) grad_depth (V,1) -> dense grads, fully written (zero for culled points):
+ * grad_position (N,3) grad_log_scaling (N,3) grad_rotation (N,4) grad_alpha_logit (N,1)
+ * grad_T_camera_world (4,4; last row zero) grad_projection (4).  Any grad pointer may be NULL. */
+int gs_project_bwd(const GsProjectParams* p, int64_t num_visible, const void* position,
+                   const void* log_scaling, const void* rotation, const void* alpha_logit,
+                   const void* T_camera_world, const void* projection, const int64_t* indexes,
+                   const void* grad_points, const void* grad_depth, void* grad_position,
+                   void* grad_log_scaling, void* grad_rotation, void* grad_alpha_logit,
+                   void* grad_T_camera_world, void* grad_projection, void* stream);
+
+/* ------------------------------------------------------------------ spherical harmonics
+ * replaces evaluate_sh_at_kernel and its .grad (spherical_harmonics.py:118-134, :154-161). */
+typedef struct GsSHParams {
+  int32_t dtype;
+  int32_t num_channels;    /* K */
+  int32_t num_coeffs;      /* D = (degree+1)^2, degree 0..3 */
+  int64_t num_points;      /* M */
+  int64_t num_indexes;     /* V */
+} GsSHParams;
+
+/* params (M,K,D) positions (M,3) indexes (V) int64 camera_pos (3) -> out (V,K) */
+int gs_sh_fwd(const GsSHParams* p, const void* params, const void* positions,
+              const int64_t* indexes, const void* camera_pos, void* out, void* stream);
+
+/* grad_out (V,K) -> grad_params (M,K,D) grad_positions (M,3) grad_camera_pos (3); each fully
+ * written (zeroed then accumulated; repeated indexes are summed).  Any may be NULL. */
+int gs_sh_bwd(const GsSHParams* p, const void* params, const void* positions,
+              const int64_t* indexes, const void* camera_pos, const void* grad_out,
+              void* grad_params, void* grad_positions, void* grad_camera_pos, void* stream);
+
+/* ------------------------------------------------------------------ tile mapper (f32)
+ * replaces tile_overlaps_kernel / generate_sort_keys_kernel / find_ranges_kernel
+ * (mapper/tile_mapper.py:73-84, :112-144, :90-110) with the OBB query of
+ * taichi_lib/grid_query.py:9-91, and cuda_lib.full_cumsum / cuda_lib.radix_sort_pairs
+ * (cuda_lib/full_cumsum.cu:16-67, cuda_lib/radix_sort_pairs.cu:9-69). */
+typedef struct GsTileParams {
+  int32_t image_width, image_height; /* unpadded; padded to tile_size internally */
+  int32_t tile_size;
+  int32_t use_depth16;               /* 0: u64 key = tile<<32 | f32 bits; 1: u32 key = tile<<16 | depth16 */
+  int64_t num_points;                /* V */
+  double alpha_threshold;
+} GsTileParams;
+
+/* gaussians (V,7) -> counts (V) int32 */
+int gs_tile_count(const GsTileParams* p, const float* gaussians, int32_t* counts, void* stream);
+
+/* full_cumsum: out has n+1 entries, out[i] = sum(in[0..i)), out[n] = total (stays on the device;
+ * the caller reads it back when it needs the size).  elem_bytes 4 (int32) or 8 (int64). */
+size_t gs_full_cumsum_workspace_bytes(int64_t n, int32_t elem_bytes);
+int gs_full_cumsum(int64_t n, int32_t elem_bytes, const void* in, void* out, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* gaussians (V,7) depth (V) cum (V) -> keys (K) u64|u32, values (K) int32 (gaussian index) */
+int gs_tile_emit_keys(const GsTileParams* p, const float* gaussians, const float* depth,
+                      const int32_t* cum, void* keys, int32_t* values, void* stream);
+
+/* stable LSD onesweep radix sort of (key, int32 value) pairs on key bits [begin_bit, end_bit).
+ * key_bytes 4 or 8.  Inputs are preserved. */
+size_t gs_radix_sort_pairs_workspace_bytes(int64_t n, int32_t key_bytes, int32_t begin_bit,
+                                           int32_t end_bit);
+int gs_radix_sort_pairs(int64_t n, int32_t key_bytes, const void* keys_in, const int32_t* values_in,
+                        void* keys_out, int32_t* values_out, int32_t begin_bit, int32_t end_bit,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* sorted keys (K) -> tile_ranges (T,2) int32, fully written ([0,0] for empty tiles) */
+int gs_find_ranges(const GsTileParams* p, int64_t num_overlaps, const void* sorted_keys,
+                   int32_t* tile_ranges, void* stream);
+
+/* ------------------------------------------------------------------ rasterizer
+ * replaces _forward_kernel (rasterizer/forward.py:24-137) and _backward_kernel
+ * (rasterizer/backward.py:52-228). */
+typedef struct GsRasterParams {
+  int32_t dtype;
+  int32_t image_width, image_height;
+  int32_t tile_size;                 /* 8, 16 or 32 */
+  int32_t num_features;              /* F */
+  int32_t antialias;
+  int32_t use_alpha_blending;
+  int32_t compute_visibility;
+  int32_t compute_point_heuristic;
+  int32_t points_requires_grad, features_requires_grad;
+  int32_t emulate_stale_tail;        /* reproduce forward.py:88; 1 for reference parity */
+  int32_t pixel_stride_x, pixel_stride_y; /* validated like backward.py:33-34, otherwise a hint */
+  int32_t workspace_holds_packed;    /* bwd: workspace still holds the records packed by fwd */
+  int32_t reserved_;
+  int64_t num_points;                /* V */
+  int64_t num_overlaps;              /* K */
+  double clamp_max_alpha, alpha_threshold, saturate_threshold;
+  /* forward stops a tile once every pixel's transmittance 1-W is <= this; 0 = exact
+   * (1-W == 0, after which no output can change).  The reference has no forward exit. */
+  double forward_exit_transmittance;
+} GsRasterParams;
+
+size_t gs_raster_workspace_bytes(const GsRasterParams* p);
+
+/* gaussians2d (V,7) features (V,F) tile_ranges (T,2) int32 overlap_to_point (K) int32 ->
+ * image (H,W,F) image_alpha (H,W) visibility (V; zeroed by the callee) or NULL */
+int gs_raster_fwd(const GsRasterParams* p, const void* gaussians2d, const void* features,
+                  const int32_t* tile_ranges, const int32_t* overlap_to_point, void* image,
+                  void* image_alpha, void* visibility, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* image (H,W,F: forward output) grad_image (H,W,F) -> grad_gaussians (V,7) grad_features (V,F)
+ * (each zeroed by the callee; NULL if the matching *_requires_grad is 0) and point_heuristic
+ * (V,2), ACCUMULATED in place like backward.py:227-228 (the caller zero-fills it in forward). */
+int gs_raster_bwd(const GsRasterParams* p, const void* gaussians2d, const void* features,
+                  const int32_t* tile_ranges, const int32_t* overlap_to_point, const void* image,
+                  const void* grad_image, void* grad_gaussians, void* grad_features,
+                  void* point_heuristic, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSPLAT_B200_H */

@@ -1,0 +1,120 @@
+"""ctypes binding of libgsplat_b200.so (include/gsplat_b200.h).
+
+There is no CPU or eager-torch fallback behind these functions: if the library has not been built
+(``python -m taichi_gaussian_rasterizer_b200.csrc.build`` / ``__graft_entry__.build()``) or a
+tensor is not a CUDA tensor, the call raises.  torch is used for device memory and streams only.
+"""
+import ctypes
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libgsplat_b200.so"
+
+GS_F32, GS_F64 = 0, 1
+
+EXPORTS = [
+  "gs_abi_version", "gs_last_error_string",
+  "gs_project_fwd_workspace_bytes", "gs_project_fwd", "gs_project_bwd",
+  "gs_sh_fwd", "gs_sh_bwd",
+  "gs_tile_count", "gs_full_cumsum_workspace_bytes", "gs_full_cumsum", "gs_tile_emit_keys",
+  "gs_radix_sort_pairs_workspace_bytes", "gs_radix_sort_pairs", "gs_find_ranges",
+  "gs_raster_workspace_bytes", "gs_raster_fwd", "gs_raster_bwd",
+]
+
+
+class GsProjectParams(ctypes.Structure):
+  _fields_ = [("dtype", ctypes.c_int32), ("image_width", ctypes.c_int32), ("image_height", ctypes.c_int32),
+              ("num_points", ctypes.c_int64), ("near_plane", ctypes.c_double), ("far_plane", ctypes.c_double),
+              ("blur_cov", ctypes.c_double), ("clamp_margin", ctypes.c_double),
+              ("alpha_threshold", ctypes.c_double)]
+
+
+class GsSHParams(ctypes.Structure):
+  _fields_ = [("dtype", ctypes.c_int32), ("num_channels", ctypes.c_int32), ("num_coeffs", ctypes.c_int32),
+              ("num_points", ctypes.c_int64), ("num_indexes", ctypes.c_int64)]
+
+
+class GsTileParams(ctypes.Structure):
+  _fields_ = [("image_width", ctypes.c_int32), ("image_height", ctypes.c_int32), ("tile_size", ctypes.c_int32),
+              ("use_depth16", ctypes.c_int32), ("num_points", ctypes.c_int64),
+              ("alpha_threshold", ctypes.c_double)]
+
+
+class GsRasterParams(ctypes.Structure):
+  _fields_ = [("dtype", ctypes.c_int32), ("image_width", ctypes.c_int32), ("image_height", ctypes.c_int32),
+              ("tile_size", ctypes.c_int32), ("num_features", ctypes.c_int32), ("antialias", ctypes.c_int32),
+              ("use_alpha_blending", ctypes.c_int32), ("compute_visibility", ctypes.c_int32),
+              ("compute_point_heuristic", ctypes.c_int32), ("points_requires_grad", ctypes.c_int32),
+              ("features_requires_grad", ctypes.c_int32), ("emulate_stale_tail", ctypes.c_int32),
+              ("pixel_stride_x", ctypes.c_int32), ("pixel_stride_y", ctypes.c_int32),
+              ("workspace_holds_packed", ctypes.c_int32), ("reserved_", ctypes.c_int32),
+              ("num_points", ctypes.c_int64), ("num_overlaps", ctypes.c_int64),
+              ("clamp_max_alpha", ctypes.c_double), ("alpha_threshold", ctypes.c_double),
+              ("saturate_threshold", ctypes.c_double), ("forward_exit_transmittance", ctypes.c_double)]
+
+
+_lib = None
+
+
+def lib():
+  global _lib
+  if _lib is None:
+    if not LIB_PATH.exists():
+      raise RuntimeError(
+        f"{LIB_PATH} is missing: the sm_100a extension has not been built. Run "
+        "`python -m taichi_gaussian_rasterizer_b200.csrc.build` (or __graft_entry__.build()). "
+        "There is no CPU fallback.")
+    l = ctypes.CDLL(str(LIB_PATH))
+    l.gs_last_error_string.restype = ctypes.c_char_p
+    for name in ("gs_project_fwd_workspace_bytes", "gs_full_cumsum_workspace_bytes",
+                 "gs_radix_sort_pairs_workspace_bytes", "gs_raster_workspace_bytes"):
+      getattr(l, name).restype = ctypes.c_size_t
+    l.gs_full_cumsum_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int32]
+    l.gs_radix_sort_pairs_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                                      ctypes.c_int32]
+    _lib = l
+  return _lib
+
+
+def check(rc: int, what: str):
+  if rc != 0:
+    msg = lib().gs_last_error_string().decode("utf-8", "replace")
+    raise RuntimeError(f"{what} failed ({rc}): {msg}")
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+  if dtype == torch.float32:
+    return GS_F32
+  if dtype == torch.float64:
+    return GS_F64
+  raise TypeError(f"unsupported dtype {dtype}: the kernels are float32 / float64")
+
+
+def require_cuda(*tensors):
+  """Every operator of this package runs on the GPU only; fail loudly otherwise (no CPU fallback)."""
+  for t in tensors:
+    if t is not None and not t.is_cuda:
+      raise RuntimeError("expected a CUDA tensor: this package runs on sm_100a only, there is no CPU path "
+                         f"(got device {t.device})")
+
+
+def ptr(t):
+  """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+  if t is None:
+    return ctypes.c_void_p(0)
+  if not t.is_cuda:
+    raise RuntimeError("expected a CUDA tensor: this package runs on sm_100a only, there is no CPU path "
+                       f"(got device {t.device})")
+  if not t.is_contiguous():
+    raise RuntimeError("expected a contiguous tensor")
+  return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+  return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+  return torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=device)

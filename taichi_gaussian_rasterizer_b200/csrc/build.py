@@ -1,0 +1,82 @@
+"""Builds libgsplat_b200.so in-tree with nvcc for sm_100a (no torch headers: the library is a
+plain C ABI, see include/gsplat_b200.h).
+
+  python -m taichi_gaussian_rasterizer_b200.csrc.build [--force] [--verbose]
+
+geom_kernels.cu carries the bit-exactness contract (include/gs_numeric.h) and is compiled without
+FMA contraction on both its device image (-fmad=false) and its host image (-ffp-contract=off).
+"""
+import argparse
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+CSRC = Path(__file__).resolve().parent
+PKG = CSRC.parent
+ROOT = PKG.parent
+OUT = PKG / "libgsplat_b200.so"
+OBJ = ROOT / "build" / "obj"
+
+SOURCES = ["api.cu", "geom_kernels.cu", "point_kernels.cu", "scan_sort.cu", "raster_api.cu",
+           "raster_generic.cu", "raster_fast_fwd.cu", "raster_fast_bwd.cu"]
+HEADERS = ["common.cuh", "geom_math.cuh", "lookback.cuh", "raster.cuh", "raster_math.cuh", "raster_fast.cuh",
+           "../../include/gsplat_b200.h", "../../include/gs_numeric.h"]
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+PER_FILE = {
+  "geom_kernels.cu": ["-fmad=false", "-Xcompiler", "-ffp-contract=off"],
+}
+
+
+def nvcc() -> str:
+  cand = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
+  return cand if Path(cand).exists() else "nvcc"
+
+
+def host_compiler_args():
+  # the image exports CXX=/opt/gcc/bin/g++ (a wrapper without libgomp specs); the system g++ is fine
+  ccbin = os.environ.get("GS_CCBIN", "/usr/bin/g++")
+  return ["-ccbin", ccbin] if Path(ccbin).exists() else []
+
+
+def _newest_input() -> float:
+  files = [CSRC / s for s in SOURCES] + [CSRC / h for h in HEADERS] + [Path(__file__)]
+  return max(f.stat().st_mtime for f in files)
+
+
+def _compile(src: str, verbose: bool, ptxas_info: bool) -> Path:
+  obj = OBJ / (src.replace(".cu", ".o"))
+  cmd = [nvcc(), *host_compiler_args(), *ARCH, *COMMON, *PER_FILE.get(src, []), "-c", str(CSRC / src), "-o", str(obj)]
+  if ptxas_info:
+    cmd += ["-Xptxas", "-v"]
+  r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+  if r.returncode != 0:
+    raise RuntimeError(f"nvcc failed for {src}:\n{' '.join(cmd)}\n{r.stdout}")
+  if verbose or ptxas_info:
+    print(f"[build] {src}\n{r.stdout}")
+  return obj
+
+
+def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> Path:
+  if not force and OUT.exists() and OUT.stat().st_mtime >= _newest_input():
+    return OUT
+  OBJ.mkdir(parents=True, exist_ok=True)
+  with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as pool:
+    objs = list(pool.map(lambda s: _compile(s, verbose, ptxas_info), SOURCES))
+  cmd = [nvcc(), *host_compiler_args(), *ARCH, "-shared", "-o", str(OUT), *[str(o) for o in objs]]
+  r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+  if r.returncode != 0:
+    raise RuntimeError(f"link failed:\n{' '.join(cmd)}\n{r.stdout}")
+  return OUT
+
+
+if __name__ == "__main__":
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--force", action="store_true")
+  ap.add_argument("--verbose", action="store_true")
+  ap.add_argument("--ptxas-info", action="store_true")
+  args = ap.parse_args()
+  print(build(args.force, args.verbose, args.ptxas_info))

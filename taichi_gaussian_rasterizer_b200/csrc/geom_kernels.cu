@@ -1,0 +1,372 @@
+// geom_kernels.cu — projection forward (fused cull + ordered compaction), tile overlap count,
+// sort-key emission, tile range detection.   Build with -fmad=false (bit-exactness contract,
+// see include/gs_numeric.h).
+//
+// Replaces (paths relative to /root/reference/taichi_splatting/):
+//   project_kernel + nonzero + gathers      perspective/projection.py:31-80, :146-149
+//   tile_overlaps_kernel                    mapper/tile_mapper.py:73-84
+//   generate_sort_keys_kernel               mapper/tile_mapper.py:112-144
+//   find_ranges_kernel                      mapper/tile_mapper.py:90-110
+#include "common.cuh"
+#include "geom_math.cuh"
+#include "lookback.cuh"
+
+namespace gs {
+
+// ------------------------------------------------------------------------------------------------
+// Projection forward.  One thread per gaussian; culled gaussians are dropped in-kernel with an
+// order-preserving compaction (block scan + decoupled look-back), so `indexes` comes out ascending
+// exactly like torch.nonzero() without materialising the (N,7) intermediate or syncing the host.
+// HBM traffic: 44 B read per gaussian, 44 B written per visible gaussian.
+// ------------------------------------------------------------------------------------------------
+constexpr int kProjBlock = 256;
+
+template <typename T>
+__device__ __forceinline__ void load_camera(const T* __restrict__ Tcw, const T* __restrict__ proj,
+                                            const GsProjectParams& p, CameraConst<T>& C) {
+#pragma unroll
+  for (int i = 0; i < 12; ++i) C.Tcw[i] = Tcw[i];
+  C.fx = proj[0]; C.fy = proj[1]; C.cx = proj[2]; C.cy = proj[3];
+  C.w = T(p.image_width); C.h = T(p.image_height);
+  C.near_ = T(p.near_plane); C.far_ = T(p.far_plane); C.blur = T(p.blur_cov);
+  C.lo_x = T(-(double)p.image_width * p.clamp_margin);
+  C.lo_y = T(-(double)p.image_height * p.clamp_margin);
+  C.hi_x = T(((double)p.image_width - 1.0) * (1.0 + p.clamp_margin));
+  C.hi_y = T(((double)p.image_height - 1.0) * (1.0 + p.clamp_margin));
+  C.alpha_threshold = T(p.alpha_threshold);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kProjBlock)
+project_fwd_kernel(const __grid_constant__ GsProjectParams p, const T* __restrict__ position,
+                   const T* __restrict__ log_scaling, const T* __restrict__ rotation,
+                   const T* __restrict__ alpha_logit, const T* __restrict__ Tcw, const T* __restrict__ proj,
+                   T* __restrict__ points, T* __restrict__ depth, int64_t* __restrict__ indexes,
+                   int32_t* __restrict__ num_visible, unsigned long long* __restrict__ status,
+                   unsigned int* __restrict__ ticket) {
+  __shared__ int s_tile;
+  __shared__ int s_warp_count[kProjBlock / 32];
+  __shared__ unsigned long long s_prefix;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  const int64_t i = (int64_t)tile * kProjBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  CameraConst<T> C;
+  load_camera<T>(Tcw, proj, p, C);
+
+  Projected<T> o;
+  o.in_view = false;
+  if (i < p.num_points) {
+    T pos[3] = {position[3 * i], position[3 * i + 1], position[3 * i + 2]};
+    T ls[3] = {log_scaling[3 * i], log_scaling[3 * i + 1], log_scaling[3 * i + 2]};
+    T q[4];
+    if (sizeof(T) == 4) {
+      float4 qv = reinterpret_cast<const float4*>(rotation)[i];
+      q[0] = qv.x; q[1] = qv.y; q[2] = qv.z; q[3] = qv.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) q[k] = rotation[4 * i + k];
+    }
+    o = project_one<T>(pos, ls, q, alpha_logit[i], C);
+  }
+  const unsigned ballot = __ballot_sync(kFull, o.in_view);
+  if (lane == 0) s_warp_count[warp] = __popc(ballot);
+  __syncthreads();
+  int warp_offset = 0, block_total = 0;
+#pragma unroll
+  for (int wi = 0; wi < kProjBlock / 32; ++wi) {
+    int c = s_warp_count[wi];
+    if (wi < warp) warp_offset += c;
+    block_total += c;
+  }
+  if (warp == 0) {
+    unsigned long long ex = lookback_exclusive(status, tile, (unsigned long long)block_total);
+    if (lane == 0) {
+      s_prefix = ex;
+      if (tile == (int)gridDim.x - 1) *num_visible = (int32_t)(ex + block_total);
+    }
+  }
+  __syncthreads();
+  if (o.in_view) {
+    const int64_t dst = (int64_t)s_prefix + warp_offset + __popc(ballot & ((1u << lane) - 1u));
+    T* g = points + 7 * dst;
+    g[0] = o.mean_x; g[1] = o.mean_y; g[2] = o.axis_x; g[3] = o.axis_y;
+    g[4] = o.sigma_x; g[5] = o.sigma_y; g[6] = o.alpha;
+    depth[dst] = o.z;
+    indexes[dst] = i;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile overlap count / key emission.  One lane per gaussian computes the OBB query; spans of at
+// most kSerialSpan tiles are walked by the owning lane, larger spans are handed to the whole warp
+// (query broadcast by shuffle, lanes stride over the span, ballot/popc for counts and ranks) so a
+// single screen-filling gaussian does not stall 31 idle lanes.  The predicate is the same function
+// in both passes.  Emission order within a gaussian is x-outer / y-inner as in the reference.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileBlock = 128;
+constexpr int kSerialSpan = 32;
+
+__device__ __forceinline__ uint64_t make_key64(float depth, int tile_id) {
+  return (uint64_t)__float_as_uint(depth) | ((uint64_t)(uint32_t)tile_id << 32);
+}
+__device__ __forceinline__ uint32_t make_key32(float depth, int tile_id) {
+  float c = depth < 0.f ? 0.f : (depth > 1.f ? 1.f : depth);
+  return (uint32_t)(c * 65535.0f) | ((uint32_t)tile_id << 16);
+}
+
+__device__ __forceinline__ TileQuery shfl_query(const TileQuery& q, int src) {
+  TileQuery r;
+  r.ib00 = __shfl_sync(kFull, q.ib00, src); r.ib01 = __shfl_sync(kFull, q.ib01, src);
+  r.ib10 = __shfl_sync(kFull, q.ib10, src); r.ib11 = __shfl_sync(kFull, q.ib11, src);
+  r.rel_x = __shfl_sync(kFull, q.rel_x, src); r.rel_y = __shfl_sync(kFull, q.rel_y, src);
+  r.min_x = __shfl_sync(kFull, q.min_x, src); r.min_y = __shfl_sync(kFull, q.min_y, src);
+  r.span_x = __shfl_sync(kFull, q.span_x, src); r.span_y = __shfl_sync(kFull, q.span_y, src);
+  return r;
+}
+
+// EMIT = false: counts[i] = number of overlapped tiles.  EMIT = true: write keys / values at cum[i].
+template <bool EMIT, typename KeyT>
+__global__ void __launch_bounds__(kTileBlock)
+tile_query_kernel(const __grid_constant__ GsTileParams p, int img_w, int img_h, const float* __restrict__ g,
+                  const float* __restrict__ depth, const int32_t* __restrict__ cum, int32_t* __restrict__ counts,
+                  KeyT* __restrict__ keys, int32_t* __restrict__ values) {
+  const int64_t i = (int64_t)blockIdx.x * kTileBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int ts = p.tile_size;
+  const int tiles_wide = img_w / ts;
+  const bool valid = i < p.num_points;
+
+  TileQuery qy;
+  qy.span_x = qy.span_y = 0;
+  float d = 0.f;
+  int64_t base = 0;
+  if (valid) {
+    const float* gi = g + 7 * i;
+    qy = obb_query(gi[0], gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], img_w, img_h, ts, (float)p.alpha_threshold);
+    if (EMIT) { d = depth[i]; base = cum[i]; }
+  }
+  const int n = span_count(qy);
+  int count = 0;
+
+  if (n <= kSerialSpan) {
+    for (int tu = 0; tu < qy.span_x; ++tu)
+      for (int tv = 0; tv < qy.span_y; ++tv)
+        if (test_tile(qy, tu, tv, ts)) {
+          if (EMIT) {
+            int tile_id = (tu + qy.min_x) + (tv + qy.min_y) * tiles_wide;
+            keys[base + count] = sizeof(KeyT) == 8 ? (KeyT)make_key64(d, tile_id) : (KeyT)make_key32(d, tile_id);
+            values[base + count] = (int32_t)i;
+          }
+          ++count;
+        }
+  }
+  unsigned big = __ballot_sync(kFull, n > kSerialSpan);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const TileQuery q = shfl_query(qy, src);
+    const int nq = q.span_x * q.span_y;
+    const float dq = __shfl_sync(kFull, d, src);
+    const long long bq = __shfl_sync(kFull, (long long)base, src);
+    const long long iq = __shfl_sync(kFull, (long long)i, src);
+    int running = 0;
+    for (int t0 = 0; t0 < nq; t0 += 32) {
+      const int t = t0 + lane;
+      bool hit = false;
+      int tu = 0, tv = 0;
+      if (t < nq) {
+        tu = t / q.span_y; tv = t - tu * q.span_y;
+        hit = test_tile(q, tu, tv, ts);
+      }
+      const unsigned hm = __ballot_sync(kFull, hit);
+      if (EMIT && hit) {
+        const int r = running + __popc(hm & ((1u << lane) - 1u));
+        int tile_id = (tu + q.min_x) + (tv + q.min_y) * tiles_wide;
+        keys[bq + r] = sizeof(KeyT) == 8 ? (KeyT)make_key64(dq, tile_id) : (KeyT)make_key32(dq, tile_id);
+        values[bq + r] = (int32_t)iq;
+      }
+      running += __popc(hm);
+    }
+    if (lane == src) count = running;
+  }
+  if (!EMIT && valid) counts[i] = count;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile ranges from sorted keys.  ranges[t] = [first, last+1); tiles without overlaps stay [0,0].
+// ------------------------------------------------------------------------------------------------
+template <typename KeyT, int SHIFT>
+__global__ void find_ranges_kernel(int64_t n, const KeyT* __restrict__ keys, int32_t* __restrict__ ranges) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int max_tile = 65535;
+  const int tile = (int)(keys[i] >> SHIFT);
+  int next = max_tile;
+  if (i + 1 < n) next = (int)(keys[i + 1] >> SHIFT);
+  if (tile != next) {
+    ranges[2 * tile + 1] = (int32_t)(i + 1);
+    if (next < max_tile) ranges[2 * next] = (int32_t)(i + 1);
+  }
+}
+
+}  // namespace gs
+
+using namespace gs;
+
+// ================================================================================================ C ABI
+extern "C" {
+
+size_t gs_project_fwd_workspace_bytes(const GsProjectParams* p) {
+  if (!p) return 0;
+  int64_t blocks = ceil_div(p->num_points > 0 ? p->num_points : 1, kProjBlock);
+  return align_up((size_t)blocks * sizeof(unsigned long long) + 16, 256);
+}
+
+int gs_project_fwd(const GsProjectParams* p, const void* position, const void* log_scaling, const void* rotation,
+                   const void* alpha_logit, const void* T_camera_world, const void* projection, void* points,
+                   void* depth, int64_t* indexes, int32_t* num_visible, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  GS_CHECK_ARG(p != nullptr, "gs_project_fwd: null params");
+  GS_CHECK_ARG(p->dtype == GS_F32 || p->dtype == GS_F64, "gs_project_fwd: dtype must be GS_F32 or GS_F64");
+  GS_CHECK_ARG(p->num_points >= 0 && p->image_width > 0 && p->image_height > 0, "gs_project_fwd: bad sizes");
+  GS_CHECK_ARG(num_visible != nullptr, "gs_project_fwd: num_visible is null");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->num_points == 0) {
+    GS_CUDA(cudaMemsetAsync(num_visible, 0, sizeof(int32_t), st));
+    return GS_OK;
+  }
+  GS_CHECK_ARG(position && log_scaling && rotation && alpha_logit && T_camera_world && projection && points &&
+                   depth && indexes, "gs_project_fwd: null tensor");
+  size_t need = gs_project_fwd_workspace_bytes(p);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("gs_project_fwd: workspace %zu < %zu bytes", workspace_bytes, need);
+    return GS_ERR_WORKSPACE;
+  }
+  int64_t blocks = ceil_div(p->num_points, kProjBlock);
+  GS_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+  unsigned long long* status = (unsigned long long*)workspace;
+  unsigned int* ticket = (unsigned int*)(status + blocks);
+  if (p->dtype == GS_F32) {
+    project_fwd_kernel<float><<<(unsigned)blocks, kProjBlock, 0, st>>>(
+        *p, (const float*)position, (const float*)log_scaling, (const float*)rotation, (const float*)alpha_logit,
+        (const float*)T_camera_world, (const float*)projection, (float*)points, (float*)depth, indexes, num_visible,
+        status, ticket);
+  } else {
+    project_fwd_kernel<double><<<(unsigned)blocks, kProjBlock, 0, st>>>(
+        *p, (const double*)position, (const double*)log_scaling, (const double*)rotation,
+        (const double*)alpha_logit, (const double*)T_camera_world, (const double*)projection, (double*)points,
+        (double*)depth, indexes, num_visible, status, ticket);
+  }
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+static int check_tile_params(const GsTileParams* p, const char* who) {
+  if (!p) { set_error("%s: null params", who); return GS_ERR_INVALID; }
+  if (p->tile_size <= 0 || p->image_width <= 0 || p->image_height <= 0 || p->num_points < 0) {
+    set_error("%s: bad sizes", who);
+    return GS_ERR_INVALID;
+  }
+  int64_t tw = ceil_div(p->image_width, p->tile_size), th = ceil_div(p->image_height, p->tile_size);
+  if (tw * th >= 65535) {  // mapper/tile_mapper.py:175-176
+    set_error("%s: %lld x %lld tiles exceed the 16 bit tile id, increase tile_size", who, (long long)th,
+              (long long)tw);
+    return GS_ERR_INVALID;
+  }
+  return GS_OK;
+}
+
+int gs_tile_count(const GsTileParams* p, const float* gaussians, int32_t* counts, void* stream) {
+  int rc = check_tile_params(p, "gs_tile_count");
+  if (rc != GS_OK) return rc;
+  if (p->num_points == 0) return GS_OK;
+  GS_CHECK_ARG(gaussians && counts, "gs_tile_count: null tensor");
+  int ts = p->tile_size;
+  int img_w = (int)ceil_div(p->image_width, ts) * ts, img_h = (int)ceil_div(p->image_height, ts) * ts;
+  int64_t blocks = ceil_div(p->num_points, kTileBlock);
+  tile_query_kernel<false, uint64_t><<<(unsigned)blocks, kTileBlock, 0, (cudaStream_t)stream>>>(
+      *p, img_w, img_h, gaussians, nullptr, nullptr, counts, nullptr, nullptr);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+int gs_tile_emit_keys(const GsTileParams* p, const float* gaussians, const float* depth, const int32_t* cum,
+                      void* keys, int32_t* values, void* stream) {
+  int rc = check_tile_params(p, "gs_tile_emit_keys");
+  if (rc != GS_OK) return rc;
+  if (p->num_points == 0) return GS_OK;
+  GS_CHECK_ARG(gaussians && depth && cum && keys && values, "gs_tile_emit_keys: null tensor");
+  int ts = p->tile_size;
+  int img_w = (int)ceil_div(p->image_width, ts) * ts, img_h = (int)ceil_div(p->image_height, ts) * ts;
+  int64_t blocks = ceil_div(p->num_points, kTileBlock);
+  if (p->use_depth16)
+    tile_query_kernel<true, uint32_t><<<(unsigned)blocks, kTileBlock, 0, (cudaStream_t)stream>>>(
+        *p, img_w, img_h, gaussians, depth, cum, nullptr, (uint32_t*)keys, values);
+  else
+    tile_query_kernel<true, uint64_t><<<(unsigned)blocks, kTileBlock, 0, (cudaStream_t)stream>>>(
+        *p, img_w, img_h, gaussians, depth, cum, nullptr, (uint64_t*)keys, values);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+int gs_find_ranges(const GsTileParams* p, int64_t num_overlaps, const void* sorted_keys, int32_t* tile_ranges,
+                   void* stream) {
+  int rc = check_tile_params(p, "gs_find_ranges");
+  if (rc != GS_OK) return rc;
+  GS_CHECK_ARG(tile_ranges != nullptr && num_overlaps >= 0, "gs_find_ranges: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t tiles = ceil_div(p->image_width, p->tile_size) * ceil_div(p->image_height, p->tile_size);
+  GS_CUDA(cudaMemsetAsync(tile_ranges, 0, (size_t)tiles * 2 * sizeof(int32_t), st));
+  if (num_overlaps == 0) return GS_OK;
+  GS_CHECK_ARG(sorted_keys != nullptr, "gs_find_ranges: null keys");
+  int64_t blocks = ceil_div(num_overlaps, 256);
+  if (p->use_depth16)
+    find_ranges_kernel<uint32_t, 16><<<(unsigned)blocks, 256, 0, st>>>(num_overlaps, (const uint32_t*)sorted_keys,
+                                                                      tile_ranges);
+  else
+    find_ranges_kernel<uint64_t, 32><<<(unsigned)blocks, 256, 0, st>>>(num_overlaps, (const uint64_t*)sorted_keys,
+                                                                      tile_ranges);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+// ---- host image of the device math, for CPU-side op-order checks against the oracle (tests only).
+// Not a compute path: evaluates ONE gaussian per call.
+int gs_selftest_project_one_f32(const float* pos, const float* ls, const float* q, float logit, const float* Tcw16,
+                                const float* proj4, int w, int h, double near_, double far_, double blur,
+                                double margin, double thr, float* out8, int* in_view) {
+  GsProjectParams p;
+  p.dtype = GS_F32; p.image_width = w; p.image_height = h; p.num_points = 1; p.near_plane = near_;
+  p.far_plane = far_; p.blur_cov = blur; p.clamp_margin = margin; p.alpha_threshold = thr;
+  CameraConst<float> C;
+  for (int i = 0; i < 12; ++i) C.Tcw[i] = Tcw16[i];
+  C.fx = proj4[0]; C.fy = proj4[1]; C.cx = proj4[2]; C.cy = proj4[3];
+  C.w = (float)w; C.h = (float)h; C.near_ = (float)near_; C.far_ = (float)far_; C.blur = (float)blur;
+  C.lo_x = (float)(-(double)w * margin); C.lo_y = (float)(-(double)h * margin);
+  C.hi_x = (float)(((double)w - 1.0) * (1.0 + margin)); C.hi_y = (float)(((double)h - 1.0) * (1.0 + margin));
+  C.alpha_threshold = (float)thr;
+  Projected<float> o = project_one<float>(pos, ls, q, logit, C);
+  out8[0] = o.mean_x; out8[1] = o.mean_y; out8[2] = o.axis_x; out8[3] = o.axis_y;
+  out8[4] = o.sigma_x; out8[5] = o.sigma_y; out8[6] = o.alpha; out8[7] = o.z;
+  *in_view = o.in_view ? 1 : 0;
+  return GS_OK;
+}
+
+// Overlapped tile ids of ONE gaussian in emission order; returns the count (tests only).
+int gs_selftest_tile_query(const float* g7, int img_w_padded, int img_h_padded, int ts, float thr, int32_t* tile_ids,
+                           int capacity) {
+  TileQuery qy = obb_query(g7[0], g7[1], g7[2], g7[3], g7[4], g7[5], g7[6], img_w_padded, img_h_padded, ts, thr);
+  int tiles_wide = img_w_padded / ts, n = 0;
+  for (int tu = 0; tu < qy.span_x; ++tu)
+    for (int tv = 0; tv < qy.span_y; ++tv)
+      if (test_tile(qy, tu, tv, ts)) {
+        if (tile_ids && n < capacity) tile_ids[n] = (tu + qy.min_x) + (tv + qy.min_y) * tiles_wide;
+        ++n;
+      }
+  return n;
+}
+
+}  // extern "C"

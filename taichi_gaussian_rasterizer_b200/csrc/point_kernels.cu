@@ -1,0 +1,465 @@
+// point_kernels.cu — per-gaussian kernels that are bound by HBM: spherical-harmonics forward /
+// backward and the hand-derived backward of the projection.
+//
+// Replaces (paths relative to /root/reference/taichi_splatting/):
+//   evaluate_sh_at_kernel and its Taichi-autodiff .grad      spherical_harmonics.py:118-134, :154-161
+//   indexed_project_kernel.grad (Taichi autodiff)             perspective/projection.py:83-118, :164-185
+// The reference obtains both backward passes from Taichi's reverse-mode autodiff; here they are
+// derived by hand (DESIGN.md §projection backward) and checked against torch autograd / gradcheck.
+#include "common.cuh"
+#include "geom_math.cuh"
+
+namespace gs {
+
+// ------------------------------------------------------------------------------------------------ SH
+template <typename T, int D>
+__device__ __forceinline__ void sh_basis(T x, T y, T z, T* o) {
+  o[0] = T(0.282094791773878);
+  if (D >= 4) {
+    o[1] = T(-0.48860251190292) * y;
+    o[2] = T(0.48860251190292) * z;
+    o[3] = T(-0.48860251190292) * x;
+  }
+  if (D >= 9) {
+    T x2 = x * x, y2 = y * y, z2 = z * z, xy = x * y, xz = x * z, yz = y * z;
+    o[4] = T(1.09254843059208) * xy;
+    o[5] = T(-1.09254843059208) * yz;
+    o[6] = T(0.94617469575756) * z2 - T(0.31539156525252);
+    o[7] = T(-1.09254843059208) * xz;
+    o[8] = T(0.54627421529604) * x2 - T(0.54627421529604) * y2;
+    if (D >= 16) {
+      o[9] = T(-0.590043589926644) * y * (T(3.0) * x2 - y2);
+      o[10] = T(2.89061144264055) * xy * z;
+      o[11] = T(0.304697199642977) * y * (T(1.5) - T(7.5) * z2);
+      o[12] = T(1.24392110863372) * z * (T(1.5) * z2 - T(0.5)) - T(0.497568443453487) * z;
+      o[13] = T(0.304697199642977) * x * (T(1.5) - T(7.5) * z2);
+      o[14] = T(1.44530572132028) * z * (x2 - y2);
+      o[15] = T(-0.590043589926644) * x * (x2 - T(3.0) * y2);
+    }
+  }
+}
+
+// d(basis_j)/d(x, y, z)
+template <typename T, int D>
+__device__ __forceinline__ void sh_basis_grad(T x, T y, T z, T* gx, T* gy, T* gz) {
+  const T c1 = T(0.48860251190292), c2 = T(1.09254843059208), c3 = T(0.94617469575756),
+          c5 = T(0.54627421529604), c6 = T(0.590043589926644), c7 = T(2.89061144264055),
+          c8 = T(0.304697199642977), c9 = T(1.24392110863372), c10 = T(0.497568443453487),
+          c11 = T(1.44530572132028);
+  gx[0] = gy[0] = gz[0] = T(0);
+  if (D >= 4) {
+    gx[1] = T(0); gy[1] = -c1; gz[1] = T(0);
+    gx[2] = T(0); gy[2] = T(0); gz[2] = c1;
+    gx[3] = -c1; gy[3] = T(0); gz[3] = T(0);
+  }
+  if (D >= 9) {
+    gx[4] = c2 * y; gy[4] = c2 * x; gz[4] = T(0);
+    gx[5] = T(0); gy[5] = -c2 * z; gz[5] = -c2 * y;
+    gx[6] = T(0); gy[6] = T(0); gz[6] = T(2) * c3 * z;
+    gx[7] = -c2 * z; gy[7] = T(0); gz[7] = -c2 * x;
+    gx[8] = T(2) * c5 * x; gy[8] = T(-2) * c5 * y; gz[8] = T(0);
+    if (D >= 16) {
+      T x2 = x * x, y2 = y * y, z2 = z * z;
+      gx[9] = T(-6) * c6 * x * y; gy[9] = -c6 * (T(3) * x2 - T(3) * y2); gz[9] = T(0);
+      gx[10] = c7 * y * z; gy[10] = c7 * x * z; gz[10] = c7 * x * y;
+      gx[11] = T(0); gy[11] = c8 * (T(1.5) - T(7.5) * z2); gz[11] = T(-15) * c8 * y * z;
+      gx[12] = T(0); gy[12] = T(0); gz[12] = c9 * (T(4.5) * z2 - T(0.5)) - c10;
+      gx[13] = c8 * (T(1.5) - T(7.5) * z2); gy[13] = T(0); gz[13] = T(-15) * c8 * x * z;
+      gx[14] = T(2) * c11 * x * z; gy[14] = T(-2) * c11 * y * z; gz[14] = c11 * (x2 - y2);
+      gx[15] = -c6 * (T(3) * x2 - T(3) * y2); gy[15] = T(6) * c6 * x * y; gz[15] = T(0);
+    }
+  }
+}
+
+template <typename T> __device__ __forceinline__ T rsqrt_(T x);
+template <> __device__ __forceinline__ float rsqrt_(float x) { return 1.0f / sqrtf(x); }
+template <> __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256)
+sh_fwd_kernel(const __grid_constant__ GsSHParams p, const T* __restrict__ params, const T* __restrict__ positions,
+              const int64_t* __restrict__ indexes, const T* __restrict__ cam, T* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.num_indexes) return;
+  const int64_t idx = indexes[i];
+  const int K = p.num_channels;
+  T dx = positions[3 * idx] - cam[0], dy = positions[3 * idx + 1] - cam[1], dz = positions[3 * idx + 2] - cam[2];
+  T inv = rsqrt_<T>(dx * dx + dy * dy + dz * dz);
+  T b[D];
+  sh_basis<T, D>(dx * inv, dy * inv, dz * inv, b);
+  const T* row = params + idx * K * D;
+  for (int k = 0; k < K; ++k) {
+    T acc = T(0);
+    if (D % 4 == 0 && sizeof(T) == 4) {
+      const float4* r4 = reinterpret_cast<const float4*>(row + k * D);
+#pragma unroll
+      for (int j = 0; j < D / 4; ++j) {
+        float4 v = __ldg(r4 + j);
+        acc += b[4 * j] * v.x + b[4 * j + 1] * v.y + b[4 * j + 2] * v.z + b[4 * j + 3] * v.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < D; ++j) acc += b[j] * row[k * D + j];
+    }
+    T v = acc + T(0.5);
+    out[i * K + k] = v < T(0) ? T(0) : (v > T(1) ? T(1) : v);
+  }
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256)
+sh_bwd_kernel(const __grid_constant__ GsSHParams p, const T* __restrict__ params, const T* __restrict__ positions,
+              const int64_t* __restrict__ indexes, const T* __restrict__ cam, const T* __restrict__ grad_out,
+              T* __restrict__ grad_params, T* __restrict__ grad_positions, T* __restrict__ grad_cam) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int K = p.num_channels;
+  T gpx = T(0), gpy = T(0), gpz = T(0);
+  if (i < p.num_indexes) {
+    const int64_t idx = indexes[i];
+    T dx = positions[3 * idx] - cam[0], dy = positions[3 * idx + 1] - cam[1], dz = positions[3 * idx + 2] - cam[2];
+    T inv = rsqrt_<T>(dx * dx + dy * dy + dz * dz);
+    T x = dx * inv, y = dy * inv, z = dz * inv;
+    T b[D];
+    sh_basis<T, D>(x, y, z, b);
+    T gb[D];  // d loss / d basis_j
+#pragma unroll
+    for (int j = 0; j < D; ++j) gb[j] = T(0);
+    const T* row = params + idx * K * D;
+    for (int k = 0; k < K; ++k) {
+      T acc = T(0);
+#pragma unroll
+      for (int j = 0; j < D; ++j) acc += b[j] * row[k * D + j];
+      T v = acc + T(0.5);
+      T g = (v > T(0) && v < T(1)) ? grad_out[i * K + k] : T(0);  // clamp passes gradient strictly inside
+      if (g != T(0)) {
+        if (grad_params) {
+          T* gr = grad_params + (idx * K + k) * D;
+#pragma unroll
+          for (int j = 0; j < D; ++j) red_add(gr + j, g * b[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j) gb[j] += g * row[k * D + j];
+      }
+    }
+    if (grad_positions || grad_cam) {
+      T gx[D], gy[D], gz[D];
+      sh_basis_grad<T, D>(x, y, z, gx, gy, gz);
+      T ddx = T(0), ddy = T(0), ddz = T(0);  // grad wrt the unit direction
+#pragma unroll
+      for (int j = 0; j < D; ++j) { ddx += gb[j] * gx[j]; ddy += gb[j] * gy[j]; ddz += gb[j] * gz[j]; }
+      T dot = ddx * x + ddy * y + ddz * z;  // through normalize: (I - d d^T) / |v|
+      gpx = (ddx - x * dot) * inv; gpy = (ddy - y * dot) * inv; gpz = (ddz - z * dot) * inv;
+      if (grad_positions) {
+        red_add(grad_positions + 3 * idx, gpx);
+        red_add(grad_positions + 3 * idx + 1, gpy);
+        red_add(grad_positions + 3 * idx + 2, gpz);
+      }
+    }
+  }
+  if (grad_cam) {  // camera position receives minus the sum of the point gradients
+    __shared__ T s_red[3][8];
+    T sx = warp_sum(gpx), sy = warp_sum(gpy), sz = warp_sum(gpz);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_red[0][warp] = sx; s_red[1][warp] = sy; s_red[2][warp] = sz; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      T t = T(0);
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[threadIdx.x][w];
+      if (t != T(0)) red_add(grad_cam + threadIdx.x, -t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ projection bwd
+constexpr int kPBwdBlock = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(kPBwdBlock)
+project_bwd_kernel(const __grid_constant__ GsProjectParams p, int64_t num_visible, const T* __restrict__ position,
+                   const T* __restrict__ log_scaling, const T* __restrict__ rotation,
+                   const T* __restrict__ alpha_logit, const T* __restrict__ Tcw, const T* __restrict__ proj,
+                   const int64_t* __restrict__ indexes, const T* __restrict__ grad_points,
+                   const T* __restrict__ grad_depth, T* __restrict__ g_position, T* __restrict__ g_log_scaling,
+                   T* __restrict__ g_rotation, T* __restrict__ g_alpha_logit, T* __restrict__ g_Tcw,
+                   T* __restrict__ g_proj) {
+  const int64_t i = (int64_t)blockIdx.x * kPBwdBlock + threadIdx.x;
+  CameraConst<T> C;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) C.Tcw[k] = Tcw[k];
+  C.fx = proj[0]; C.fy = proj[1]; C.cx = proj[2]; C.cy = proj[3];
+  C.w = T(p.image_width); C.h = T(p.image_height);
+  C.near_ = T(p.near_plane); C.far_ = T(p.far_plane); C.blur = T(p.blur_cov);
+  C.lo_x = T(-(double)p.image_width * p.clamp_margin);
+  C.lo_y = T(-(double)p.image_height * p.clamp_margin);
+  C.hi_x = T(((double)p.image_width - 1.0) * (1.0 + p.clamp_margin));
+  C.hi_y = T(((double)p.image_height - 1.0) * (1.0 + p.clamp_margin));
+  C.alpha_threshold = T(p.alpha_threshold);
+
+  T cam_grad[16];  // dW (3x3 in rows 0..2, cols 0..2), dt (col 3), then dfx dfy dcx dcy
+#pragma unroll
+  for (int k = 0; k < 16; ++k) cam_grad[k] = T(0);
+
+  if (i < num_visible) {
+    const int64_t idx = indexes[i];
+    T pos[3] = {position[3 * idx], position[3 * idx + 1], position[3 * idx + 2]};
+    T ls[3] = {log_scaling[3 * idx], log_scaling[3 * idx + 1], log_scaling[3 * idx + 2]};
+    T q[4] = {rotation[4 * idx], rotation[4 * idx + 1], rotation[4 * idx + 2], rotation[4 * idx + 3]};
+    ProjectState<T> S;
+    Projected<T> o = project_one<T>(pos, ls, q, alpha_logit[idx], C, &S);
+
+    const T* gp = grad_points + 7 * i;
+    const T d_mean_x = gp[0], d_mean_y = gp[1], d_axis_x = gp[2], d_axis_y = gp[3];
+    const T d_sig0 = gp[4], d_sig1 = gp[5], d_alpha = gp[6];
+    const T d_depth = grad_depth ? grad_depth[i] : T(0);
+
+    // 1. alpha = sigmoid(logit)
+    const T d_logit = d_alpha * o.alpha * (T(1) - o.alpha);
+    // 2. sigma = sqrt(lambda), axis = n / |n|, n = (a - l2, b)
+    T dl1 = d_sig0 / (T(2) * o.sigma_x);
+    T dl2 = d_sig1 / (T(2) * o.sigma_y);
+    T da = T(0), db = T(0), dc = T(0);
+    if (S.nn > T(0)) {
+      T dotv = o.axis_x * d_axis_x + o.axis_y * d_axis_y;
+      T dnx = (d_axis_x - o.axis_x * dotv) / S.nn;
+      T dny = (d_axis_y - o.axis_y * dotv) / S.nn;
+      da += dnx; dl2 -= dnx; db += dny;
+    }
+    // 3. eigenvalues of [[a, b], [b, c]]
+    T dtr = (dl1 + dl2) * T(0.5);
+    T dsg = (dl1 - dl2) * T(0.5);
+    T dgap = S.sg > T(0) ? dsg / (T(2) * S.sg) : T(0);
+    T tr = S.a + S.c;
+    dtr += T(2) * tr * dgap;
+    T ddet = T(-4) * dgap;
+    da += dtr + S.c * ddet;
+    dc += dtr + S.a * ddet;
+    db += T(-2) * S.b * ddet;
+    // 4. cov = M M^T (upper triangle read): dM = [[2da, db], [db, 2dc]] M
+    T dM[2][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      dM[0][j] = T(2) * da * S.m[0][j] + db * S.m[1][j];
+      dM[1][j] = db * S.m[0][j] + T(2) * dc * S.m[1][j];
+    }
+    // rebuild R, RS, J, B = W RS
+    const T x = S.q[0], y = S.q[1], z = S.q[2], w = S.q[3];
+    T R[3][3] = {{T(1) - T(2) * y * y - T(2) * z * z, T(2) * x * y - T(2) * w * z, T(2) * x * z + T(2) * w * y},
+                 {T(2) * x * y + T(2) * w * z, T(1) - T(2) * x * x - T(2) * z * z, T(2) * y * z - T(2) * w * x},
+                 {T(2) * x * z - T(2) * w * y, T(2) * y * z + T(2) * w * x, T(1) - T(2) * x * x - T(2) * y * y}};
+    const T zc = S.cam[2];
+    const T J00 = C.fx / zc, J02 = -(S.tu - C.cx) / zc, J11 = C.fy / zc, J12 = -(S.tv - C.cy) / zc;
+    T B[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        B[r][j] = (C.Tcw[r * 4 + 0] * R[0][j] + C.Tcw[r * 4 + 1] * R[1][j] + C.Tcw[r * 4 + 2] * R[2][j]) * S.s[j];
+    // 5. M = J B
+    T dJ00 = T(0), dJ02 = T(0), dJ11 = T(0), dJ12 = T(0);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      dJ00 += dM[0][j] * B[0][j]; dJ02 += dM[0][j] * B[2][j];
+      dJ11 += dM[1][j] * B[1][j]; dJ12 += dM[1][j] * B[2][j];
+    }
+    T dB[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      dB[0][j] = J00 * dM[0][j];
+      dB[1][j] = J11 * dM[1][j];
+      dB[2][j] = J02 * dM[0][j] + J12 * dM[1][j];
+    }
+    // B = W RS: dW += dB RS^T ; dRS = W^T dB
+    T dRS[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        cam_grad[r * 4 + j] += dB[r][0] * R[j][0] * S.s[0] + dB[r][1] * R[j][1] * S.s[1] + dB[r][2] * R[j][2] * S.s[2];
+        dRS[r][j] = C.Tcw[0 * 4 + r] * dB[0][j] + C.Tcw[1 * 4 + r] * dB[1][j] + C.Tcw[2 * 4 + r] * dB[2][j];
+      }
+    T d_ls[3], dR[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      T dsj = R[0][j] * dRS[0][j] + R[1][j] * dRS[1][j] + R[2][j] * dRS[2][j];
+      d_ls[j] = dsj * S.s[j];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) dR[r][j] = dRS[r][j] * S.s[j];
+    }
+    // 6. R(q_hat), q_hat = q / |q|
+    T dqx = dR[0][1] * T(2) * y + dR[0][2] * T(2) * z + dR[1][0] * T(2) * y - dR[1][1] * T(4) * x -
+            dR[1][2] * T(2) * w + dR[2][0] * T(2) * z + dR[2][1] * T(2) * w - dR[2][2] * T(4) * x;
+    T dqy = -dR[0][0] * T(4) * y + dR[0][1] * T(2) * x + dR[0][2] * T(2) * w + dR[1][0] * T(2) * x +
+            dR[1][2] * T(2) * z - dR[2][0] * T(2) * w + dR[2][1] * T(2) * z - dR[2][2] * T(4) * y;
+    T dqz = -dR[0][0] * T(4) * z - dR[0][1] * T(2) * w + dR[0][2] * T(2) * x + dR[1][0] * T(2) * w -
+            dR[1][1] * T(4) * z + dR[1][2] * T(2) * y + dR[2][0] * T(2) * x + dR[2][1] * T(2) * y;
+    T dqw = -dR[0][1] * T(2) * z + dR[0][2] * T(2) * y + dR[1][0] * T(2) * z - dR[1][2] * T(2) * x -
+            dR[2][0] * T(2) * y + dR[2][1] * T(2) * x;
+    T qd = x * dqx + y * dqy + z * dqz + w * dqw;
+    T d_rot[4] = {(dqx - x * qd) / S.qn, (dqy - y * qd) / S.qn, (dqz - z * qd) / S.qn, (dqw - w * qd) / S.qn};
+    // 7. jacobian entries
+    const T iz = T(1) / zc, iz2 = iz * iz;
+    T dfx = dJ00 * iz, dfy = dJ11 * iz;
+    T dz = (-(dJ00 * C.fx + dJ11 * C.fy) + dJ02 * (S.tu - C.cx) + dJ12 * (S.tv - C.cy)) * iz2;
+    T dtu = -dJ02 * iz, dtv = -dJ12 * iz;
+    T dcx = dJ02 * iz, dcy = dJ12 * iz;
+    // 8. clamp passes gradient strictly inside
+    T du = d_mean_x + ((S.u > C.lo_x && S.u < C.hi_x) ? dtu : T(0));
+    T dv = d_mean_y + ((S.v > C.lo_y && S.v < C.hi_y) ? dtv : T(0));
+    // 9. u = fx x / z + cx
+    const T xc = S.cam[0], yc = S.cam[1];
+    dfx += du * xc * iz; dcx += du;
+    dfy += dv * yc * iz; dcy += dv;
+    T dxc = du * C.fx * iz, dyc = dv * C.fy * iz;
+    dz += -(du * C.fx * xc + dv * C.fy * yc) * iz2 + d_depth;
+    // 10. cam = W p + t
+    T dcam[3] = {dxc, dyc, dz};
+    T d_pos[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      d_pos[j] = C.Tcw[0 * 4 + j] * dcam[0] + C.Tcw[1 * 4 + j] * dcam[1] + C.Tcw[2 * 4 + j] * dcam[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) cam_grad[r * 4 + j] += dcam[r] * pos[j];
+      cam_grad[r * 4 + 3] += dcam[r];
+    }
+    cam_grad[12] = dfx; cam_grad[13] = dfy; cam_grad[14] = dcx; cam_grad[15] = dcy;
+
+    if (g_position) { g_position[3 * idx] = d_pos[0]; g_position[3 * idx + 1] = d_pos[1]; g_position[3 * idx + 2] = d_pos[2]; }
+    if (g_log_scaling) { g_log_scaling[3 * idx] = d_ls[0]; g_log_scaling[3 * idx + 1] = d_ls[1]; g_log_scaling[3 * idx + 2] = d_ls[2]; }
+    if (g_rotation) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) g_rotation[4 * idx + k] = d_rot[k];
+    }
+    if (g_alpha_logit) g_alpha_logit[idx] = d_logit;
+  }
+
+  if (g_Tcw || g_proj) {  // camera gradients are summed over gaussians (expand backward, projection.py:212-213)
+    __shared__ T s_red[16][kPBwdBlock / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      T v = warp_sum(cam_grad[k]);
+      if (lane == 0) s_red[k][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      T t = T(0);
+#pragma unroll
+      for (int wi = 0; wi < kPBwdBlock / 32; ++wi) t += s_red[threadIdx.x][wi];
+      if (threadIdx.x < 12) { if (g_Tcw && t != T(0)) red_add(g_Tcw + threadIdx.x, t); }
+      else if (g_proj && t != T(0)) red_add(g_proj + (threadIdx.x - 12), t);
+    }
+  }
+}
+
+}  // namespace gs
+
+using namespace gs;
+
+template <typename T>
+static int sh_dispatch(bool backward, const GsSHParams* p, const void* params, const void* positions,
+                       const int64_t* indexes, const void* cam, const void* grad_out, void* out_or_gparams,
+                       void* gpos, void* gcam, cudaStream_t st) {
+  const int64_t blocks = ceil_div(p->num_indexes, 256);
+#define GS_SH_CASE(DD)                                                                                              \
+  case DD:                                                                                                          \
+    if (!backward)                                                                                                  \
+      sh_fwd_kernel<T, DD><<<(unsigned)blocks, 256, 0, st>>>(*p, (const T*)params, (const T*)positions, indexes,    \
+                                                             (const T*)cam, (T*)out_or_gparams);                    \
+    else                                                                                                            \
+      sh_bwd_kernel<T, DD><<<(unsigned)blocks, 256, 0, st>>>(*p, (const T*)params, (const T*)positions, indexes,    \
+                                                             (const T*)cam, (const T*)grad_out, (T*)out_or_gparams, \
+                                                             (T*)gpos, (T*)gcam);                                   \
+    break;
+  switch (p->num_coeffs) {
+    GS_SH_CASE(1)
+    GS_SH_CASE(4)
+    GS_SH_CASE(9)
+    GS_SH_CASE(16)
+    default:
+      GS_UNSUPPORTED("spherical harmonics: %d coefficients (degree must be 0..3)", p->num_coeffs);
+  }
+#undef GS_SH_CASE
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+static int check_sh(const GsSHParams* p, const char* who) {
+  if (!p) { set_error("%s: null params", who); return GS_ERR_INVALID; }
+  if (p->dtype != GS_F32 && p->dtype != GS_F64) { set_error("%s: bad dtype", who); return GS_ERR_INVALID; }
+  if (p->num_channels <= 0 || p->num_points < 0 || p->num_indexes < 0) { set_error("%s: bad sizes", who); return GS_ERR_INVALID; }
+  return GS_OK;
+}
+
+extern "C" {
+
+int gs_sh_fwd(const GsSHParams* p, const void* params, const void* positions, const int64_t* indexes,
+              const void* camera_pos, void* out, void* stream) {
+  int rc = check_sh(p, "gs_sh_fwd");
+  if (rc != GS_OK) return rc;
+  if (p->num_indexes == 0) return GS_OK;
+  GS_CHECK_ARG(params && positions && indexes && camera_pos && out, "gs_sh_fwd: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  return p->dtype == GS_F32
+             ? sh_dispatch<float>(false, p, params, positions, indexes, camera_pos, nullptr, out, nullptr, nullptr, st)
+             : sh_dispatch<double>(false, p, params, positions, indexes, camera_pos, nullptr, out, nullptr, nullptr, st);
+}
+
+int gs_sh_bwd(const GsSHParams* p, const void* params, const void* positions, const int64_t* indexes,
+              const void* camera_pos, const void* grad_out, void* grad_params, void* grad_positions,
+              void* grad_camera_pos, void* stream) {
+  int rc = check_sh(p, "gs_sh_bwd");
+  if (rc != GS_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t es = p->dtype == GS_F32 ? 4 : 8;
+  if (grad_params)
+    GS_CUDA(cudaMemsetAsync(grad_params, 0, (size_t)p->num_points * p->num_channels * p->num_coeffs * es, st));
+  if (grad_positions) GS_CUDA(cudaMemsetAsync(grad_positions, 0, (size_t)p->num_points * 3 * es, st));
+  if (grad_camera_pos) GS_CUDA(cudaMemsetAsync(grad_camera_pos, 0, 3 * es, st));
+  if (p->num_indexes == 0) return GS_OK;
+  GS_CHECK_ARG(params && positions && indexes && camera_pos && grad_out, "gs_sh_bwd: null tensor");
+  return p->dtype == GS_F32 ? sh_dispatch<float>(true, p, params, positions, indexes, camera_pos, grad_out,
+                                                 grad_params, grad_positions, grad_camera_pos, st)
+                            : sh_dispatch<double>(true, p, params, positions, indexes, camera_pos, grad_out,
+                                                  grad_params, grad_positions, grad_camera_pos, st);
+}
+
+int gs_project_bwd(const GsProjectParams* p, int64_t num_visible, const void* position, const void* log_scaling,
+                   const void* rotation, const void* alpha_logit, const void* T_camera_world, const void* projection,
+                   const int64_t* indexes, const void* grad_points, const void* grad_depth, void* grad_position,
+                   void* grad_log_scaling, void* grad_rotation, void* grad_alpha_logit, void* grad_T_camera_world,
+                   void* grad_projection, void* stream) {
+  GS_CHECK_ARG(p != nullptr, "gs_project_bwd: null params");
+  GS_CHECK_ARG(p->dtype == GS_F32 || p->dtype == GS_F64, "gs_project_bwd: bad dtype");
+  GS_CHECK_ARG(num_visible >= 0 && num_visible <= p->num_points, "gs_project_bwd: bad num_visible");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t es = p->dtype == GS_F32 ? 4 : 8;
+  const size_t n = (size_t)p->num_points;
+  if (grad_position) GS_CUDA(cudaMemsetAsync(grad_position, 0, n * 3 * es, st));
+  if (grad_log_scaling) GS_CUDA(cudaMemsetAsync(grad_log_scaling, 0, n * 3 * es, st));
+  if (grad_rotation) GS_CUDA(cudaMemsetAsync(grad_rotation, 0, n * 4 * es, st));
+  if (grad_alpha_logit) GS_CUDA(cudaMemsetAsync(grad_alpha_logit, 0, n * es, st));
+  if (grad_T_camera_world) GS_CUDA(cudaMemsetAsync(grad_T_camera_world, 0, 16 * es, st));
+  if (grad_projection) GS_CUDA(cudaMemsetAsync(grad_projection, 0, 4 * es, st));
+  if (num_visible == 0) return GS_OK;
+  GS_CHECK_ARG(position && log_scaling && rotation && alpha_logit && T_camera_world && projection && indexes &&
+                   grad_points, "gs_project_bwd: null tensor");
+  const int64_t blocks = ceil_div(num_visible, kPBwdBlock);
+  if (p->dtype == GS_F32)
+    project_bwd_kernel<float><<<(unsigned)blocks, kPBwdBlock, 0, st>>>(
+        *p, num_visible, (const float*)position, (const float*)log_scaling, (const float*)rotation,
+        (const float*)alpha_logit, (const float*)T_camera_world, (const float*)projection, indexes,
+        (const float*)grad_points, (const float*)grad_depth, (float*)grad_position, (float*)grad_log_scaling,
+        (float*)grad_rotation, (float*)grad_alpha_logit, (float*)grad_T_camera_world, (float*)grad_projection);
+  else
+    project_bwd_kernel<double><<<(unsigned)blocks, kPBwdBlock, 0, st>>>(
+        *p, num_visible, (const double*)position, (const double*)log_scaling, (const double*)rotation,
+        (const double*)alpha_logit, (const double*)T_camera_world, (const double*)projection, indexes,
+        (const double*)grad_points, (const double*)grad_depth, (double*)grad_position, (double*)grad_log_scaling,
+        (double*)grad_rotation, (double*)grad_alpha_logit, (double*)grad_T_camera_world, (double*)grad_projection);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+}  // extern "C"

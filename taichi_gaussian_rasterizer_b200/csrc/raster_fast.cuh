@@ -1,0 +1,77 @@
+// raster_fast.cuh — shared pieces of the fast (f32, alpha blending, tile 16) rasterizer kernels:
+// packed per-gaussian records, cp.async staging, the lane-parallel ellipse / pixel-block cull test.
+#pragma once
+
+#include "raster.cuh"
+
+namespace gs {
+
+constexpr int kFastTile = 16;
+constexpr int kFastTileArea = kFastTile * kFastTile;
+
+// padded feature row length used by the fast kernels for a given F (0 = unsupported)
+inline int fast_feature_pad(int F) { return F <= 4 ? 4 : (F <= 8 ? 8 : 0); }
+
+// Workspace layout (all 256 B aligned):
+//   recF  V x 2 float4 : {mx, my, a1x, a1y} {a2x, a2y, log2(alpha), idx}       (forward records)
+//   featP V x FP float  : features padded to FP
+//   recB  V x 2 float4 : {mx, my, ax, ay} {1/sx, 1/sy, alpha, idx}             (backward records)
+struct FastLayout {
+  size_t off_recF, off_feat, off_recB, total;
+  int FP;
+};
+
+inline FastLayout fast_layout(const GsRasterParams& p) {
+  FastLayout L;
+  L.FP = fast_feature_pad(p.num_features);
+  const size_t V = (size_t)(p.num_points > 0 ? p.num_points : 1);
+  size_t off = 0;
+  L.off_recF = off; off += align_up(V * 32, 256);
+  L.off_feat = off; off += align_up(V * (size_t)L.FP * 4, 256);
+  L.off_recB = off; off += align_up(V * 32, 256);
+  L.total = off;
+  return L;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// exp(-0.5 (tx^2 + ty^2)) == exp2(-(c tx)^2 - (c ty)^2) with c = sqrt(0.5 log2(e))
+constexpr float kSqrtHalfLog2e = 0.8493218002880191f;
+constexpr float kHalfLog2e = 0.7213475204444817f;
+
+// Conservative test: can gaussian (conic A of the scaled axes, exponent budget qmax) reach any pixel centre
+// of the block [x0, x1] x [y0, y1]?  Minimises the quadratic form over the rectangle exactly (interior, or the
+// clamped 1-D minimum on each edge facing the mean) and adds slack for rounding; the per pixel test stays exact.
+__device__ __forceinline__ bool block_may_touch(float mx, float my, float a1x, float a1y, float a2x, float a2y,
+                                                float qmax, float x0, float x1, float y0, float y1) {
+  const float dx0 = x0 - mx, dx1 = x1 - mx, dy0 = y0 - my, dy1 = y1 - my;
+  const float dxc = fminf(fmaxf(0.f, dx0), dx1);
+  const float dyc = fminf(fmaxf(0.f, dy0), dy1);
+  const float A00 = a1x * a1x + a2x * a2x, A01 = a1x * a1y + a2x * a2y, A11 = a1y * a1y + a2y * a2y;
+  const float dyv = fminf(fmaxf(__fdividef(-A01 * dxc, A11), dy0), dy1);
+  const float qv = A00 * dxc * dxc + 2.f * A01 * dxc * dyv + A11 * dyv * dyv;
+  const float dxh = fminf(fmaxf(__fdividef(-A01 * dyc, A00), dx0), dx1);
+  const float qh = A00 * dxh * dxh + 2.f * A01 * dxh * dyc + A11 * dyc * dyc;
+  return fminf(qv, qh) < qmax * 1.001f + 1e-3f;
+}
+
+int raster_fast_pack(const GsRasterParams& p, const RasterArgs& a, bool forward, bool features, cudaStream_t st);
+
+}  // namespace gs

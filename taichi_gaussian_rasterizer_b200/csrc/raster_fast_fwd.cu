@@ -1,0 +1,223 @@
+// raster_fast_fwd.cu — forward rasterizer, f32 / alpha blending / tile 16 (the measured path).
+//
+// Replaces rasterizer/forward.py:24-137 of /root/reference/taichi_splatting/.  Same per pixel arithmetic
+// (front-to-back blend in depth order, weight = alpha (1 - W), alpha = min(alpha0 p, clamp) tested against
+// alpha_threshold), different machine mapping:
+//   * one CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel block (one pixel per lane);
+//   * the tile's sorted gaussians are staged in batches of 128 through shared memory with cp.async
+//     (16 B gathers of pre-packed 32 B records + padded feature rows), double buffered;
+//   * per batch each warp first tests 32 gaussians at a time, one per lane, against ITS pixel block
+//     (exact minimum of the ellipse's quadratic form over the block) and then only walks the survivors
+//     (ballot mask) — a gaussian that cannot pass alpha_threshold anywhere in the block contributes
+//     exactly nothing, so results do not change, but most (warp, gaussian) pairs of a tile list vanish;
+//   * exp via ex2.approx on a pre-scaled exponent (alpha = 2^(log2 alpha0 - |M d|^2));
+//   * a warp stops when every lane's transmittance is <= forward_exit_transmittance (0 = exact: no
+//     later term can change anything); the CTA stops when all warps have;
+//   * the reference's stale-slot re-read (forward.py:88) is reproduced, when requested, by
+//     re-walking entries [C-256, (G-1) 256) after the C real ones with visibility recording off.
+#include "raster_fast.cuh"
+
+namespace gs {
+
+constexpr int kFwdBatch = 128;
+constexpr int kFwdThreads = 256;
+
+// ------------------------------------------------------------------------------------------------ pack
+template <int FP>
+__global__ void __launch_bounds__(256)
+raster_pack_kernel(int64_t V, int F, const float* __restrict__ g, const float* __restrict__ feat,
+                   float4* __restrict__ recF, float* __restrict__ featP, float4* __restrict__ recB) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const float* gi = g + 7 * i;
+  const float mx = gi[0], my = gi[1], ax = gi[2], ay = gi[3], sx = gi[4], sy = gi[5], alpha = gi[6];
+  const float isx = 1.0f / sx, isy = 1.0f / sy;
+  if (recF) {
+    const float cx = kSqrtHalfLog2e * isx, cy = kSqrtHalfLog2e * isy;
+    recF[2 * i] = make_float4(mx, my, ax * cx, ay * cx);
+    recF[2 * i + 1] = make_float4(-ay * cy, ax * cy, log2f(alpha), __int_as_float((int)i));
+  }
+  if (recB) {
+    recB[2 * i] = make_float4(mx, my, ax, ay);
+    recB[2 * i + 1] = make_float4(isx, isy, alpha, __int_as_float((int)i));
+  }
+  if (featP) {
+    float f[FP];
+#pragma unroll
+    for (int c = 0; c < FP; ++c) f[c] = c < F ? feat[i * F + c] : 0.f;
+#pragma unroll
+    for (int c = 0; c < FP; c += 4)
+      *reinterpret_cast<float4*>(featP + i * FP + c) = make_float4(f[c], f[c + 1], f[c + 2], f[c + 3]);
+  }
+}
+
+int raster_fast_pack(const GsRasterParams& p, const RasterArgs& a, bool forward, bool features, cudaStream_t st) {
+  if (p.num_points == 0) return GS_OK;
+  const FastLayout L = fast_layout(p);
+  unsigned char* ws = (unsigned char*)a.workspace;
+  float4* recF = forward ? (float4*)(ws + L.off_recF) : nullptr;
+  float4* recB = forward ? nullptr : (float4*)(ws + L.off_recB);
+  float* featP = features ? (float*)(ws + L.off_feat) : nullptr;
+  const int64_t blocks = ceil_div(p.num_points, 256);
+  if (L.FP == 4)
+    raster_pack_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(p.num_points, p.num_features, (const float*)a.gaussians2d,
+                                                           (const float*)a.features, recF, featP, recB);
+  else
+    raster_pack_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(p.num_points, p.num_features, (const float*)a.gaussians2d,
+                                                           (const float*)a.features, recF, featP, recB);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int FP, bool VIS>
+__global__ void __launch_bounds__(kFwdThreads)
+raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
+                       const float* __restrict__ featP, const int32_t* __restrict__ ranges,
+                       const int32_t* __restrict__ o2p, float* __restrict__ image, float* __restrict__ image_alpha,
+                       float* __restrict__ visibility) {
+  __shared__ __align__(16) float4 s_r0[2][kFwdBatch];
+  __shared__ __align__(16) float4 s_r1[2][kFwdBatch];
+  __shared__ __align__(16) float s_feat[2][kFwdBatch][FP];
+  __shared__ float s_vis[2][kFwdBatch];
+
+  const int tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int tw = (p.image_width + kFastTile - 1) / kFastTile;
+  const int F = p.num_features;
+  const int wx0 = (tile % tw) * kFastTile + (warp & 1) * 8;
+  const int wy0 = (tile / tw) * kFastTile + (warp >> 1) * 4;
+  const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
+  const bool inb = px < p.image_width && py < p.image_height;
+  const float pxf = (float)px + 0.5f, pyf = (float)py + 0.5f;
+  const float bx0 = (float)wx0 + 0.5f, bx1 = (float)wx0 + 7.5f, by0 = (float)wy0 + 0.5f, by1 = (float)wy0 + 3.5f;
+  const float thr = (float)p.alpha_threshold, cmax = (float)p.clamp_max_alpha;
+  const float l2thr = log2f(thr);
+  const float exit_T = (float)p.forward_exit_transmittance;
+
+  float acc[FP];
+#pragma unroll
+  for (int c = 0; c < FP; ++c) acc[c] = 0.f;
+  float W = inb ? 0.f : 1.f;
+
+  const int start = ranges[2 * tile], end = ranges[2 * tile + 1];
+  const int C = end - start;
+  const int G = (C + kFastTileArea - 1) / kFastTileArea;
+  const int extra = (p.emulate_stale_tail && G > 1) ? (G * kFastTileArea - C) : 0;  // stale slots re-read (Q1)
+  const int total = C + extra;
+  const int nb = (total + kFwdBatch - 1) / kFwdBatch;
+
+  auto issue_load = [&](int b) {
+    const int buf = b & 1;
+    const int slot = t & (kFwdBatch - 1);
+    const int v = b * kFwdBatch + slot;
+    if (v < total) {
+      const int k = v < C ? v : v - kFastTileArea;
+      const int idx = o2p[start + k];
+      if (t < kFwdBatch) {
+        cp_async16(&s_r0[buf][slot], rec + 2 * (int64_t)idx);
+        cp_async16(&s_r1[buf][slot], rec + 2 * (int64_t)idx + 1);
+        if (VIS) s_vis[buf][slot] = 0.f;
+      } else {
+#pragma unroll
+        for (int c = 0; c < FP; c += 4) cp_async16(&s_feat[buf][slot][c], featP + (int64_t)idx * FP + c);
+      }
+    }
+    cp_async_commit();
+  };
+
+  bool warp_done = __all_sync(kFull, (1.f - W) <= exit_T);
+  if (nb > 0) issue_load(0);
+  for (int b = 0; b < nb; ++b) {
+    const int buf = b & 1;
+    if (b + 1 < nb) {
+      issue_load(b + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int vbase = b * kFwdBatch;
+    const int n_in = min(kFwdBatch, total - vbase);
+    if (!warp_done) {
+      for (int c0 = 0; c0 < n_in; c0 += 32) {
+        const int e = c0 + lane;
+        bool hit = false;
+        if (e < n_in) {
+          const float4 r0 = s_r0[buf][e], r1 = s_r1[buf][e];
+          hit = block_may_touch(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z - l2thr, bx0, bx1, by0, by1);
+        }
+        unsigned mask = __ballot_sync(kFull, hit);
+        while (mask) {
+          const int j = c0 + __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float4 r0 = s_r0[buf][j], r1 = s_r1[buf][j];
+          const float dx = pxf - r0.x, dy = pyf - r0.y;
+          const float tx = fmaf(dy, r0.w, dx * r0.z);
+          const float ty = fmaf(dy, r1.y, dx * r1.x);
+          const float ex = fmaf(-ty, ty, fmaf(-tx, tx, r1.z));
+          float alpha = fminf(fast_ex2(ex), cmax);
+          float weight = 0.f;
+          if (alpha > thr) {
+            weight = alpha * (1.f - W);
+            W += weight;
+#pragma unroll
+            for (int c = 0; c < FP; ++c) acc[c] = fmaf(s_feat[buf][j][c], weight, acc[c]);
+          }
+          if (VIS) {
+            if (vbase + j < C && __any_sync(kFull, weight > 0.f)) {
+              const float v = warp_sum(weight);
+              if (lane == 0) atomicAdd(&s_vis[buf][j], v);
+            }
+          }
+        }
+      }
+      warp_done = __all_sync(kFull, (1.f - W) <= exit_T);
+    }
+    const bool all_done = __syncthreads_and(warp_done);
+    if (VIS) {
+      if (t < n_in && vbase + t < C) {
+        const float v = s_vis[buf][t];
+        if (v != 0.f) atomicAdd(visibility + __float_as_int(s_r1[buf][t].w), v);
+      }
+    }
+    if (all_done) break;
+  }
+  cp_async_wait<0>();
+
+  if (inb) {
+    const int64_t pix = (int64_t)py * p.image_width + px;
+#pragma unroll
+    for (int c = 0; c < FP; ++c)
+      if (c < F) image[pix * F + c] = acc[c];
+    image_alpha[pix] = W;
+  }
+}
+
+bool raster_fast_supported(const GsRasterParams& p) {
+  return p.dtype == GS_F32 && p.tile_size == kFastTile && !p.antialias && p.use_alpha_blending &&
+         fast_feature_pad(p.num_features) != 0 && p.num_points < (1ll << 31);
+}
+
+size_t raster_fast_workspace_bytes(const GsRasterParams& p) { return fast_layout(p).total; }
+
+int raster_fwd_fast(const GsRasterParams& p, const RasterArgs& a, cudaStream_t st) {
+  int rc = raster_fast_pack(p, a, /*forward=*/true, /*features=*/true, st);
+  if (rc != GS_OK) return rc;
+  const FastLayout L = fast_layout(p);
+  unsigned char* ws = (unsigned char*)a.workspace;
+  const float4* rec = (const float4*)(ws + L.off_recF);
+  const float* featP = (const float*)(ws + L.off_feat);
+  const int tiles = tiles_wide(p) * tiles_high(p);
+  const bool vis = p.compute_visibility && a.visibility != nullptr;
+#define GS_FWD_LAUNCH(FPV, VISV)                                                                             \
+  raster_fwd_fast_kernel<FPV, VISV><<<tiles, kFwdThreads, 0, st>>>(p, rec, featP, a.tile_ranges,             \
+                                                                   a.overlap_to_point, (float*)a.image,      \
+                                                                   (float*)a.image_alpha, (float*)a.visibility)
+  if (L.FP == 4) { if (vis) GS_FWD_LAUNCH(4, true); else GS_FWD_LAUNCH(4, false); }
+  else { if (vis) GS_FWD_LAUNCH(8, true); else GS_FWD_LAUNCH(8, false); }
+#undef GS_FWD_LAUNCH
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+}  // namespace gs

@@ -1,0 +1,390 @@
+// scan_sort.cu — full_cumsum (single-pass chained scan) and a stable onesweep LSD radix sort of
+// (key, int32 value) pairs.
+//
+// Replaces the reference's CUB wrappers (paths relative to /root/reference/taichi_splatting/):
+//   cuda_lib/full_cumsum.cu:16-67        cub::DeviceScan::ExclusiveSum + complete_cumsum + device sync
+//   cuda_lib/radix_sort_pairs.cu:9-69    cub::DeviceRadixSort::SortPairs + device sync
+// Both are integer / byte work bound by HBM: scan moves 8 B per element, the sort 8 B per key for the
+// histogram plus (2*key + 2*4) B per key per 8-bit pass.  No host synchronisation happens here.
+#include "common.cuh"
+#include "lookback.cuh"
+
+namespace gs {
+
+// ------------------------------------------------------------------------------------------------ scan
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanBlock * kScanItems;
+
+template <typename T>
+__global__ void __launch_bounds__(kScanBlock)
+full_cumsum_kernel(int64_t n, const T* __restrict__ in, T* __restrict__ out, unsigned long long* status,
+                   unsigned int* ticket) {
+  __shared__ int s_tile;
+  __shared__ unsigned long long s_warp_total[kScanBlock / 32];
+  __shared__ unsigned long long s_prefix;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t base = (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
+
+  T v[kScanItems];
+  unsigned long long thread_sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : T(0);
+    thread_sum += (unsigned long long)v[k];
+  }
+  unsigned long long incl = thread_sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp_total[warp] = incl;
+  __syncthreads();
+  unsigned long long warp_offset = 0, block_total = 0;
+#pragma unroll
+  for (int wi = 0; wi < kScanBlock / 32; ++wi) {
+    unsigned long long c = s_warp_total[wi];
+    if (wi < warp) warp_offset += c;
+    block_total += c;
+  }
+  if (warp == 0) {
+    unsigned long long ex = lookback_exclusive(status, tile, block_total);
+    if (lane == 0) {
+      s_prefix = ex;
+      if (tile == (int)gridDim.x - 1) out[n] = (T)(ex + block_total);
+    }
+  }
+  __syncthreads();
+  unsigned long long run = s_prefix + warp_offset + (incl - thread_sum);
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < n) out[base + k] = (T)run;
+    run += (unsigned long long)v[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ radix sort
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kSortBlock = 256;  // == kRadix: thread t owns digit t in the per-digit phases
+constexpr int kSortWarps = kSortBlock / 32;
+constexpr int kMaxPasses = 8;
+constexpr unsigned kSortFlagAgg = 1u << 30, kSortFlagPrefix = 2u << 30, kSortValueMask = (1u << 30) - 1u;
+
+template <typename KeyT> struct SortCfg;
+template <> struct SortCfg<uint32_t> { static constexpr int kItems = 22; };
+template <> struct SortCfg<uint64_t> { static constexpr int kItems = 16; };
+
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Digit histograms of every pass in one sweep over the keys (8 B/key of HBM traffic).
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+radix_histogram_kernel(int64_t n, const KeyT* __restrict__ keys, int begin_bit, int end_bit, int passes,
+                       unsigned* __restrict__ global_hist) {
+  __shared__ unsigned h[kMaxPasses * kRadix];
+  for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const KeyT k = keys[i];
+#pragma unroll 1
+    for (int p = 0; p < passes; ++p) {
+      const int shift = begin_bit + p * kRadixBits;
+      const int nb = min(kRadixBits, end_bit - shift);
+      atomicAdd(&h[p * kRadix + (unsigned)((k >> shift) & (KeyT)((1u << nb) - 1u))], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x)
+    if (h[i]) atomicAdd(&global_hist[i], h[i]);
+}
+
+// In-place exclusive scan of each pass's 256 bins.  grid = passes, block = 256.
+__global__ void radix_histogram_scan_kernel(unsigned* __restrict__ global_hist) {
+  __shared__ unsigned s_warp[kSortWarps];
+  unsigned* h = global_hist + blockIdx.x * kRadix;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned c = h[threadIdx.x];
+  unsigned incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  unsigned off = 0;
+  for (int wi = 0; wi < warp; ++wi) off += s_warp[wi];
+  h[threadIdx.x] = off + incl - c;
+}
+
+// One onesweep pass: rank keys of a tile by the current digit (warp match-any multi-split + per-warp
+// shared histograms), chain the per-digit tile counts through decoupled look-back, reorder the tile in
+// shared memory and write digit runs back coalesced.  Stable: ranks follow input order.
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortBlock)
+onesweep_pass_kernel(int64_t n, const KeyT* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
+                     KeyT* __restrict__ keys_out, int32_t* __restrict__ vals_out, int shift, unsigned mask,
+                     const unsigned* __restrict__ global_excl, unsigned* __restrict__ status,
+                     unsigned* __restrict__ ticket) {
+  constexpr int ITEMS = SortCfg<KeyT>::kItems;
+  constexpr int TILE = kSortBlock * ITEMS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
+  int32_t* s_vals = reinterpret_cast<int32_t*>(s_keys + TILE);
+  unsigned* s_warp_hist = reinterpret_cast<unsigned*>(s_vals + TILE);  // [kSortWarps][kRadix]
+  unsigned* s_digit_off = s_warp_hist + kSortWarps * kRadix;           // [kRadix] exclusive offset in tile
+  unsigned* s_global = s_digit_off + kRadix;                           // [kRadix] global base of the digit
+  __shared__ int s_tile;
+  __shared__ unsigned s_scan_warp[kSortWarps];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  for (int i = tid; i < kSortWarps * kRadix; i += kSortBlock) s_warp_hist[i] = 0;
+  __syncthreads();
+  const int tile = s_tile;
+  const int64_t tile_base = (int64_t)tile * TILE;
+  const int valid = (int)min((int64_t)TILE, n - tile_base);
+  const int64_t warp_base = tile_base + (int64_t)warp * (32 * ITEMS);
+
+  KeyT key[ITEMS];
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int64_t idx = warp_base + k * 32 + lane;
+    key[k] = idx < n ? keys_in[idx] : ~KeyT(0);
+  }
+
+  unsigned rank[ITEMS];
+  unsigned* my_hist = s_warp_hist + warp * kRadix;
+  const unsigned lanemask_le = 0xffffffffu >> (31 - lane);
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const unsigned d = (unsigned)(key[k] >> shift) & mask;
+    const unsigned peers = __match_any_sync(kFull, d);
+    const int leader = 31 - __clz(peers);
+    const unsigned cnt_le = __popc(peers & lanemask_le);
+    unsigned old = 0;
+    if (lane == leader) {
+      old = my_hist[d];
+      my_hist[d] = old + cnt_le;
+    }
+    __syncwarp();
+    old = __shfl_sync(kFull, old, leader);
+    rank[k] = old + cnt_le - 1u;
+  }
+  __syncthreads();
+
+  // thread tid owns digit tid: exclusive scan of the warp histograms, then the tile count look-back
+  unsigned tile_count = 0;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; ++w) {
+    const unsigned c = s_warp_hist[w * kRadix + tid];
+    s_warp_hist[w * kRadix + tid] = tile_count;
+    tile_count += c;
+  }
+  {
+    unsigned* st = status + (size_t)tile * kRadix + tid;
+    unsigned exclusive = 0;
+    if (tile == 0) {
+      st_relaxed_u32(st, kSortFlagPrefix | tile_count);
+    } else {
+      st_relaxed_u32(st, kSortFlagAgg | tile_count);
+      int j = tile - 1;
+      while (true) {
+        const unsigned v = ld_relaxed_u32(status + (size_t)j * kRadix + tid);
+        if ((v >> 30) == 0u) continue;
+        exclusive += v & kSortValueMask;
+        if ((v >> 30) == 2u) break;
+        --j;
+      }
+      st_relaxed_u32(st, kSortFlagPrefix | ((exclusive + tile_count) & kSortValueMask));
+    }
+    s_global[tid] = global_excl[tid] + exclusive;
+  }
+  // exclusive scan of tile_count over the 256 digits
+  {
+    unsigned incl = tile_count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_scan_warp[warp] = incl;
+    __syncthreads();
+    unsigned off = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w)
+      if (w < warp) off += s_scan_warp[w];
+    s_digit_off[tid] = off + incl - tile_count;
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const unsigned d = (unsigned)(key[k] >> shift) & mask;
+    const unsigned pos = s_digit_off[d] + my_hist[d] + rank[k];
+    const int64_t idx = warp_base + k * 32 + lane;
+    s_keys[pos] = key[k];
+    s_vals[pos] = idx < n ? vals_in[idx] : 0;
+  }
+  __syncthreads();
+
+  for (int i = tid; i < valid; i += kSortBlock) {
+    const KeyT k = s_keys[i];
+    const unsigned d = (unsigned)(k >> shift) & mask;
+    const int64_t dst = (int64_t)s_global[d] + (i - (int)s_digit_off[d]);
+    keys_out[dst] = k;
+    vals_out[dst] = s_vals[i];
+  }
+}
+
+template <typename KeyT>
+static size_t sort_smem_bytes() {
+  constexpr int TILE = kSortBlock * SortCfg<KeyT>::kItems;
+  return (size_t)TILE * (sizeof(KeyT) + sizeof(int32_t)) + (size_t)(kSortWarps + 2) * kRadix * sizeof(unsigned);
+}
+
+struct SortLayout {
+  int passes;
+  int64_t tiles;
+  size_t off_hist, off_ticket, off_status, off_tmp_keys, off_tmp_vals, total, zero_bytes;
+};
+
+static SortLayout sort_layout(int64_t n, int key_bytes, int begin_bit, int end_bit) {
+  SortLayout L;
+  L.passes = (int)ceil_div(end_bit - begin_bit, kRadixBits);
+  int items = key_bytes == 8 ? SortCfg<uint64_t>::kItems : SortCfg<uint32_t>::kItems;
+  L.tiles = ceil_div(n > 0 ? n : 1, (int64_t)kSortBlock * items);
+  size_t off = 0;
+  L.off_hist = off; off += (size_t)kMaxPasses * kRadix * sizeof(unsigned);
+  L.off_ticket = off; off += 64;
+  L.off_status = off; off += (size_t)L.passes * L.tiles * kRadix * sizeof(unsigned);
+  L.zero_bytes = off;  // everything up to here must be zero before the first kernel
+  off = align_up(off, 256);
+  L.off_tmp_keys = off; off += align_up((size_t)n * key_bytes, 256);
+  L.off_tmp_vals = off; off += align_up((size_t)n * sizeof(int32_t), 256);
+  L.total = off;
+  return L;
+}
+
+template <typename KeyT>
+static int radix_sort_impl(int64_t n, const KeyT* keys_in, const int32_t* vals_in, KeyT* keys_out, int32_t* vals_out,
+                           int begin_bit, int end_bit, unsigned char* ws, cudaStream_t st) {
+  const SortLayout L = sort_layout(n, sizeof(KeyT), begin_bit, end_bit);
+  unsigned* hist = (unsigned*)(ws + L.off_hist);
+  unsigned* tickets = (unsigned*)(ws + L.off_ticket);
+  unsigned* status = (unsigned*)(ws + L.off_status);
+  KeyT* tmp_keys = (KeyT*)(ws + L.off_tmp_keys);
+  int32_t* tmp_vals = (int32_t*)(ws + L.off_tmp_vals);
+
+  GS_CUDA(cudaMemsetAsync(ws, 0, L.zero_bytes, st));
+  int hist_blocks = (int)min((int64_t)148 * 8, ceil_div(n, 256));
+  radix_histogram_kernel<KeyT><<<hist_blocks, 256, 0, st>>>(n, keys_in, begin_bit, end_bit, L.passes, hist);
+  GS_LAUNCH_CHECK();
+  radix_histogram_scan_kernel<<<L.passes, kRadix, 0, st>>>(hist);
+  GS_LAUNCH_CHECK();
+
+  static bool attr_set = false;
+  const size_t smem = sort_smem_bytes<KeyT>();
+  if (!attr_set) {
+    GS_CUDA(cudaFuncSetAttribute(onesweep_pass_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  const KeyT* src_k = keys_in;
+  const int32_t* src_v = vals_in;
+  for (int p = 0; p < L.passes; ++p) {
+    // alternate between the temporary and the output so that the last pass lands in the output
+    const bool to_out = ((L.passes - 1 - p) % 2) == 0;
+    KeyT* dst_k = to_out ? keys_out : tmp_keys;
+    int32_t* dst_v = to_out ? vals_out : tmp_vals;
+    const int shift = begin_bit + p * kRadixBits;
+    const int nb = min(kRadixBits, end_bit - shift);
+    onesweep_pass_kernel<KeyT><<<(unsigned)L.tiles, kSortBlock, smem, st>>>(
+        n, src_k, src_v, dst_k, dst_v, shift, (1u << nb) - 1u, hist + p * kRadix,
+        status + (size_t)p * L.tiles * kRadix, tickets + p);
+    GS_LAUNCH_CHECK();
+    src_k = dst_k;
+    src_v = dst_v;
+  }
+  return GS_OK;
+}
+
+}  // namespace gs
+
+using namespace gs;
+
+extern "C" {
+
+size_t gs_full_cumsum_workspace_bytes(int64_t n, int32_t /*elem_bytes*/) {
+  int64_t tiles = ceil_div(n > 0 ? n : 1, kScanTile);
+  return align_up((size_t)tiles * sizeof(unsigned long long) + 16, 256);
+}
+
+int gs_full_cumsum(int64_t n, int32_t elem_bytes, const void* in, void* out, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  GS_CHECK_ARG(n >= 0 && out != nullptr, "gs_full_cumsum: bad arguments");
+  GS_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "gs_full_cumsum: elem_bytes must be 4 or 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    GS_CUDA(cudaMemsetAsync(out, 0, elem_bytes, st));
+    return GS_OK;
+  }
+  GS_CHECK_ARG(in != nullptr, "gs_full_cumsum: null input");
+  size_t need = gs_full_cumsum_workspace_bytes(n, elem_bytes);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("gs_full_cumsum: workspace %zu < %zu bytes", workspace_bytes, need);
+    return GS_ERR_WORKSPACE;
+  }
+  int64_t tiles = ceil_div(n, kScanTile);
+  GS_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+  unsigned long long* status = (unsigned long long*)workspace;
+  unsigned int* ticket = (unsigned int*)(status + tiles);
+  if (elem_bytes == 4)
+    full_cumsum_kernel<int32_t><<<(unsigned)tiles, kScanBlock, 0, st>>>(n, (const int32_t*)in, (int32_t*)out, status,
+                                                                       ticket);
+  else
+    full_cumsum_kernel<long long><<<(unsigned)tiles, kScanBlock, 0, st>>>(n, (const long long*)in, (long long*)out,
+                                                                         status, ticket);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+size_t gs_radix_sort_pairs_workspace_bytes(int64_t n, int32_t key_bytes, int32_t begin_bit, int32_t end_bit) {
+  if (n < 0 || (key_bytes != 4 && key_bytes != 8) || end_bit <= begin_bit) return 0;
+  return sort_layout(n, key_bytes, begin_bit, end_bit).total;
+}
+
+int gs_radix_sort_pairs(int64_t n, int32_t key_bytes, const void* keys_in, const int32_t* values_in, void* keys_out,
+                        int32_t* values_out, int32_t begin_bit, int32_t end_bit, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  GS_CHECK_ARG(key_bytes == 4 || key_bytes == 8, "gs_radix_sort_pairs: key_bytes must be 4 or 8");
+  GS_CHECK_ARG(begin_bit >= 0 && end_bit > begin_bit && end_bit <= key_bytes * 8,
+               "gs_radix_sort_pairs: bad bit range [%d, %d)", begin_bit, end_bit);
+  GS_CHECK_ARG(n >= 0 && n < (1ll << 30), "gs_radix_sort_pairs: n must be in [0, 2^30)");
+  if (n == 0) return GS_OK;
+  GS_CHECK_ARG(keys_in && values_in && keys_out && values_out, "gs_radix_sort_pairs: null tensor");
+  GS_CHECK_ARG(ceil_div(end_bit - begin_bit, kRadixBits) <= kMaxPasses, "gs_radix_sort_pairs: too many passes");
+  size_t need = gs_radix_sort_pairs_workspace_bytes(n, key_bytes, begin_bit, end_bit);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("gs_radix_sort_pairs: workspace %zu < %zu bytes", workspace_bytes, need);
+    return GS_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (key_bytes == 8)
+    return radix_sort_impl<uint64_t>(n, (const uint64_t*)keys_in, values_in, (uint64_t*)keys_out, values_out,
+                                     begin_bit, end_bit, (unsigned char*)workspace, st);
+  return radix_sort_impl<uint32_t>(n, (const uint32_t*)keys_in, values_in, (uint32_t*)keys_out, values_out, begin_bit,
+                                   end_bit, (unsigned char*)workspace, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+"""Scan and sort primitives with the surface of taichi_splatting/cuda_lib/__init__.py:16-43.
+
+``full_cumsum`` (cuda_lib/full_cumsum.cu:16-67: CUB ExclusiveSum + device sync) is a single-pass
+chained scan here, ``radix_sort_pairs`` (cuda_lib/radix_sort_pairs.cu:9-69: CUB SortPairs +
+device sync) a hand-written onesweep LSD radix sort (csrc/scan_sort.cu).  Neither synchronises
+the device; ``full_cumsum`` reads the total back because its signature returns a Python int.
+"""
+import ctypes
+
+import torch
+from beartype.typing import Tuple
+
+from .. import _native as N
+
+_KEY_BYTES = {torch.int32: 4, torch.uint32: 4, torch.int64: 8, torch.uint64: 8}
+
+
+def check_cuda(name, arg):
+  N.require_cuda(arg)
+
+
+def full_cumsum_device(x: torch.Tensor) -> torch.Tensor:
+  """Exclusive scan with the total appended: out (n+1,), out[n] = sum(x).  No host sync."""
+  check_cuda("full_cumsum", x)
+  assert x.dtype in (torch.int32, torch.int64) and x.dim() == 1, "full_cumsum: 1-D int32 / int64 only"
+  n = x.shape[0]
+  out = torch.empty((n + 1,), dtype=x.dtype, device=x.device)
+  lib = N.lib()
+  eb = x.element_size()
+  ws = N.workspace(lib.gs_full_cumsum_workspace_bytes(n, eb), x.device)
+  N.check(lib.gs_full_cumsum(ctypes.c_int64(n), ctypes.c_int32(eb), N.ptr(x.contiguous()), N.ptr(out), N.ptr(ws),
+                             ctypes.c_size_t(ws.numel()), N.stream_ptr(x.device)), "gs_full_cumsum")
+  return out
+
+
+def full_cumsum(x: torch.Tensor) -> Tuple[torch.Tensor, int]:
+  check_cuda("full_cumsum", x)
+  if x.shape[0] == 0:
+    return x.new_zeros((1,)), 0
+  out = full_cumsum_device(x)
+  return out, int(out[-1].item())
+
+
+def radix_sort_pairs(keys: torch.Tensor, values: torch.Tensor, start_bit=0, end_bit=None):
+  """Stable sort of (key, int32 value) pairs on key bits [start_bit, end_bit)."""
+  check_cuda("keys", keys)
+  check_cuda("values", values)
+  assert keys.dtype in _KEY_BYTES, f"keys must be a 32 or 64 bit integer tensor, got {keys.dtype}"
+  assert values.dtype == torch.int32, f"values must be int32, got {values.dtype}"
+  assert keys.shape == values.shape and keys.dim() == 1
+  kb = _KEY_BYTES[keys.dtype]
+  if end_bit is None or end_bit < 0:
+    end_bit = kb * 8
+  n = keys.shape[0]
+  keys_out, values_out = torch.empty_like(keys), torch.empty_like(values)
+  if n == 0:
+    return keys_out, values_out
+  lib = N.lib()
+  ws = N.workspace(lib.gs_radix_sort_pairs_workspace_bytes(n, kb, start_bit, end_bit), keys.device)
+  N.check(lib.gs_radix_sort_pairs(ctypes.c_int64(n), ctypes.c_int32(kb), N.ptr(keys.contiguous()),
+                                  N.ptr(values.contiguous()), N.ptr(keys_out), N.ptr(values_out),
+                                  ctypes.c_int32(start_bit), ctypes.c_int32(end_bit), N.ptr(ws),
+                                  ctypes.c_size_t(ws.numel()), N.stream_ptr(keys.device)), "gs_radix_sort_pairs")
+  return keys_out, values_out
+
+
+def radix_argsort(keys: torch.Tensor):
+  idx = torch.arange(keys.shape[0], dtype=torch.int32, device=keys.device)
+  _, idx = radix_sort_pairs(keys, idx)
+  return idx
+
+
+def segmented_sort_pairs(*args, **kwargs):
+  raise NotImplementedError("segmented_sort_pairs is exported by the reference's cuda_lib but not used by the "
+                            "render path (SURVEY.md K12); it is out of scope here")
+
+
+__all__ = ["full_cumsum", "full_cumsum_device", "radix_sort_pairs", "radix_argsort", "segmented_sort_pairs"]

@@ -1,0 +1,100 @@
+"""Maps 2D gaussians to the image tiles they overlap, sorted front to back per tile.
+
+Operator surface of taichi_splatting/mapper/tile_mapper.py: ``map_to_tiles`` (:202-223) and
+``pad_to_tile`` (:18-22).  Stages (csrc/geom_kernels.cu, csrc/scan_sort.cu): OBB overlap count per
+gaussian -> exclusive scan -> (tile, depth) key emission -> stable onesweep radix sort on the
+significant key bits -> tile range detection.  The only host read-back is the overlap total K,
+which sizes the key buffers (the reference synchronises the whole device twice here,
+cuda_lib/full_cumsum.cu:45 and cuda_lib/radix_sort_pairs.cu:27).
+"""
+import ctypes
+import math
+from numbers import Integral
+
+import torch
+from beartype import beartype
+from beartype.typing import Tuple
+
+from .. import _native as N
+from ..cuda_lib import full_cumsum_device, radix_sort_pairs
+from ..data_types import RasterConfig
+
+MAX_TILE = 65535  # 16 bit tile id inside the sorted key bits (tile_mapper.py:29)
+
+
+def pad_to_tile(image_size: Tuple[Integral, Integral], tile_size: int):
+  def pad(x):
+    return int(math.ceil(x / tile_size) * tile_size)
+  return tuple(pad(x) for x in image_size)
+
+
+def tile_shape(image_size, tile_size):
+  padded = pad_to_tile(image_size, tile_size)
+  return (padded[1] // tile_size, padded[0] // tile_size)
+
+
+def _tile_params(n, image_size, config, use_depth16):
+  return N.GsTileParams(int(image_size[0]), int(image_size[1]), config.tile_size, int(use_depth16), n,
+                        float(config.alpha_threshold))
+
+
+@beartype
+def map_to_tiles(gaussians: torch.Tensor, depth: torch.Tensor,
+                 image_size: Tuple[Integral, Integral],
+                 config: RasterConfig,
+                 use_depth16: bool = False
+                 ) -> Tuple[torch.Tensor, torch.Tensor]:
+  """ maps gaussians to tiles, sorted by depth (front to back):
+    Parameters:
+     gaussians: (N, 7) torch.Tensor of packed gaussians (float32)
+     depth: (N, 1)  torch.Tensor of depths (float32, >= 0)
+     image_size: (2, ) tuple of ints, (width, height)
+     config: RasterConfig (tile_size, alpha_threshold)
+
+    Returns:
+     overlap_to_point: (K, ) int32, maps overlap index to point index
+     tile_ranges: (TH, TW, 2) int32, maps tile index to its [start, end) range of overlap indices
+  """
+  assert gaussians.ndim == 2 and gaussians.shape[1] == 7, f"gaussians must be Nx7 got {gaussians.shape}"
+  assert depth.ndim == 2 and depth.shape[1] == 1, f"depths must be Nx1, got {depth.shape}"
+  assert gaussians.shape[0] == depth.shape[0]
+  N.require_cuda(gaussians, depth)
+
+  shape = tile_shape(image_size, config.tile_size)
+  assert shape[0] * shape[1] < MAX_TILE, \
+    f"tile dimensions {shape} for image size {image_size} exceed maximum tile count (16 bit id), try increasing tile_size"
+
+  with torch.no_grad():
+    device = gaussians.device
+    g = gaussians.detach().to(torch.float32).contiguous()   # the tile mapper is f32 (tile_mapper.py:12)
+    d = depth.detach().to(torch.float32).contiguous()
+    n = g.shape[0]
+    lib = N.lib()
+    stream = N.stream_ptr(device)
+    p = _tile_params(n, image_size, config, use_depth16)
+    tile_ranges = torch.empty((*shape, 2), dtype=torch.int32, device=device)
+
+    total = 0
+    if n > 0:
+      counts = torch.empty((n,), dtype=torch.int32, device=device)
+      N.check(lib.gs_tile_count(ctypes.byref(p), N.ptr(g), N.ptr(counts), stream), "gs_tile_count")
+      cum = full_cumsum_device(counts)
+      total = int(cum[-1].item())   # host read-back of K
+
+    if total > 0:
+      key_dtype = torch.int32 if use_depth16 else torch.int64   # bit patterns of u32 / u64 keys
+      keys = torch.empty((total,), dtype=key_dtype, device=device)
+      values = torch.empty((total,), dtype=torch.int32, device=device)
+      N.check(lib.gs_tile_emit_keys(ctypes.byref(p), N.ptr(g), N.ptr(d), N.ptr(cum), N.ptr(keys), N.ptr(values),
+                                    stream), "gs_tile_emit_keys")
+      # depth bits + only as many tile-id bits as there are tiles (same order as sorting all 16)
+      tile_bits = max(1, (shape[0] * shape[1] - 1).bit_length())
+      end_bit = (16 if use_depth16 else 32) + tile_bits
+      keys, overlap_to_point = radix_sort_pairs(keys, values, 0, end_bit)
+    else:
+      keys = None
+      overlap_to_point = torch.empty((0,), dtype=torch.int32, device=device)
+
+    N.check(lib.gs_find_ranges(ctypes.byref(p), ctypes.c_int64(total), N.ptr(keys), N.ptr(tile_ranges), stream),
+            "gs_find_ranges")
+    return overlap_to_point, tile_ranges

@@ -1,0 +1,107 @@
+"""Perspective projection of 3D gaussians to packed 2D gaussians (EWA splatting).
+
+Operator surface of taichi_splatting/perspective/projection.py: ``apply`` (:190-215) and
+``project_to_image`` (:218-248) with the same arguments, outputs and autograd conventions.
+Underneath, one sm_100a kernel projects, culls and compacts in a single pass
+(csrc/geom_kernels.cu, replacing project_kernel + torch.nonzero + two gathers, :31-80 and
+:146-149) and a hand-derived backward kernel (csrc/point_kernels.cu) replaces the Taichi
+autodiff of indexed_project_kernel (:83-118, :164-185).  The camera is read by the kernels
+directly; it is not expanded per point as in :212-213.
+"""
+import ctypes
+from numbers import Integral
+
+import torch
+from beartype import beartype
+from beartype.typing import Tuple
+
+from .. import _native as N
+from ..data_types import Gaussians3D, RasterConfig
+from .params import CameraParams
+
+
+class _ProjectFunction(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, position, log_scaling, rotation, alpha_logit, T_camera_world, projection,
+              image_size, depth_range, blur_cov, clamp_margin, alpha_threshold):
+    dtype, device = position.dtype, position.device
+    n = position.shape[0]
+    params = N.GsProjectParams(N.dtype_code(dtype), int(image_size[0]), int(image_size[1]), n,
+                               float(depth_range[0]), float(depth_range[1]), float(blur_cov),
+                               float(clamp_margin), float(alpha_threshold))
+    points = torch.empty((n, 7), dtype=dtype, device=device)
+    depth = torch.empty((n, 1), dtype=dtype, device=device)
+    indexes = torch.empty((n,), dtype=torch.int64, device=device)
+    count = torch.zeros((1,), dtype=torch.int32, device=device)
+    lib = N.lib()
+    ws = N.workspace(lib.gs_project_fwd_workspace_bytes(ctypes.byref(params)), device)
+    N.check(lib.gs_project_fwd(ctypes.byref(params), N.ptr(position), N.ptr(log_scaling), N.ptr(rotation),
+                               N.ptr(alpha_logit), N.ptr(T_camera_world), N.ptr(projection), N.ptr(points),
+                               N.ptr(depth), N.ptr(indexes), N.ptr(count), N.ptr(ws),
+                               ctypes.c_size_t(ws.numel()), N.stream_ptr(device)), "gs_project_fwd")
+    v = int(count.item())  # the one host read-back: the number of gaussians in view
+    points, depth, indexes = points[:v], depth[:v], indexes[:v]
+
+    ctx.params = params
+    ctx.mark_non_differentiable(indexes)
+    ctx.save_for_backward(position, log_scaling, rotation, alpha_logit, T_camera_world, projection, indexes)
+    return points, depth, indexes
+
+  @staticmethod
+  def backward(ctx, dpoints, ddepth, dindexes):
+    position, log_scaling, rotation, alpha_logit, T_camera_world, projection, indexes = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    v = indexes.shape[0]
+    grads = [torch.empty_like(t) if need[i] else None
+             for i, t in enumerate((position, log_scaling, rotation, alpha_logit, T_camera_world, projection))]
+    N.check(N.lib().gs_project_bwd(
+      ctypes.byref(ctx.params), ctypes.c_int64(v), N.ptr(position), N.ptr(log_scaling), N.ptr(rotation),
+      N.ptr(alpha_logit), N.ptr(T_camera_world), N.ptr(projection), N.ptr(indexes),
+      N.ptr(dpoints.contiguous()), N.ptr(ddepth.contiguous()), *[N.ptr(g) for g in grads],
+      N.stream_ptr(position.device)), "gs_project_bwd")
+    return (*grads, None, None, None, None, None)
+
+
+@beartype
+def apply(position: torch.Tensor, log_scaling: torch.Tensor,
+          rotation: torch.Tensor, alpha_logit: torch.Tensor,
+          T_camera_world: torch.Tensor,
+          projection: torch.Tensor,
+
+          image_size: Tuple[Integral, Integral],
+          depth_range: Tuple[float, float],
+
+          blur_cov: float = 0.0,
+          clamp_margin: float = 0.15,
+          alpha_threshold: float = 1. / 255.
+          ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+  dtype = position.dtype
+  N.require_cuda(position, log_scaling, rotation, alpha_logit, T_camera_world, projection)
+  return _ProjectFunction.apply(
+    position.contiguous(), log_scaling.contiguous(), rotation.contiguous(), alpha_logit.contiguous(),
+    T_camera_world.to(dtype).contiguous(), projection.to(dtype).contiguous(),
+    image_size, depth_range, blur_cov, clamp_margin, alpha_threshold)
+
+
+@beartype
+def project_to_image(gaussians: Gaussians3D, camera_params: CameraParams, config: RasterConfig,
+                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+  """
+  Project 3D gaussians to 2D gaussians in image space using perspective projection
+  (EWA approximation of the projected covariance, Zwicker et al. 2003).
+
+  Returns:
+    points:    torch.Tensor (V, 7)  - packed 2D gaussians in image space (mean, axis, sigma, alpha)
+    depths:    torch.Tensor (V, 1)  - camera space depth
+    indexes:   torch.Tensor (V,)    - indexes of the gaussians that are in view (int64, ascending)
+  """
+  return apply(
+    *gaussians.shape_tensors(),
+    camera_params.T_camera_world,
+    camera_params.projection,
+    camera_params.image_size,
+    camera_params.depth_range,
+    config.blur_cov,
+    config.clamp_margin,
+    config.alpha_threshold)

@@ -1,0 +1,63 @@
+"""View dependent colour from real spherical harmonics (degree 0..3).
+
+Operator surface of taichi_splatting/spherical_harmonics.py:167-178 (``evaluate_sh_at``); the
+forward / backward kernels are csrc/point_kernels.cu (replacing evaluate_sh_at_kernel and its
+Taichi autodiff, :118-134 and :154-161).  Layout is channel major: (M, K, (degree+1)^2).
+"""
+import ctypes
+import math
+
+import torch
+from beartype import beartype
+
+from . import _native as N
+
+
+def check_sh_degree(sh_features):
+  assert len(sh_features.shape) == 3, f"SH features must have 3 dimensions, got {sh_features.shape}"
+  n_sh = sh_features.shape[2]
+  n = int(math.isqrt(n_sh))
+  assert n * n == n_sh, f"SH feature count must be square, got {n_sh} ({sh_features.shape})"
+  assert 0 <= n - 1 <= 3, f"SH degree must be between 0 and 3, got {n - 1}"
+  return n - 1
+
+
+class _SHFunction(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, params, points, indexes, camera_pos):
+    m, k, d = params.shape
+    v = indexes.shape[0]
+    p = N.GsSHParams(N.dtype_code(params.dtype), k, d, m, v)
+    out = torch.empty((v, k), dtype=params.dtype, device=params.device)
+    N.check(N.lib().gs_sh_fwd(ctypes.byref(p), N.ptr(params), N.ptr(points), N.ptr(indexes), N.ptr(camera_pos),
+                              N.ptr(out), N.stream_ptr(params.device)), "gs_sh_fwd")
+    ctx.p = p
+    ctx.mark_non_differentiable(indexes)
+    ctx.save_for_backward(params, points, indexes, camera_pos)
+    return out
+
+  @staticmethod
+  def backward(ctx, doutput):
+    params, points, indexes, camera_pos = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    g_params = torch.empty_like(params) if need[0] else None
+    g_points = torch.empty_like(points) if need[1] else None
+    g_cam = torch.empty_like(camera_pos) if need[3] else None
+    N.check(N.lib().gs_sh_bwd(ctypes.byref(ctx.p), N.ptr(params), N.ptr(points), N.ptr(indexes),
+                              N.ptr(camera_pos), N.ptr(doutput.contiguous()), N.ptr(g_params), N.ptr(g_points),
+                              N.ptr(g_cam), N.stream_ptr(params.device)), "gs_sh_bwd")
+    return g_params, g_points, None, g_cam
+
+
+@beartype
+def evaluate_sh_at(sh_params: torch.Tensor,   # M, K, (degree + 1)^2  (usually K=3, for RGB)
+                   positions: torch.Tensor,   # M, 3
+                   indexes: torch.Tensor,     # V   (int64 indexes into the M gaussians)
+                   camera_pos: torch.Tensor   # 3
+                   ) -> torch.Tensor:         # V, K
+  check_sh_degree(sh_params)
+  N.require_cuda(sh_params, positions, indexes, camera_pos)
+  dtype = sh_params.dtype
+  return _SHFunction.apply(sh_params.contiguous(), positions.to(dtype).contiguous(),
+                           indexes.to(torch.int64).contiguous(), camera_pos.to(dtype).contiguous())
