@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Benchmark of the render path: forward + backward of render_gaussians on synthetic gaussians.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json metric "fwd+bwd ms/frame & Gaussians*px/s at 3M Gauss 2048px"): 3,000,000 seeded random
+gaussians (taichi_splatting/tests/random_data.py recipe), spherical harmonics degree 3, 2048x1365, tile 16.
+A step is one batch of `views_per_rank` camera views per rank, forward + backward through the public API
+(render_gaussians -> L1 loss -> backward), gradients accumulated over the views, then ONE gradient all-reduce
+(NCCL) when N > 1.  Gaussians are replicated on every rank, views are partitioned (weak scaling: per-GPU work
+is fixed).  value = gaussians * pixels * views of all ranks / second.
+
+Prints ONE JSON line (see the keys below).  `--impl reference` times the CPU restatement of the reference
+algorithm (oracle/) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CPU_SAMPLE_STRIDE = 16   # the CPU legs render every 16th gaussian of the scene
+
+WORKLOAD = dict(num_gaussians=3_000_000, image_size=(2048, 1365), sh_degree=3, scale_factor=1.5,
+                alpha_range=(0.1, 0.9), tile_size=16, seed=0)
+
+
+# ----------------------------------------------------------------------------------------------- scene
+def build_scene(n, image_size, sh_degree, scale_factor, alpha_range, seed, num_views):
+  from taichi_gaussian_rasterizer_b200.synthetic import random_3d_gaussians, random_camera
+  from taichi_gaussian_rasterizer_b200.torch_lib.projection import join_rt, quat_to_mat
+  torch.manual_seed(seed)
+  base = random_camera(image_size=image_size)
+  gaussians = random_3d_gaussians(n, base, scale_factor=scale_factor, alpha_range=alpha_range, sh_degree=sh_degree)
+  cameras = []
+  g = torch.Generator().manual_seed(seed + 1)
+  for i in range(num_views):
+    # small pose jitter around the base view so that every view sees a comparable part of the scene
+    axis = torch.nn.functional.normalize(torch.randn(3, generator=g), dim=0)
+    angle = (torch.rand(1, generator=g) * 2 - 1) * 0.02
+    q = torch.cat([axis * torch.sin(angle / 2), torch.cos(angle / 2)])
+    delta = join_rt(quat_to_mat(q), (torch.rand(3, generator=g) * 2 - 1) * 0.02)
+    cameras.append(base.transformed(delta) if i > 0 else base)
+  return gaussians, cameras
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+  FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index):
+    self.index, self.samples, self.proc = index, [], None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                    "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.samples.append(line.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    sm, mx, reasons = [], None, set()
+    for s in self.samples:
+      parts = [p.strip() for p in s.split(",")]
+      if len(parts) < 6:
+        continue
+      try:
+        sm.append(float(parts[0])); mx = float(parts[1])
+      except ValueError:
+        continue
+      for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
+        if v.lower().startswith("active"):
+          reasons.add(name)
+    sm.sort()
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+            "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- ours
+KERNELS_PER_CALL = {  # kernels launched by each entry point (memsets not counted)
+  "gs_project_fwd": 1, "gs_project_bwd": 1, "gs_sh_fwd": 1, "gs_sh_bwd": 1, "gs_tile_count": 1, "gs_full_cumsum": 1,
+  "gs_tile_emit_keys": 1, "gs_find_ranges": 1, "gs_raster_fwd": 2, "gs_raster_bwd": 2,
+}
+
+
+def run_ours(args):
+  import torch.distributed as dist
+  from taichi_gaussian_rasterizer_b200 import RasterConfig, _native, render_gaussians
+  from taichi_gaussian_rasterizer_b200.distributed import GradientBucket
+  from taichi_gaussian_rasterizer_b200.perspective import CameraParams
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+  torch.cuda.set_device(local_rank)
+  device = torch.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=device)
+
+  W = dict(WORKLOAD)
+  if args.num_gaussians:
+    W["num_gaussians"] = args.num_gaussians
+  if args.image_size:
+    W["image_size"] = tuple(args.image_size)
+  views = args.views_per_rank
+  w, h = W["image_size"]
+  gaussians_cpu, cameras = build_scene(W["num_gaussians"], W["image_size"], W["sh_degree"], W["scale_factor"],
+                                       W["alpha_range"], W["seed"], num_views=views * world)
+  my_cameras = cameras[rank::world][:views]
+  gaussians = gaussians_cpu.to(device=device)
+  gaussians.requires_grad_(True)
+  params = [gaussians.position, gaussians.log_scaling, gaussians.rotation, gaussians.alpha_logit, gaussians.feature]
+  bucket = GradientBucket(params)
+  config = RasterConfig(tile_size=W["tile_size"])
+
+  # per step inputs: camera (projection + pose) and the target image of every view, in pinned host memory
+  torch.manual_seed(1234 + rank)
+  host_targets = [torch.rand(h, w, 3).pin_memory() for _ in range(views)]
+  host_proj = [c.projection.clone().pin_memory() for c in my_cameras]
+  host_pose = [c.T_camera_world.clone().pin_memory() for c in my_cameras]
+  dev_targets = [t.to(device) for t in host_targets]
+  dev_cams = [c.to(device=device) for c in my_cameras]
+  h2d_bytes = sum(t.numel() * 4 for t in host_targets) + sum(p.numel() * 4 for p in host_proj + host_pose)
+  loss_host = torch.zeros(1).pin_memory()
+  stats = {}
+
+  def step(from_host: bool):
+    bucket.zero_()
+    total = torch.zeros((), device=device)
+    for i in range(views):
+      if from_host:
+        cam = CameraParams(projection=host_proj[i].to(device, non_blocking=True),
+                           T_camera_world=host_pose[i].to(device, non_blocking=True),
+                           near_plane=my_cameras[i].near_plane, far_plane=my_cameras[i].far_plane,
+                           image_size=my_cameras[i].image_size)
+        target = host_targets[i].to(device, non_blocking=True)
+      else:
+        cam, target = dev_cams[i], dev_targets[i]
+      rendering = render_gaussians(gaussians, cam, config, use_sh=True)
+      loss = (rendering.image - target).abs().mean()
+      loss.backward()
+      total += loss.detach()
+      stats["V"] = rendering.points_in_view.shape[0]
+    bucket.all_reduce()
+    if from_host:
+      loss_host.copy_(total.reshape(1), non_blocking=True)
+      torch.cuda.current_stream().synchronize()   # the step's result is read on the host
+    return total
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(from_host, steps, timer=None):
+    barrier()
+    _native.set_stage_timer(timer)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+      step(from_host)
+    b.record()
+    barrier()
+    _native.set_stage_timer(None)
+    ms = a.elapsed_time(b)
+    if world > 1:
+      t = torch.tensor([ms], device=device)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = float(t.item())
+    return ms
+
+  for _ in range(args.warmup):
+    step(False)
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  timer = _native.StageTimer()
+  ms_dev = timed(False, args.steps, timer)
+  stage = timer.summary()
+  clocks = sampler.stop() if rank == 0 else None
+  step(True)
+  ms_e2e = timed(True, args.steps)
+
+  n, px = W["num_gaussians"], w * h
+  units_per_step = n * px * views * world
+  value = units_per_step / (ms_dev / args.steps / 1e3)
+  e2e = units_per_step / (ms_e2e / args.steps / 1e3)
+
+  # K of the last view, for the roofline's algorithmic bytes
+  from taichi_gaussian_rasterizer_b200 import map_to_tiles
+  from taichi_gaussian_rasterizer_b200.perspective.projection import project_to_image
+  from taichi_gaussian_rasterizer_b200.torch_lib.projection import ndc_depth
+  with torch.no_grad():
+    g2d, depths, idx = project_to_image(gaussians, dev_cams[0], config)
+    o2p, ranges = map_to_tiles(g2d, ndc_depth(depths, dev_cams[0].near_plane, dev_cams[0].far_plane),
+                               dev_cams[0].image_size, config)
+  V, K, F = int(idx.shape[0]), int(o2p.shape[0]), 3
+  counts = (ranges[..., 1] - ranges[..., 0]).float()
+
+  peaks = {}
+  try:
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+  except Exception:
+    pass
+  peak_gbs, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json") if "hbm_gbs" in peaks else (6650.0, "fallback")
+  calls, bwd_ms = stage.get("gs_raster_bwd", (0, 0.0))
+  bwd_avg_ms = bwd_ms / max(calls, 1)
+  bwd_bytes = K * (32 + 4 * F) + 8 * px * F + V * (28 + 4 * F)   # SURVEY.md §8(d) raster_bwd
+  achieved = bwd_bytes / (bwd_avg_ms * 1e-3) / 1e9 if bwd_avg_ms > 0 else 0.0
+  fwd_calls, fwd_ms = stage.get("gs_raster_fwd", (0, 0.0))
+  stage_ms = {k: round(v[1] / args.steps / views, 4) for k, v in sorted(stage.items())}
+  launches = sum(KERNELS_PER_CALL.get(k, 0) * v[0] for k, v in stage.items())
+  sort_calls = stage.get("gs_radix_sort_pairs", (0, 0.0))[0]
+  tile_bits = max(1, (int(ranges.shape[0] * ranges.shape[1]) - 1).bit_length())
+  launches += sort_calls * (2 + -(-(32 + tile_bits) // 8))
+  launches = launches // max(args.steps, 1)
+
+  out = {
+    "metric": "gaussians_px_per_s_fwd_bwd", "value": value, "unit": "gaussian*pixel/s",
+    "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    "ms_per_step": ms_dev / args.steps, "ms_per_frame": ms_dev / args.steps / views,
+    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    "config": {"workload": f"render_gaussians fwd+bwd, {n} random gaussians, SH degree {W['sh_degree']}, "
+                           f"{w}x{h}, tile {W['tile_size']}, L1 loss",
+               "views_per_rank": views, "parallelism": f"view-parallel x{world}, replicated gaussians, "
+                                                       "one gradient all-reduce per step",
+               "V_in_view": V, "K_overlaps": K, "K_per_tile_mean": float(counts.mean()),
+               "K_per_tile_max": int(counts.max()), "scale_factor": W["scale_factor"],
+               "l2_policy": "inputs larger than L2 (708 MB of gaussians per view)",
+               "emulate_stale_tail": True, "forward_exit_transmittance": 0.0},
+    "e2e": {"value": e2e, "unit": "gaussian*pixel/s", "ms_per_step": ms_e2e / args.steps,
+            "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+    "gpu_launches": launches,
+    "roofline": {"kernel": "raster_bwd_fast_kernel (gs_raster_bwd)", "bound": "hbm", "achieved": achieved,
+                 "peak": peak_gbs, "peak_source": peak_src, "unit": "GB/s",
+                 "frac": achieved / peak_gbs if peak_gbs else None, "traffic": None,
+                 "algorithmic_bytes": bwd_bytes, "avg_launch_ms": bwd_avg_ms,
+                 "note": "instruction bound kernel (SURVEY.md §8d): HBM fraction is low by construction; "
+                         "blend_evals_per_s is the informative figure",
+                 "blend_evals_per_s": K * 256 / (bwd_avg_ms * 1e-3) if bwd_avg_ms > 0 else None},
+    "stage_ms_per_frame": stage_ms,
+    "clocks": clocks,
+  }
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    out["cpu_baseline"] = cpu_baseline(W, budget_s=args.cpu_budget)
+  if rank == 0:
+    print(json.dumps(out))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------- CPU legs
+def oracle_frame(gaussians, camera, config):
+  """One forward + backward frame of the CPU restatement (oracle/): C++/OpenMP for projection forward, SH
+  forward, tile mapping, rasterizer forward / backward; torch (CPU) autograd for the per point backward."""
+  import oracle
+  from oracle import torch_ref
+  g = gaussians
+  pts, depth, idx = torch_ref.projection_apply(*g.shape_tensors(), camera.T_camera_world, camera.projection,
+                                               camera.image_size, camera.depth_range, config.blur_cov,
+                                               config.clamp_margin, config.alpha_threshold)
+  feats = torch_ref.evaluate_sh_at(g.feature, g.position.detach(), idx, camera.camera_position)
+  ndc = torch_ref.ndc_depth(depth, camera.near_plane, camera.far_plane)
+  o2p, ranges = oracle.map_to_tiles(pts.detach(), ndc.detach(), camera.image_size, config)
+  raster = oracle.rasterize_with_tiles(pts, feats, o2p, ranges.view(-1, 2), camera.image_size, config)
+  raster.image.abs().mean().backward()
+  return int(idx.shape[0]), int(o2p.shape[0])
+
+
+def cpu_sample(W, stride):
+  """Every `stride`-th gaussian of the benchmark scene (same sizes, opacities and camera as the GPU arm)."""
+  gaussians, cameras = build_scene(W["num_gaussians"], W["image_size"], W["sh_degree"], W["scale_factor"],
+                                   W["alpha_range"], W["seed"], num_views=1)
+  gaussians = gaussians[::stride].contiguous()
+  gaussians.requires_grad_(True)
+  return gaussians.batch_size[0], gaussians, cameras[0]
+
+
+def cpu_baseline(W, budget_s=20.0):
+  import oracle
+  from taichi_gaussian_rasterizer_b200 import RasterConfig
+  config = RasterConfig(tile_size=W["tile_size"])
+  n, gaussians, camera = cpu_sample(W, CPU_SAMPLE_STRIDE)
+  t0 = time.perf_counter()
+  frames = 0
+  while True:
+    for p in (gaussians.position, gaussians.log_scaling, gaussians.rotation, gaussians.alpha_logit, gaussians.feature):
+      p.grad = None
+    V, K = oracle_frame(gaussians, camera, config)
+    frames += 1
+    if time.perf_counter() - t0 > budget_s or frames >= 3:
+      break
+  dt = (time.perf_counter() - t0) / frames
+  w, h = W["image_size"]
+  return {"value": n * w * h / dt, "unit": "gaussian*pixel/s", "cores": oracle.num_threads(), "kind": "port",
+          "sample": f"{frames} frame(s) of every {CPU_SAMPLE_STRIDE}th gaussian of the benchmark scene ({n} gaussians, "
+                    f"same camera, {w}x{h}, SH3, fwd+bwd): {dt:.2f} s/frame, V={V}, K={K}"}
+
+
+def run_reference(args):
+  """The reference's algorithm on the host cores: the Taichi package cannot be installed here (no wheel, no
+  network; its rasterizer has no CPU arch anyway, SURVEY.md header), so this arm times oracle/ — the C++/OpenMP
+  + torch restatement — with all host threads on a bounded sample of the same workload."""
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  import oracle
+  from taichi_gaussian_rasterizer_b200 import RasterConfig
+  W = dict(WORKLOAD)
+  config = RasterConfig(tile_size=W["tile_size"])
+  n, gaussians, camera = cpu_sample(W, CPU_SAMPLE_STRIDE)
+  w, h = W["image_size"]
+
+  def frame():
+    for p in (gaussians.position, gaussians.log_scaling, gaussians.rotation, gaussians.alpha_logit, gaussians.feature):
+      p.grad = None
+    return oracle_frame(gaussians, camera, config)
+
+  for _ in range(min(args.warmup, 1)):
+    frame()
+  steps = min(args.steps, 3)
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    V, K = frame()
+  dt = (time.perf_counter() - t0) / steps
+  value = n * w * h / dt
+  sample = (f"each step = 1 frame fwd+bwd of every {CPU_SAMPLE_STRIDE}th gaussian of the benchmark scene ({n} gaussians, "
+            f"same camera), {w}x{h}, SH3; V={V}, K={K}; {steps} timed steps")
+  print(json.dumps({
+    "impl": "reference", "metric": "gaussians_px_per_s_fwd_bwd", "value": value, "unit": "gaussian*pixel/s",
+    "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    "config": {"workload": f"oracle restatement fwd+bwd on host cores, {n} gaussians (bounded sample), {w}x{h}"},
+    "cpu_baseline": {"value": value, "unit": "gaussian*pixel/s", "cores": oracle.num_threads(), "kind": "port",
+                     "sample": sample},
+    "e2e": {"value": value, "unit": "gaussian*pixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    "gpu_launches": 0}))
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=10)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+  ap.add_argument("--views-per-rank", type=int, default=8)
+  ap.add_argument("--num-gaussians", type=int, default=0)
+  ap.add_argument("--image-size", type=int, nargs=2, default=None)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--cpu-budget", type=float, default=20.0)
+  args = ap.parse_args()
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    args.warmup = max(args.warmup, 3)
+    run_ours(args)
+
+
+if __name__ == "__main__":
+  main()

@@ -84,6 +84,50 @@ def check(rc: int, what: str):
     raise RuntimeError(f"{what} failed ({rc}): {msg}")
 
 
+class StageTimer:
+  """Optional per-entry-point device timing: CUDA events recorded on the launching stream around each
+  C-ABI call (used by bench.py for the per-kernel roofline; off by default)."""
+
+  def __init__(self):
+    self.records = []   # (name, start_event, end_event)
+
+  def summary(self):
+    """name -> (calls, total_ms); synchronises."""
+    torch.cuda.synchronize()
+    out = {}
+    for name, a, b in self.records:
+      n, t = out.get(name, (0, 0.0))
+      out[name] = (n + 1, t + a.elapsed_time(b))
+    return out
+
+  def reset(self):
+    self.records = []
+
+
+_timer = None
+
+
+def set_stage_timer(timer):
+  global _timer
+  _timer = timer
+  return timer
+
+
+def call(name: str, *args):
+  """Invoke an entry point of the library, raising RuntimeError with its message on failure."""
+  fn = getattr(lib(), name)
+  if _timer is None:
+    rc = fn(*args)
+  else:
+    a = torch.cuda.Event(enable_timing=True)
+    b = torch.cuda.Event(enable_timing=True)
+    a.record()
+    rc = fn(*args)
+    b.record()
+    _timer.records.append((name, a, b))
+  check(rc, name)
+
+
 def dtype_code(dtype: torch.dtype) -> int:
   if dtype == torch.float32:
     return GS_F32

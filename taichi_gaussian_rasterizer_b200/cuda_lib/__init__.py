@@ -28,8 +28,8 @@ def full_cumsum_device(x: torch.Tensor) -> torch.Tensor:
   lib = N.lib()
   eb = x.element_size()
   ws = N.workspace(lib.gs_full_cumsum_workspace_bytes(n, eb), x.device)
-  N.check(lib.gs_full_cumsum(ctypes.c_int64(n), ctypes.c_int32(eb), N.ptr(x.contiguous()), N.ptr(out), N.ptr(ws),
-                             ctypes.c_size_t(ws.numel()), N.stream_ptr(x.device)), "gs_full_cumsum")
+  N.call("gs_full_cumsum", ctypes.c_int64(n), ctypes.c_int32(eb), N.ptr(x.contiguous()), N.ptr(out), N.ptr(ws),
+                             ctypes.c_size_t(ws.numel()), N.stream_ptr(x.device))
   return out
 
 
@@ -57,10 +57,10 @@ def radix_sort_pairs(keys: torch.Tensor, values: torch.Tensor, start_bit=0, end_
     return keys_out, values_out
   lib = N.lib()
   ws = N.workspace(lib.gs_radix_sort_pairs_workspace_bytes(n, kb, start_bit, end_bit), keys.device)
-  N.check(lib.gs_radix_sort_pairs(ctypes.c_int64(n), ctypes.c_int32(kb), N.ptr(keys.contiguous()),
+  N.call("gs_radix_sort_pairs", ctypes.c_int64(n), ctypes.c_int32(kb), N.ptr(keys.contiguous()),
                                   N.ptr(values.contiguous()), N.ptr(keys_out), N.ptr(values_out),
                                   ctypes.c_int32(start_bit), ctypes.c_int32(end_bit), N.ptr(ws),
-                                  ctypes.c_size_t(ws.numel()), N.stream_ptr(keys.device)), "gs_radix_sort_pairs")
+                                  ctypes.c_size_t(ws.numel()), N.stream_ptr(keys.device))
   return keys_out, values_out
 
 

@@ -1,0 +1,57 @@
+"""View-parallel rendering across GPUs (one process per GPU, torch.distributed).
+
+The reference is single process / single GPU (no collective call sites).  A single view
+does not shard (global sort, per tile lists over all gaussians), views are independent: every rank holds
+a replica of the gaussians, renders its share of a batch of cameras (rank r takes views r::world),
+accumulates dense gradients locally and the ranks sum them ONCE per batch with a single all-reduce over
+one flat bucket (NCCL over NVLink on the B200 box, gloo in the CPU tests).  Camera gradients are per
+view and stay local.
+"""
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def partition_views(num_views: int, rank: int, world_size: int) -> List[int]:
+  """Indices of the views rendered by `rank` (round robin, so any prefix of the batch stays balanced)."""
+  return list(range(rank, num_views, world_size))
+
+
+class GradientBucket:
+  """One flat buffer holding the gradients of a fixed set of parameters, views into it installed as
+  ``param.grad`` so that autograd accumulates straight into the bucket (no flatten copy before the
+  all-reduce)."""
+
+  def __init__(self, params: Sequence[torch.Tensor]):
+    self.params = [p for p in params if p.requires_grad]
+    assert len(self.params) > 0
+    dtype, device = self.params[0].dtype, self.params[0].device
+    sizes = [p.numel() for p in self.params]
+    self.flat = torch.zeros((sum(sizes),), dtype=dtype, device=device)
+    off = 0
+    for p, n in zip(self.params, sizes):
+      p.grad = self.flat[off:off + n].view_as(p)
+      off += n
+
+  def zero_(self):
+    self.flat.zero_()
+
+  @property
+  def nbytes(self) -> int:
+    return self.flat.numel() * self.flat.element_size()
+
+  def all_reduce(self, group=None, async_op: bool = False):
+    """Sum the bucket over ranks (no-op without an initialised process group / single rank)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+      return None
+    return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def all_reduce_statistics(tensors: Iterable[Optional[torch.Tensor]], group=None):
+  """Sum per gaussian statistics (visibility (N,), heuristics (N,2) scattered to dense) over ranks."""
+  if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+    return
+  for t in tensors:
+    if t is not None:
+      dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)

@@ -77,7 +77,7 @@ def map_to_tiles(gaussians: torch.Tensor, depth: torch.Tensor,
     total = 0
     if n > 0:
       counts = torch.empty((n,), dtype=torch.int32, device=device)
-      N.check(lib.gs_tile_count(ctypes.byref(p), N.ptr(g), N.ptr(counts), stream), "gs_tile_count")
+      N.call("gs_tile_count", ctypes.byref(p), N.ptr(g), N.ptr(counts), stream)
       cum = full_cumsum_device(counts)
       total = int(cum[-1].item())   # host read-back of K
 
@@ -85,8 +85,8 @@ def map_to_tiles(gaussians: torch.Tensor, depth: torch.Tensor,
       key_dtype = torch.int32 if use_depth16 else torch.int64   # bit patterns of u32 / u64 keys
       keys = torch.empty((total,), dtype=key_dtype, device=device)
       values = torch.empty((total,), dtype=torch.int32, device=device)
-      N.check(lib.gs_tile_emit_keys(ctypes.byref(p), N.ptr(g), N.ptr(d), N.ptr(cum), N.ptr(keys), N.ptr(values),
-                                    stream), "gs_tile_emit_keys")
+      N.call("gs_tile_emit_keys", ctypes.byref(p), N.ptr(g), N.ptr(d), N.ptr(cum), N.ptr(keys), N.ptr(values),
+                                    stream)
       # depth bits + only as many tile-id bits as there are tiles (same order as sorting all 16)
       tile_bits = max(1, (shape[0] * shape[1] - 1).bit_length())
       end_bit = (16 if use_depth16 else 32) + tile_bits
@@ -95,6 +95,5 @@ def map_to_tiles(gaussians: torch.Tensor, depth: torch.Tensor,
       keys = None
       overlap_to_point = torch.empty((0,), dtype=torch.int32, device=device)
 
-    N.check(lib.gs_find_ranges(ctypes.byref(p), ctypes.c_int64(total), N.ptr(keys), N.ptr(tile_ranges), stream),
-            "gs_find_ranges")
+    N.call("gs_find_ranges", ctypes.byref(p), ctypes.c_int64(total), N.ptr(keys), N.ptr(tile_ranges), stream)
     return overlap_to_point, tile_ranges

@@ -36,10 +36,10 @@ class _ProjectFunction(torch.autograd.Function):
     count = torch.zeros((1,), dtype=torch.int32, device=device)
     lib = N.lib()
     ws = N.workspace(lib.gs_project_fwd_workspace_bytes(ctypes.byref(params)), device)
-    N.check(lib.gs_project_fwd(ctypes.byref(params), N.ptr(position), N.ptr(log_scaling), N.ptr(rotation),
+    N.call("gs_project_fwd", ctypes.byref(params), N.ptr(position), N.ptr(log_scaling), N.ptr(rotation),
                                N.ptr(alpha_logit), N.ptr(T_camera_world), N.ptr(projection), N.ptr(points),
                                N.ptr(depth), N.ptr(indexes), N.ptr(count), N.ptr(ws),
-                               ctypes.c_size_t(ws.numel()), N.stream_ptr(device)), "gs_project_fwd")
+                               ctypes.c_size_t(ws.numel()), N.stream_ptr(device))
     v = int(count.item())  # the one host read-back: the number of gaussians in view
     points, depth, indexes = points[:v], depth[:v], indexes[:v]
 
@@ -55,11 +55,10 @@ class _ProjectFunction(torch.autograd.Function):
     v = indexes.shape[0]
     grads = [torch.empty_like(t) if need[i] else None
              for i, t in enumerate((position, log_scaling, rotation, alpha_logit, T_camera_world, projection))]
-    N.check(N.lib().gs_project_bwd(
-      ctypes.byref(ctx.params), ctypes.c_int64(v), N.ptr(position), N.ptr(log_scaling), N.ptr(rotation),
+    N.call("gs_project_bwd", ctypes.byref(ctx.params), ctypes.c_int64(v), N.ptr(position), N.ptr(log_scaling), N.ptr(rotation),
       N.ptr(alpha_logit), N.ptr(T_camera_world), N.ptr(projection), N.ptr(indexes),
       N.ptr(dpoints.contiguous()), N.ptr(ddepth.contiguous()), *[N.ptr(g) for g in grads],
-      N.stream_ptr(position.device)), "gs_project_bwd")
+      N.stream_ptr(position.device))
     return (*grads, None, None, None, None, None)
 
 

@@ -78,10 +78,9 @@ class _RasterFunction(torch.autograd.Function):
     params = _raster_params(config, dtype, image_size, F, V, K, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
     lib = N.lib()
     ws = N.workspace(lib.gs_raster_workspace_bytes(ctypes.byref(params)), device)
-    N.check(lib.gs_raster_fwd(
-      ctypes.byref(params), N.ptr(gaussians), N.ptr(features), N.ptr(tile_overlap_ranges), N.ptr(overlap_to_point),
+    N.call("gs_raster_fwd", ctypes.byref(params), N.ptr(gaussians), N.ptr(features), N.ptr(tile_overlap_ranges), N.ptr(overlap_to_point),
       N.ptr(image_feature), N.ptr(image_alpha), N.ptr(visibility) if config.compute_visibility else N.ptr(None),
-      N.ptr(ws), ctypes.c_size_t(ws.numel()), N.stream_ptr(device)), "gs_raster_fwd")
+      N.ptr(ws), ctypes.c_size_t(ws.numel()), N.stream_ptr(device))
 
     ctx.params = params
     ctx.workspace = ws            # packed records are reused by backward
@@ -104,11 +103,10 @@ class _RasterFunction(torch.autograd.Function):
     params.features_requires_grad = int(need_f)
     params.workspace_holds_packed = 1
     heur = ctx.point_heuristic if ctx.config.compute_point_heuristic else None
-    N.check(N.lib().gs_raster_bwd(
-      ctypes.byref(params), N.ptr(gaussians), N.ptr(features), N.ptr(ctx.tile_overlap_ranges),
+    N.call("gs_raster_bwd", ctypes.byref(params), N.ptr(gaussians), N.ptr(features), N.ptr(ctx.tile_overlap_ranges),
       N.ptr(ctx.overlap_to_point), N.ptr(image_feature), N.ptr(grad_image_feature.contiguous()),
       N.ptr(grad_gaussians), N.ptr(grad_features), N.ptr(heur), N.ptr(ctx.workspace),
-      ctypes.c_size_t(ctx.workspace.numel()), N.stream_ptr(gaussians.device)), "gs_raster_bwd")
+      ctypes.c_size_t(ctx.workspace.numel()), N.stream_ptr(gaussians.device))
     return grad_gaussians, grad_features, None, None, None, None
 
 

@@ -30,8 +30,8 @@ class _SHFunction(torch.autograd.Function):
     v = indexes.shape[0]
     p = N.GsSHParams(N.dtype_code(params.dtype), k, d, m, v)
     out = torch.empty((v, k), dtype=params.dtype, device=params.device)
-    N.check(N.lib().gs_sh_fwd(ctypes.byref(p), N.ptr(params), N.ptr(points), N.ptr(indexes), N.ptr(camera_pos),
-                              N.ptr(out), N.stream_ptr(params.device)), "gs_sh_fwd")
+    N.call("gs_sh_fwd", ctypes.byref(p), N.ptr(params), N.ptr(points), N.ptr(indexes), N.ptr(camera_pos),
+                              N.ptr(out), N.stream_ptr(params.device))
     ctx.p = p
     ctx.mark_non_differentiable(indexes)
     ctx.save_for_backward(params, points, indexes, camera_pos)
@@ -44,9 +44,9 @@ class _SHFunction(torch.autograd.Function):
     g_params = torch.empty_like(params) if need[0] else None
     g_points = torch.empty_like(points) if need[1] else None
     g_cam = torch.empty_like(camera_pos) if need[3] else None
-    N.check(N.lib().gs_sh_bwd(ctypes.byref(ctx.p), N.ptr(params), N.ptr(points), N.ptr(indexes),
+    N.call("gs_sh_bwd", ctypes.byref(ctx.p), N.ptr(params), N.ptr(points), N.ptr(indexes),
                               N.ptr(camera_pos), N.ptr(doutput.contiguous()), N.ptr(g_params), N.ptr(g_points),
-                              N.ptr(g_cam), N.stream_ptr(params.device)), "gs_sh_bwd")
+                              N.ptr(g_cam), N.stream_ptr(params.device))
     return g_params, g_points, None, g_cam
 
 

@@ -1,0 +1,136 @@
+"""Projection and spherical harmonics on the GPU against the oracle and torch autograd — the checks of
+the reference's tests/test_projection.py:76-116 and tests/test_spherical_harmonics.py:33-62, with the
+CUDA kernels in place of the Taichi ones."""
+import pytest
+import torch
+
+import oracle
+from oracle import torch_ref
+from taichi_gaussian_rasterizer_b200 import evaluate_sh_at
+from taichi_gaussian_rasterizer_b200.perspective import projection as gpu_proj
+from util import GRAD_REL_L2, rel_l2, scene3d
+
+pytestmark = pytest.mark.gpu
+
+
+def proj_args(g, cam):
+  return (*g.shape_tensors(), cam.T_camera_world, cam.projection, cam.image_size, cam.depth_range)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_projection_f32_bit_exact_vs_oracle(cuda_device, seed):
+  torch.manual_seed(seed)
+  n = int(torch.randint(1, 20000, (1,)))
+  g, cam = scene3d(seed, n, margin=0.5, scale_factor=0.3)
+  p_ref, d_ref, i_ref = oracle.projection_forward(*proj_args(g, cam), blur_cov=0.3)
+  gc, cc = g.to(device=cuda_device), cam.to(device=cuda_device)
+  p, d, i = gpu_proj.apply(*proj_args(gc, cc), blur_cov=0.3)
+  assert i.dtype == torch.int64 and torch.equal(i.cpu(), i_ref), "visible index set differs"
+  assert torch.equal(p.cpu().view(torch.int32), p_ref.view(torch.int32)), "packed gaussians are not bit-identical"
+  assert torch.equal(d.cpu().view(torch.int32), d_ref.view(torch.int32))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_projection_f64_outputs_and_grads_vs_torch(cuda_device, seed):
+  torch.manual_seed(100 + seed)
+  n = int(torch.randint(1, 5000, (1,)))
+  g, cam = scene3d(100 + seed, n, margin=0.5, scale_factor=0.1)
+  g, cam = g.to(dtype=torch.float64), cam.to(dtype=torch.float64)
+
+  def run(fn, device):
+    ts = [t.detach().clone().to(device).requires_grad_(True) for t in
+          (*g.shape_tensors(), cam.T_camera_world, cam.projection)]
+    pts, depth, idx = fn(*ts, cam.image_size, cam.depth_range, blur_cov=0.3)
+    (pts.mean() + depth.mean()).backward()
+    return (pts, depth, idx), [t.grad for t in ts]
+
+  (p1, d1, i1), g1 = run(gpu_proj.apply, cuda_device)
+  (p2, d2, i2), g2 = run(torch_ref.projection_apply, "cpu")
+  assert torch.equal(i1.cpu(), i2)
+  assert torch.allclose(p1.cpu(), p2, rtol=1e-9, atol=1e-9)
+  assert torch.allclose(d1.cpu(), d2, rtol=1e-10, atol=1e-10)
+  names = ["position", "log_scaling", "rotation", "alpha_logit", "T_camera_world", "projection"]
+  for name, a, b in zip(names, g1, g2):
+    assert a is not None and a.shape == b.shape, name
+    assert torch.allclose(a.cpu(), b, rtol=1e-6, atol=1e-9), f"{name} grad: rel l2 {rel_l2(a, b)}"
+
+
+def test_projection_f32_grads_within_tolerance(cuda_device):
+  g, cam = scene3d(7, 20000, margin=0.3, scale_factor=0.3)
+
+  def run(fn, device, dtype):
+    ts = [t.detach().clone().to(device=device, dtype=dtype).requires_grad_(True) for t in
+          (*g.shape_tensors(), cam.T_camera_world, cam.projection)]
+    pts, depth, idx = fn(*ts, cam.image_size, cam.depth_range, blur_cov=0.3)
+    w = torch.linspace(0.5, 1.5, 7, dtype=dtype, device=device)
+    ((pts * w).sum() * 1e-3 + depth.sum() * 1e-3).backward()
+    return idx, [t.grad for t in ts]
+
+  i1, g1 = run(gpu_proj.apply, cuda_device, torch.float32)
+  i2, g2 = run(torch_ref.projection_apply, "cpu", torch.float64)
+  for a, b in zip(g1, g2):
+    assert rel_l2(a, b) < GRAD_REL_L2
+
+
+def test_projection_gradcheck_f64(cuda_device):
+  for seed in range(5):
+    g, cam = scene3d(200 + seed, 12, margin=0.2, scale_factor=0.3)
+    ts = [t.detach().clone().to(device=cuda_device, dtype=torch.float64).requires_grad_(True) for t in
+          (*g.shape_tensors(), cam.T_camera_world, cam.projection)]
+
+    def f(*a):
+      pts, depth, _ = gpu_proj.apply(*a, cam.image_size, cam.depth_range, blur_cov=0.3)
+      return pts, depth
+    assert torch.autograd.gradcheck(f, ts, eps=1e-6, atol=1e-5, nondet_tol=1e-9)
+
+
+def test_projection_empty_and_all_culled(cuda_device):
+  g, cam = scene3d(3, 10)
+  gc, cc = g.to(device=cuda_device), cam.to(device=cuda_device)
+  p, d, i = gpu_proj.apply(*[t[:0] for t in gc.shape_tensors()], cc.T_camera_world, cc.projection, cc.image_size,
+                           cc.depth_range)
+  assert p.shape == (0, 7) and d.shape == (0, 1) and i.shape == (0,)
+  far = gc.position + 1e6
+  p, d, i = gpu_proj.apply(far, *gc.shape_tensors()[1:], cc.T_camera_world, cc.projection, cc.image_size, cc.depth_range)
+  assert i.shape == (0,)
+
+
+def sh_inputs(seed, dtype, max_n=100, max_dim=3, max_deg=3):
+  torch.manual_seed(seed)
+  dim = int(torch.randint(1, max_dim + 1, (1,)))
+  deg = int(torch.randint(0, max_deg + 1, (1,)))
+  n = int(torch.randint(1, max_n + 2, (1,)))
+  params = torch.rand(n, dim, (deg + 1) ** 2, dtype=dtype)
+  points = torch.randn(n, 3, dtype=dtype)
+  cam = torch.randn(3, dtype=dtype)
+  idx = torch.randint(0, n, (max(n // 2, 1),))
+  return params, points, idx, cam
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_sh_vs_torch_with_grads(cuda_device, seed):
+  params, points, idx, cam = sh_inputs(seed, torch.float32)
+
+  def run(fn, device):
+    ts = [params.clone().to(device).requires_grad_(True), points.clone().to(device).requires_grad_(True),
+          cam.clone().to(device).requires_grad_(True)]
+    out = fn(ts[0], ts[1], idx.to(device), ts[2])
+    out.mean().backward()
+    return out, [t.grad for t in ts]
+
+  o1, g1 = run(evaluate_sh_at, cuda_device)
+  o2, g2 = run(torch_ref.evaluate_sh_at, "cpu")
+  assert torch.allclose(o1.cpu(), o2, atol=1e-5)
+  assert torch.allclose(o1.cpu(), oracle.evaluate_sh_at(params, points, idx, cam), atol=1e-5)
+  for a, b in zip(g1, g2):
+    assert torch.allclose(a.cpu(), b, atol=1e-5)
+
+
+def test_sh_gradcheck_f64(cuda_device):
+  for seed in range(40, 50):
+    params, points, idx, cam = sh_inputs(seed, torch.float64, max_n=10, max_dim=2)
+    params = params * 0.3   # keep most outputs inside the clamp
+    ts = [t.to(cuda_device).requires_grad_(True) for t in (params, points, cam)]
+    i = idx.to(cuda_device)
+    assert torch.autograd.gradcheck(lambda p, x, c: evaluate_sh_at(p, x, i, c), ts, eps=1e-6, atol=1e-5,
+                                    nondet_tol=1e-9)

@@ -1,0 +1,89 @@
+"""map_to_tiles on the GPU: overlap lists, sorted orderings and tile ranges bit-exact against the oracle
+(north_star: "tile overlap lists and sorted orderings are bit-exact")."""
+import pytest
+import torch
+
+import oracle
+from taichi_gaussian_rasterizer_b200 import RasterConfig, map_to_tiles
+from util import scene2d
+
+pytestmark = pytest.mark.gpu
+
+
+def check(cuda_device, g, depth, size, cfg, depth16=False):
+  o2p_ref, ranges_ref = oracle.map_to_tiles(g, depth, size, cfg, use_depth16=depth16)
+  o2p, ranges = map_to_tiles(g.to(cuda_device), depth.to(cuda_device), size, cfg, use_depth16=depth16)
+  assert o2p.dtype == torch.int32 and ranges.dtype == torch.int32
+  assert ranges.shape == ranges_ref.shape
+  assert o2p.shape == o2p_ref.shape, f"K differs: {o2p.shape} vs {o2p_ref.shape}"
+  assert torch.equal(ranges.cpu(), ranges_ref)
+  assert torch.equal(o2p.cpu(), o2p_ref)
+  return o2p, ranges
+
+
+@pytest.mark.parametrize("seed,n,size,ts,scale", [
+  (0, 1000, (320, 200), 16, 1.0),
+  (1, 5000, (333, 257), 16, 3.0),      # image not a multiple of the tile
+  (2, 2000, (256, 256), 8, 2.0),
+  (3, 3000, (640, 480), 32, 4.0),
+  (4, 50, (1024, 768), 16, 60.0),      # screen filling gaussians: warp-cooperative spans
+  (5, 20000, (1024, 1024), 16, 0.5),   # BASELINE config 1 shape
+])
+def test_bit_exact_vs_oracle(cuda_device, seed, n, size, ts, scale):
+  cfg = RasterConfig(tile_size=ts)
+  g, depth, _ = scene2d(seed, n, size, scale_factor=scale)
+  check(cuda_device, g, depth, size, cfg)
+
+
+def test_depth16_and_ties(cuda_device):
+  cfg = RasterConfig()
+  size = (320, 200)
+  g, depth, _ = scene2d(9, 4000, size, scale_factor=2.0)
+  depth[::5] = depth[2]
+  check(cuda_device, g, depth, size, cfg, depth16=False)
+  check(cuda_device, g, depth, size, cfg, depth16=True)
+
+
+def test_edge_cases(cuda_device):
+  cfg = RasterConfig()
+  size = (100, 60)
+  o2p, ranges = map_to_tiles(torch.zeros((0, 7), device=cuda_device), torch.zeros((0, 1), device=cuda_device), size, cfg)
+  assert o2p.shape == (0,) and ranges.shape == (4, 7, 2) and int(ranges.abs().sum()) == 0
+  g = torch.tensor([[50., 30., 1., 0., 5., 3., 0.001],       # alpha below threshold: no overlaps
+                    [1e6, 1e6, 1., 0., 5., 3., 0.5],          # far off screen
+                    [50., 30., 0.6, 0.8, 400., 300., 0.9],    # covers everything
+                    [-500., 30., 1., 0., 2., 2., 0.9],
+                    [99.5, 59.5, 0., 1., 0.4, 0.2, 0.9]])     # tiny, in the last partial tile
+  depth = torch.tensor([[0.5], [0.1], [0.9], [0.2], [0.0]])
+  check(cuda_device, g, depth, size, cfg)
+  # nothing overlaps at all
+  g2 = g[:2].clone()
+  o2p, ranges = check(cuda_device, g2, depth[:2], size, cfg)
+  assert o2p.shape == (0,)
+
+
+def test_too_many_tiles_is_rejected(cuda_device):
+  cfg = RasterConfig(tile_size=8)
+  with pytest.raises(AssertionError, match="exceed maximum tile count"):
+    map_to_tiles(torch.rand(4, 7, device=cuda_device), torch.rand(4, 1, device=cuda_device), (4096, 2048), cfg)
+
+
+def test_large_scene_properties(cuda_device):
+  """Full-size property check (no oracle): ranges partition [0, K), keys sorted per tile."""
+  cfg = RasterConfig()
+  size = (2048, 1365)
+  g, depth, _ = scene2d(21, 1_000_000, size, scale_factor=1.0)
+  o2p, ranges = map_to_tiles(g.to(cuda_device), depth.to(cuda_device), size, cfg)
+  r = ranges.view(-1, 2).cpu().long()
+  K = o2p.shape[0]
+  nonempty = r[:, 1] > r[:, 0]
+  starts, ends = r[nonempty, 0], r[nonempty, 1]
+  assert int(starts[0]) == 0 and int(ends[-1]) == K
+  assert torch.equal(starts[1:], ends[:-1])
+  d = depth.view(-1)[o2p.cpu().long()]
+  # depth non-decreasing inside every tile: check all boundaries at once
+  same_tile = torch.ones(K - 1, dtype=torch.bool)
+  same_tile[(ends[:-1] - 1)] = False
+  assert bool(((d[1:] >= d[:-1]) | ~same_tile).all())
+  counts = oracle.tile_counts(g, size, cfg)
+  assert int(counts.sum()) == K
