@@ -15,54 +15,121 @@
 // Per pixel state lives in registers; F is a template parameter (1..7 here, wider F takes raster_generic.cu).
 #include "raster_fast.cuh"
 
+#include <stdlib.h>
+
 namespace gs {
 
 constexpr int kBwdBatch = 64;
-constexpr int kBwdThreads = 64;
 
-// Transposed butterfly: on return v[0] of lane L holds the warp total of input value (L >> 1).
-template <int NV>
-__device__ __forceinline__ void warp_reduce_scatter(float (&v)[NV], int lane) {
-  static_assert(NV == 16, "16 values");
+// Transposed butterfly over NV per-lane partial sums: every exchange step halves the number of live values
+// (the lane keeps the half selected by its lane bit and adds the partner's copy of it), so NV values cost about
+// NV shuffles instead of 5 NV.  reduce_owner<NV>(lane) tells which value ends up, fully summed, in v[0] of a lane.
+template <int N, int OFF>
+__device__ __forceinline__ void reduce_scatter_step(float* v, int lane) {
+  if constexpr (OFF >= 1) {
+    if constexpr (N > 1) {
+      constexpr int H = (N + 1) / 2;
+      const bool upper = (lane & OFF) != 0;
 #pragma unroll
-  for (int half = NV / 2, off = 16; half >= 1; half >>= 1, off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const float send = upper ? v[i] : v[i + half];
-      const float keep = upper ? v[i + half] : v[i];
-      v[i] = keep + __shfl_xor_sync(kFull, send, off);
+      for (int i = 0; i < H; ++i) {
+        const float hi = (i + H < N) ? v[i + H] : 0.f;
+        const float send = upper ? v[i] : hi;
+        const float keep = upper ? hi : v[i];
+        v[i] = keep + __shfl_xor_sync(kFull, send, OFF);
+      }
+      reduce_scatter_step<H, OFF / 2>(v, lane);
+    } else {
+      v[0] += __shfl_xor_sync(kFull, v[0], OFF);
+      reduce_scatter_step<1, OFF / 2>(v, lane);
     }
   }
-  v[0] += __shfl_xor_sync(kFull, v[0], 1);
 }
 
-template <int F, int FP, bool HEUR>
-__global__ void __launch_bounds__(kBwdThreads)
+template <int NV>
+__device__ __forceinline__ int reduce_owner(int lane) {
+  int base = 0, cnt = NV, n = NV;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    if (n > 1) {
+      const int half = (n + 1) / 2;
+      if (lane & off) { base += half; cnt = max(cnt - half, 0); }
+      else cnt = min(cnt, half);
+      n = half;
+    } else if (lane & off) {
+      cnt = 0;
+    }
+  }
+  return cnt == 1 ? base : -1;
+}
+
+// The ellipse alpha0 p = thr in the form q(d) = d^T A d = qlim (log2 domain), for the block tests.
+struct CullConic {
+  float mx, my, A00, A01, A11, r00, r11, qlim;
+};
+
+__device__ __forceinline__ CullConic make_cull_conic(const float4 r0, const float4 r1, float l2thr) {
+  CullConic c;
+  const float cx = kSqrtHalfLog2e * r1.x, cy = kSqrtHalfLog2e * r1.y;
+  const float a1x = r0.z * cx, a1y = r0.w * cx, a2x = -r0.w * cy, a2y = r0.z * cy;
+  c.mx = r0.x; c.my = r0.y;
+  c.A00 = a1x * a1x + a2x * a2x; c.A01 = a1x * a1y + a2x * a2y; c.A11 = a1y * a1y + a2y * a2y;
+  c.r00 = fast_rcp(c.A00); c.r11 = fast_rcp(c.A11);
+  c.qlim = (log2f(r1.z) - l2thr) * 1.001f + 1e-3f;
+  return c;
+}
+
+// Exact minimum of q over the rectangle of pixel centres [x0, x1] x [y0, y1] (see block_may_touch).
+__device__ __forceinline__ bool conic_may_touch(const CullConic& c, float x0, float x1, float y0, float y1) {
+  const float dx0 = x0 - c.mx, dx1 = x1 - c.mx, dy0 = y0 - c.my, dy1 = y1 - c.my;
+  const float dxc = fminf(fmaxf(0.f, dx0), dx1);
+  const float dyc = fminf(fmaxf(0.f, dy0), dy1);
+  const float dyv = fminf(fmaxf(-c.A01 * dxc * c.r11, dy0), dy1);
+  const float qv = c.A00 * dxc * dxc + 2.f * c.A01 * dxc * dyv + c.A11 * dyv * dyv;
+  const float dxh = fminf(fmaxf(-c.A01 * dyc * c.r00, dx0), dx1);
+  const float qh = c.A00 * dxh * dxh + 2.f * c.A01 * dxh * dyc + c.A11 * dyc * dyc;
+  return fminf(qv, qh) < c.qlim;
+}
+
+// NSUB = 4: two warps per tile, each owns a 16x8 region; NSUB = 8: one warp owns the whole 16x16 tile.
+// A region is NSUB sub-blocks of 8x4 pixels; lane l owns pixel (l & 7, l >> 3) of every sub-block.
+template <int F, int FP, bool HEUR, int NSUB>
+__global__ void __launch_bounds__((8 / NSUB) * 32)
 raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
                        const float* __restrict__ featP, const int32_t* __restrict__ ranges,
                        const int32_t* __restrict__ o2p, const float* __restrict__ image,
                        const float* __restrict__ grad_image, float* __restrict__ grad_pts,
                        float* __restrict__ grad_feat, float* __restrict__ heuristic) {
+  constexpr int kThreads = (8 / NSUB) * 32;
+  constexpr int NV = 7 + F + (HEUR ? 2 : 0);
   __shared__ __align__(16) float4 s_r0[2][kBwdBatch];
   __shared__ __align__(16) float4 s_r1[2][kBwdBatch];
   __shared__ __align__(16) float s_feat[2][kBwdBatch][FP];
 
   const int tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int tw = (p.image_width + kFastTile - 1) / kFastTile;
-  const int ox = (tile % tw) * kFastTile, oy = (tile / tw) * kFastTile + warp * 8;
-  const int x0 = ox + 2 * (lane & 7), y0 = oy + 2 * (lane >> 3);
-  const float bx0 = (float)ox + 0.5f, bx1 = (float)ox + 15.5f, by0 = (float)oy + 0.5f, by1 = (float)oy + 7.5f;
+  const int ox = (tile % tw) * kFastTile, oy = (tile / tw) * kFastTile + warp * (NSUB * 2);
+  const int x0 = ox + (lane & 7), y0 = oy + (lane >> 3);
+  const float px0 = (float)x0 + 0.5f, py0 = (float)y0 + 0.5f;
+  const float bx = (float)ox + 0.5f, by = (float)oy + 0.5f;
   const float thr = (float)p.alpha_threshold, cmax = (float)p.clamp_max_alpha, sat = (float)p.saturate_threshold;
   const float l2thr = log2f(thr);
-  const bool pg = p.points_requires_grad && grad_pts != nullptr;
-  const bool fg = p.features_requires_grad && grad_feat != nullptr;
 
-  float W[4], R[4][F], Gd[4][F], pxf[4], pyf[4];
+  // which reduced value this lane commits, and where
+  const int own = reduce_owner<NV>(lane);
+  float* own_base = nullptr;
+  int own_stride = 0;
+  if (own >= 0 && own < 7) {
+    if (p.points_requires_grad && grad_pts != nullptr) { own_base = grad_pts + own; own_stride = 7; }
+  } else if (own >= 7 && own < 7 + F) {
+    if (p.features_requires_grad && grad_feat != nullptr) { own_base = grad_feat + (own - 7); own_stride = F; }
+  } else if (HEUR && own >= 7 + F && own < NV) {
+    own_base = heuristic + (own - 7 - F); own_stride = 2;
+  }
+
+  float W[NSUB], R[NSUB][F], Gd[NSUB][F];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int px = x0 + (i & 1), py = y0 + (i >> 1);
-    pxf[i] = (float)px + 0.5f; pyf[i] = (float)py + 0.5f;
+  for (int i = 0; i < NSUB; ++i) {
+    const int px = x0 + 8 * (i & 1), py = y0 + 4 * (i >> 1);
     const bool inb = px < p.image_width && py < p.image_height;
     W[i] = inb ? 0.f : 1.f;
     const int64_t pix = (int64_t)py * p.image_width + px;
@@ -79,18 +146,26 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
 
   auto issue_load = [&](int b) {
     const int buf = b & 1;
-    const int v = b * kBwdBatch + t;
-    if (v < C) {
-      const int idx = o2p[start + v];
-      cp_async16(&s_r0[buf][t], rec + 2 * (int64_t)idx);
-      cp_async16(&s_r1[buf][t], rec + 2 * (int64_t)idx + 1);
 #pragma unroll
-      for (int c = 0; c < FP; c += 4) cp_async16(&s_feat[buf][t][c], featP + (int64_t)idx * FP + c);
+    for (int s = t; s < kBwdBatch; s += kThreads) {
+      const int v = b * kBwdBatch + s;
+      if (v < C) {
+        const int idx = o2p[start + v];
+        cp_async16(&s_r0[buf][s], rec + 2 * (int64_t)idx);
+        cp_async16(&s_r1[buf][s], rec + 2 * (int64_t)idx + 1);
+#pragma unroll
+        for (int c = 0; c < FP; c += 4) cp_async16(&s_feat[buf][s][c], featP + (int64_t)idx * FP + c);
+      }
     }
     cp_async_commit();
   };
 
-  auto lane_done = [&]() { return W[0] >= sat && W[1] >= sat && W[2] >= sat && W[3] >= sat; };
+  auto lane_done = [&]() {
+    bool d = true;
+#pragma unroll
+    for (int i = 0; i < NSUB; ++i) d = d && (W[i] >= sat);
+    return d;
+  };
   bool warp_done = __all_sync(kFull, lane_done());
   if (nb > 0) issue_load(0);
   for (int b = 0; b < nb; ++b) {
@@ -106,17 +181,30 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
     if (!warp_done) {
       for (int c0 = 0; c0 < n_in; c0 += 32) {
         const int e = c0 + lane;
-        bool hit = false;
-        if (e < n_in) {
-          const float4 r0 = s_r0[buf][e], r1 = s_r1[buf][e];
-          const float cx = kSqrtHalfLog2e * r1.x, cy = kSqrtHalfLog2e * r1.y;
-          hit = block_may_touch(r0.x, r0.y, r0.z * cx, r0.w * cx, -r0.w * cy, r0.z * cy, log2f(r1.z) - l2thr, bx0,
-                                bx1, by0, by1);
+        // lane-parallel cull: gaussian e against each of the region's sub-blocks
+        unsigned bm[NSUB];
+        {
+          bool hit[NSUB];
+#pragma unroll
+          for (int i = 0; i < NSUB; ++i) hit[i] = false;
+          if (e < n_in) {
+            const CullConic cc = make_cull_conic(s_r0[buf][e], s_r1[buf][e], l2thr);
+#pragma unroll
+            for (int i = 0; i < NSUB; ++i) {
+              const float sx0 = bx + 8.f * (i & 1), sy0 = by + 4.f * (i >> 1);
+              hit[i] = conic_may_touch(cc, sx0, sx0 + 7.f, sy0, sy0 + 3.f);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < NSUB; ++i) bm[i] = __ballot_sync(kFull, hit[i]);
         }
-        unsigned mask = __ballot_sync(kFull, hit);
-        while (mask) {
-          const int j = c0 + __ffs(mask) - 1;
-          mask &= mask - 1;
+        unsigned any = 0;
+#pragma unroll
+        for (int i = 0; i < NSUB; ++i) any |= bm[i];
+        while (any) {
+          const int jl = __ffs(any) - 1;
+          any &= any - 1;
+          const int j = c0 + jl;
           const float4 r0 = s_r0[buf][j], r1 = s_r1[buf][j];
           const float mx = r0.x, my = r0.y, ax = r0.z, ay = r0.w, isx = r1.x, isy = r1.y, a0 = r1.z;
           float f[F];
@@ -128,60 +216,55 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
 #pragma unroll
           for (int c = 0; c < F; ++c) gf[c] = 0.f;
           bool has_grad = false;
+          const float dxb = px0 - mx, dyb = py0 - my;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float dx = pxf[i] - mx, dy = pyf[i] - my;
-            const float tx = fmaf(dy, ay, dx * ax) * isx;
-            const float ty = fmaf(dy, ax, -dx * ay) * isy;
-            const float q = fmaf(ty, ty, tx * tx);
-            const float pgauss = fast_ex2(-kHalfLog2e * q);
-            float alpha = a0 * pgauss;
-            if (alpha > thr && W[i] < sat) {
-              has_grad = true;
-              alpha = fminf(alpha, cmax);
-              const float Ti = 1.f - W[i];
-              const float w = alpha * Ti;
-              W[i] += w;
-              const float rinv = fast_rcp(1.f - alpha);
-              float ag = 0.f;
+          for (int i = 0; i < NSUB; ++i) {
+            if ((bm[i] >> jl) & 1u) {  // warp-uniform: this sub-block can be reached at all
+              const float dx = dxb + 8.f * (i & 1), dy = dyb + 4.f * (i >> 1);
+              const float tx = fmaf(dy, ay, dx * ax) * isx;
+              const float ty = fmaf(dy, ax, -dx * ay) * isy;
+              const float q = fmaf(ty, ty, tx * tx);
+              const float pgauss = fast_ex2(-kHalfLog2e * q);
+              float alpha = a0 * pgauss;
+              if (alpha > thr && W[i] < sat) {
+                has_grad = true;
+                alpha = fminf(alpha, cmax);
+                const float Ti = 1.f - W[i];
+                const float w = alpha * Ti;
+                W[i] += w;
+                const float rinv = fast_rcp(1.f - alpha);
+                float ag = 0.f;
 #pragma unroll
-              for (int c = 0; c < F; ++c) {
-                R[i][c] = fmaf(-f[c], w, R[i][c]);
-                const float diff = fmaf(f[c], Ti, -R[i][c] * rinv);
-                ag = fmaf(diff, Gd[i][c], ag);
-                gf[c] = fmaf(w, Gd[i][c], gf[c]);
-              }
-              const float aag = a0 * ag;
-              const float g = aag * pgauss;
-              const float a = g * tx * isx, bq = g * ty * isy;
-              U += a; V += bq;
-              Sx = fmaf(a, tx, Sx); Sy = fmaf(bq, ty, Sy);
-              Ax -= fmaf(a, dx, bq * dy);
-              Ay += fmaf(bq, dx, -a * dy);
-              Ga = fmaf(pgauss, ag, Ga);
-              if (HEUR) {
-                h0 = fmaf(aag, aag, h0);
-                h1 += fabsf(fmaf(a, ax, -bq * ay)) + fabsf(fmaf(a, ay, bq * ax));
+                for (int c = 0; c < F; ++c) {
+                  R[i][c] = fmaf(-f[c], w, R[i][c]);
+                  const float diff = fmaf(f[c], Ti, -R[i][c] * rinv);
+                  ag = fmaf(diff, Gd[i][c], ag);
+                  gf[c] = fmaf(w, Gd[i][c], gf[c]);
+                }
+                const float aag = a0 * ag;
+                const float g = aag * pgauss;
+                const float a = g * tx * isx, bq = g * ty * isy;
+                U += a; V += bq;
+                Sx = fmaf(a, tx, Sx); Sy = fmaf(bq, ty, Sy);
+                Ax -= fmaf(a, dx, bq * dy);
+                Ay += fmaf(bq, dx, -a * dy);
+                Ga = fmaf(pgauss, ag, Ga);
+                if (HEUR) {
+                  h0 = fmaf(aag, aag, h0);
+                  h1 += fabsf(fmaf(a, ax, -bq * ay)) + fabsf(fmaf(a, ay, bq * ax));
+                }
               }
             }
           }
           if (__any_sync(kFull, has_grad)) {
-            float v[16];
+            float v[NV];
             v[0] = fmaf(ax, U, -ay * V); v[1] = fmaf(ay, U, ax * V);
             v[2] = Ax; v[3] = Ay; v[4] = Sx; v[5] = Sy; v[6] = Ga;
 #pragma unroll
             for (int c = 0; c < F; ++c) v[7 + c] = gf[c];
             if (HEUR) { v[7 + F] = h0; v[8 + F] = h1; }
-#pragma unroll
-            for (int k = 7 + F + (HEUR ? 2 : 0); k < 16; ++k) v[k] = 0.f;
-            warp_reduce_scatter<16>(v, lane);
-            const int vi = lane >> 1;
-            const int64_t idx = __float_as_int(r1.w);
-            if ((lane & 1) == 0) {
-              if (vi < 7) { if (pg) atomicAdd(grad_pts + idx * 7 + vi, v[0]); }
-              else if (vi < 7 + F) { if (fg) atomicAdd(grad_feat + idx * F + (vi - 7), v[0]); }
-              else if (HEUR && vi < 9 + F) atomicAdd(heuristic + idx * 2 + (vi - 7 - F), v[0]);
-            }
+            reduce_scatter_step<NV, 16>(v, lane);
+            if (own_base != nullptr) atomicAdd(own_base + (int64_t)__float_as_int(r1.w) * own_stride, v[0]);
           }
         }
       }
@@ -192,19 +275,26 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
   cp_async_wait<0>();
 }
 
+static int bwd_nsub() {
+  static int v = [] {
+    const char* e = getenv("GS_BWD_NSUB");
+    return (e && atoi(e) == 8) ? 8 : 4;
+  }();
+  return v;
+}
+
 template <int F, int FP>
 static int launch_bwd_fast(const GsRasterParams& p, const RasterArgs& a, const float4* rec, const float* featP,
                            cudaStream_t st) {
   const int tiles = tiles_wide(p) * tiles_high(p);
   const bool heur = p.compute_point_heuristic && a.point_heuristic != nullptr;
-  if (heur)
-    raster_bwd_fast_kernel<F, FP, true><<<tiles, kBwdThreads, 0, st>>>(
-        p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,
-        (float*)a.grad_gaussians, (float*)a.grad_features, (float*)a.point_heuristic);
-  else
-    raster_bwd_fast_kernel<F, FP, false><<<tiles, kBwdThreads, 0, st>>>(
-        p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,
-        (float*)a.grad_gaussians, (float*)a.grad_features, nullptr);
+#define GS_BWD_LAUNCH(HEURV, NSUBV)                                                                              \
+  raster_bwd_fast_kernel<F, FP, HEURV, NSUBV><<<tiles, (8 / NSUBV) * 32, 0, st>>>(                              \
+      p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,   \
+      (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr)
+  if (bwd_nsub() == 8) { if (heur) GS_BWD_LAUNCH(true, 8); else GS_BWD_LAUNCH(false, 8); }
+  else { if (heur) GS_BWD_LAUNCH(true, 4); else GS_BWD_LAUNCH(false, 4); }
+#undef GS_BWD_LAUNCH
   GS_LAUNCH_CHECK();
   return GS_OK;
 }
