@@ -80,6 +80,8 @@ typedef struct GsSHParams {
   int32_t dtype;
   int32_t num_channels;    /* K */
   int32_t num_coeffs;      /* D = (degree+1)^2, degree 0..3 */
+  int32_t indexes_sorted_unique; /* hint: indexes strictly ascending (the visible set of gs_project_fwd); lets
+                                    gs_sh_bwd write dense gradient rows without atomics.  0 = no assumption. */
   int64_t num_points;      /* M */
   int64_t num_indexes;     /* V */
 } GsSHParams;

@@ -33,7 +33,8 @@ class GsProjectParams(ctypes.Structure):
 
 class GsSHParams(ctypes.Structure):
   _fields_ = [("dtype", ctypes.c_int32), ("num_channels", ctypes.c_int32), ("num_coeffs", ctypes.c_int32),
-              ("num_points", ctypes.c_int64), ("num_indexes", ctypes.c_int64)]
+              ("indexes_sorted_unique", ctypes.c_int32), ("num_points", ctypes.c_int64),
+              ("num_indexes", ctypes.c_int64)]
 
 
 class GsTileParams(ctypes.Structure):

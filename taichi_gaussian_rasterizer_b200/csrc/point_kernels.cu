@@ -170,6 +170,134 @@ sh_bwd_kernel(const __grid_constant__ GsSHParams p, const T* __restrict__ params
   }
 }
 
+// Dense SH backward for the render path: `indexes` strictly ascending (the visible set that gs_project_fwd
+// compacts), f32, K*D a multiple of 4.  A block owns 128 consecutive visible points AND every gaussian row
+// between them: coefficient rows are staged to shared memory with coalesced 16 B loads (12 lanes per 192 B row),
+// each thread turns its row into the gradient row in place, and the rows go back with coalesced 16 B stores.
+// Rows of culled gaussians inside the block's span are zero-filled by the same block (FILL), so grad_params /
+// grad_positions need no memset and no atomics: 2 x 4 K D bytes per gaussian of traffic in total.
+constexpr int kSHDenseBlock = 128;
+
+template <int K, int D, bool FILL>
+__global__ void __launch_bounds__(kSHDenseBlock)
+sh_bwd_dense_kernel(const __grid_constant__ GsSHParams p, const float* __restrict__ params,
+                    const float* __restrict__ positions, const int64_t* __restrict__ indexes,
+                    const float* __restrict__ cam, const float* __restrict__ grad_out, float* __restrict__ grad_params,
+                    float* __restrict__ grad_positions, float* __restrict__ grad_cam) {
+  constexpr int RL = K * D, R4 = RL / 4, S4 = (R4 + 1) | 1;  // odd float4 stride: conflict-free LDS.128 per thread
+  static_assert(RL % 4 == 0, "row length must be a multiple of 4 floats");
+  __shared__ float4 s_row[kSHDenseBlock * S4];
+  __shared__ int64_t s_idx[kSHDenseBlock + 1];
+  __shared__ float s_red[3][kSHDenseBlock / 32];
+
+  const int t = threadIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.x * kSHDenseBlock;
+  const int nrows = (int)min((int64_t)kSHDenseBlock, p.num_indexes - i0);
+  const bool last_block = i0 + nrows == p.num_indexes;
+  if (t < nrows) s_idx[t + 1] = indexes[i0 + t];
+  if (t == 0) s_idx[0] = i0 > 0 ? indexes[i0 - 1] : -1;
+  __syncthreads();
+
+  {  // R4 independent 16 B loads in flight per thread
+    float4 v[R4];
+#pragma unroll
+    for (int m = 0; m < R4; ++m) {
+      const int q = t + m * kSHDenseBlock, r = q / R4, part = q - r * R4;
+      if (q < nrows * R4) v[m] = __ldg(reinterpret_cast<const float4*>(params + s_idx[r + 1] * RL) + part);
+    }
+#pragma unroll
+    for (int m = 0; m < R4; ++m) {
+      const int q = t + m * kSHDenseBlock, r = q / R4, part = q - r * R4;
+      if (q < nrows * R4) s_row[r * S4 + part] = v[m];
+    }
+  }
+  __syncthreads();
+
+  float gpx = 0.f, gpy = 0.f, gpz = 0.f;
+  if (t < nrows) {
+    const int64_t idx = s_idx[t + 1];
+    const int64_t i = i0 + t;
+    const float dx = positions[3 * idx] - cam[0], dy = positions[3 * idx + 1] - cam[1],
+                dz = positions[3 * idx + 2] - cam[2];
+    const float inv = rsqrt_<float>(dx * dx + dy * dy + dz * dz);
+    const float x = dx * inv, y = dy * inv, z = dz * inv;
+    float b[D], gb[D];
+    sh_basis<float, D>(x, y, z, b);
+#pragma unroll
+    for (int j = 0; j < D; ++j) gb[j] = 0.f;
+    float4* row = s_row + t * S4;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float c[D];
+#pragma unroll
+      for (int j4 = 0; j4 < D / 4; ++j4) {
+        const float4 v = row[k * (D / 4) + j4];
+        c[4 * j4] = v.x; c[4 * j4 + 1] = v.y; c[4 * j4 + 2] = v.z; c[4 * j4 + 3] = v.w;
+      }
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) acc += b[j] * c[j];
+      const float v = acc + 0.5f;
+      const float g = (v > 0.f && v < 1.f) ? grad_out[i * K + k] : 0.f;  // clamp passes gradient strictly inside
+#pragma unroll
+      for (int j = 0; j < D; ++j) gb[j] += g * c[j];
+#pragma unroll
+      for (int j4 = 0; j4 < D / 4; ++j4)
+        row[k * (D / 4) + j4] = make_float4(g * b[4 * j4], g * b[4 * j4 + 1], g * b[4 * j4 + 2], g * b[4 * j4 + 3]);
+    }
+    if (grad_positions || grad_cam) {
+      float gx[D], gy[D], gz[D];
+      sh_basis_grad<float, D>(x, y, z, gx, gy, gz);
+      float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) { ddx += gb[j] * gx[j]; ddy += gb[j] * gy[j]; ddz += gb[j] * gz[j]; }
+      const float dot = ddx * x + ddy * y + ddz * z;
+      gpx = (ddx - x * dot) * inv; gpy = (ddy - y * dot) * inv; gpz = (ddz - z * dot) * inv;
+      if (grad_positions) {
+        grad_positions[3 * idx] = gpx; grad_positions[3 * idx + 1] = gpy; grad_positions[3 * idx + 2] = gpz;
+      }
+    }
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int m = 0; m < R4; ++m) {
+    const int q = t + m * kSHDenseBlock, r = q / R4, part = q - r * R4;
+    if (q < nrows * R4) reinterpret_cast<float4*>(grad_params + s_idx[r + 1] * RL)[part] = s_row[r * S4 + part];
+  }
+
+  if (FILL) {  // zero the rows of culled gaussians in (previous visible index, this block's last index] (+ the tail)
+    const bool my_gap = t < nrows && s_idx[t + 1] - s_idx[t] > 1;
+    const bool tail = last_block && s_idx[nrows] + 1 < p.num_points;
+    if (__syncthreads_or(my_gap) || tail) {
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r <= nrows; ++r) {
+        int64_t lo, hi;
+        if (r < nrows) { lo = s_idx[r] + 1; hi = s_idx[r + 1]; }
+        else if (tail) { lo = s_idx[nrows] + 1; hi = p.num_points; }
+        else break;
+        if (hi <= lo) continue;
+        float4* gp4 = reinterpret_cast<float4*>(grad_params + lo * RL);
+        for (int64_t q = t; q < (hi - lo) * R4; q += kSHDenseBlock) gp4[q] = z4;
+        if (grad_positions)
+          for (int64_t q = t; q < (hi - lo) * 3; q += kSHDenseBlock) grad_positions[lo * 3 + q] = 0.f;
+      }
+    }
+  }
+
+  if (grad_cam) {  // camera position receives minus the sum of the point gradients
+    const float sx = warp_sum(gpx), sy = warp_sum(gpy), sz = warp_sum(gpz);
+    const int lane = t & 31, warp = t >> 5;
+    if (lane == 0) { s_red[0][warp] = sx; s_red[1][warp] = sy; s_red[2][warp] = sz; }
+    __syncthreads();
+    if (t < 3) {
+      float s = 0.f;
+      for (int w = 0; w < kSHDenseBlock / 32; ++w) s += s_red[t][w];
+      if (s != 0.f) red_add(grad_cam + t, -s);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ projection bwd
 constexpr int kPBwdBlock = 128;
 
@@ -413,12 +541,27 @@ int gs_sh_bwd(const GsSHParams* p, const void* params, const void* positions, co
   if (rc != GS_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t es = p->dtype == GS_F32 ? 4 : 8;
-  if (grad_params)
+  const bool dense = p->indexes_sorted_unique && p->dtype == GS_F32 && grad_params != nullptr && p->num_indexes > 0 &&
+                     p->num_channels == 3 && (p->num_coeffs == 16 || p->num_coeffs == 4);
+  const bool fill = dense && 2 * p->num_indexes >= p->num_points;  // mostly visible: the kernel zero-fills the gaps
+  if (grad_params && !fill)
     GS_CUDA(cudaMemsetAsync(grad_params, 0, (size_t)p->num_points * p->num_channels * p->num_coeffs * es, st));
-  if (grad_positions) GS_CUDA(cudaMemsetAsync(grad_positions, 0, (size_t)p->num_points * 3 * es, st));
+  if (grad_positions && !fill) GS_CUDA(cudaMemsetAsync(grad_positions, 0, (size_t)p->num_points * 3 * es, st));
   if (grad_camera_pos) GS_CUDA(cudaMemsetAsync(grad_camera_pos, 0, 3 * es, st));
   if (p->num_indexes == 0) return GS_OK;
   GS_CHECK_ARG(params && positions && indexes && camera_pos && grad_out, "gs_sh_bwd: null tensor");
+  if (dense) {
+    const unsigned blocks = (unsigned)ceil_div(p->num_indexes, kSHDenseBlock);
+#define GS_SH_DENSE(DD, FILLV)                                                                                   \
+    sh_bwd_dense_kernel<3, DD, FILLV><<<blocks, kSHDenseBlock, 0, st>>>(                                         \
+        *p, (const float*)params, (const float*)positions, indexes, (const float*)camera_pos,                   \
+        (const float*)grad_out, (float*)grad_params, (float*)grad_positions, (float*)grad_camera_pos)
+    if (p->num_coeffs == 16) { if (fill) GS_SH_DENSE(16, true); else GS_SH_DENSE(16, false); }
+    else { if (fill) GS_SH_DENSE(4, true); else GS_SH_DENSE(4, false); }
+#undef GS_SH_DENSE
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+  }
   return p->dtype == GS_F32 ? sh_dispatch<float>(true, p, params, positions, indexes, camera_pos, grad_out,
                                                  grad_params, grad_positions, grad_camera_pos, st)
                             : sh_dispatch<double>(true, p, params, positions, indexes, camera_pos, grad_out,

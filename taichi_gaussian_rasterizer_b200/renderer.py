@@ -155,7 +155,7 @@ def render_gaussians(
 
   if use_sh:
     features = evaluate_sh_at(gaussians.feature, gaussians.position.detach(), indexes,
-                              camera_params.camera_position)
+                              camera_params.camera_position, indexes_sorted_unique=True)  # visible set: ascending
   else:
     features = gaussians.feature[indexes]
     assert len(features.shape) == 2, f"Features must be (N, C) if use_sh=False, got {features.shape}"

@@ -25,10 +25,10 @@ def check_sh_degree(sh_features):
 class _SHFunction(torch.autograd.Function):
 
   @staticmethod
-  def forward(ctx, params, points, indexes, camera_pos):
+  def forward(ctx, params, points, indexes, camera_pos, sorted_unique=False):
     m, k, d = params.shape
     v = indexes.shape[0]
-    p = N.GsSHParams(N.dtype_code(params.dtype), k, d, m, v)
+    p = N.GsSHParams(N.dtype_code(params.dtype), k, d, int(bool(sorted_unique)), m, v)
     out = torch.empty((v, k), dtype=params.dtype, device=params.device)
     N.call("gs_sh_fwd", ctypes.byref(p), N.ptr(params), N.ptr(points), N.ptr(indexes), N.ptr(camera_pos),
                               N.ptr(out), N.stream_ptr(params.device))
@@ -47,17 +47,22 @@ class _SHFunction(torch.autograd.Function):
     N.call("gs_sh_bwd", ctypes.byref(ctx.p), N.ptr(params), N.ptr(points), N.ptr(indexes),
                               N.ptr(camera_pos), N.ptr(doutput.contiguous()), N.ptr(g_params), N.ptr(g_points),
                               N.ptr(g_cam), N.stream_ptr(params.device))
-    return g_params, g_points, None, g_cam
+    return g_params, g_points, None, g_cam, None
 
 
 @beartype
 def evaluate_sh_at(sh_params: torch.Tensor,   # M, K, (degree + 1)^2  (usually K=3, for RGB)
                    positions: torch.Tensor,   # M, 3
                    indexes: torch.Tensor,     # V   (int64 indexes into the M gaussians)
-                   camera_pos: torch.Tensor   # 3
+                   camera_pos: torch.Tensor,  # 3
+                   indexes_sorted_unique: bool = False
                    ) -> torch.Tensor:         # V, K
+  """``indexes_sorted_unique`` (extension, not in the reference signature): promise that ``indexes`` is strictly
+  ascending, as the visible set returned by project_to_image is; the backward then writes dense gradient rows
+  without atomics or a memset (csrc/point_kernels.cu sh_bwd_dense_kernel).  Results are identical."""
   check_sh_degree(sh_params)
   N.require_cuda(sh_params, positions, indexes, camera_pos)
   dtype = sh_params.dtype
   return _SHFunction.apply(sh_params.contiguous(), positions.to(dtype).contiguous(),
-                           indexes.to(torch.int64).contiguous(), camera_pos.to(dtype).contiguous())
+                           indexes.to(torch.int64).contiguous(), camera_pos.to(dtype).contiguous(),
+                           indexes_sorted_unique)

@@ -144,3 +144,40 @@ def test_sh_gradcheck_f64(cuda_device):
     i = idx.to(cuda_device)
     assert torch.autograd.gradcheck(lambda p, x, c: evaluate_sh_at(p, x, i, c), ts, eps=1e-6, atol=1e-5,
                                     nondet_tol=1e-9)
+
+
+@pytest.mark.parametrize("n,keep,deg", [(1000, 0.97, 3), (1000, 0.3, 3), (517, 0.9, 1), (130, 1.0, 3), (5, 0.5, 3)])
+def test_sh_dense_backward_matches_generic(cuda_device, n, keep, deg):
+  """indexes_sorted_unique=True takes the atomic-free dense kernel (gap zero-fill when mostly visible, memset +
+  rows otherwise); its gradients must equal the generic scatter kernel's and the torch restatement's."""
+  torch.manual_seed(n + deg)
+  params = (torch.rand(n, 3, (deg + 1) ** 2) - 0.5) * 0.6
+  points = torch.randn(n, 3)
+  cam = torch.randn(3)
+  idx = torch.nonzero(torch.rand(n) < keep).squeeze(1)
+  if idx.numel() == 0:
+    idx = torch.tensor([n - 1])
+  gout = torch.randn(idx.shape[0], 3)
+
+  def run(fn, device, **kw):
+    ts = [params.clone().to(device).requires_grad_(True), points.clone().to(device).requires_grad_(True),
+          cam.clone().to(device).requires_grad_(True)]
+    out = fn(ts[0], ts[1], idx.to(device), ts[2], **kw)
+    loss = (out * gout.to(device)).sum()
+    if device != "cpu":   # poison the allocator's free blocks: the gradient buffers come from torch.empty_like
+      junk = [torch.full_like(ts[0], float("nan")), torch.full_like(ts[1], float("nan"))]
+      del junk
+    loss.backward()
+    return out, [t.grad for t in ts]
+
+  o_d, g_d = run(evaluate_sh_at, cuda_device, indexes_sorted_unique=True)
+  o_g, g_g = run(evaluate_sh_at, cuda_device)
+  o_t, g_t = run(torch_ref.evaluate_sh_at, "cpu")
+  assert torch.equal(o_d, o_g)
+  for a, b, c in zip(g_d, g_g, g_t):
+    assert torch.allclose(a, b, atol=1e-6), (a - b).abs().max()
+    assert torch.allclose(a.cpu(), c, atol=1e-5)
+  # rows of gaussians outside `indexes` are exactly zero (nothing left uninitialised by the gap fill)
+  mask = torch.ones(n, dtype=torch.bool)
+  mask[idx] = False
+  assert (g_d[0].cpu()[mask] == 0).all() and (g_d[1].cpu()[mask] == 0).all()
