@@ -179,7 +179,7 @@ sh_bwd_kernel(const __grid_constant__ GsSHParams p, const T* __restrict__ params
 constexpr int kSHDenseBlock = 128;
 
 template <int K, int D, bool FILL>
-__global__ void __launch_bounds__(kSHDenseBlock)
+__global__ void __launch_bounds__(kSHDenseBlock, 6)
 sh_bwd_dense_kernel(const __grid_constant__ GsSHParams p, const float* __restrict__ params,
                     const float* __restrict__ positions, const int64_t* __restrict__ indexes,
                     const float* __restrict__ cam, const float* __restrict__ grad_out, float* __restrict__ grad_params,
@@ -198,19 +198,17 @@ sh_bwd_dense_kernel(const __grid_constant__ GsSHParams p, const float* __restric
   if (t == 0) s_idx[0] = i0 > 0 ? indexes[i0 - 1] : -1;
   __syncthreads();
 
-  {  // R4 independent 16 B loads in flight per thread
-    float4 v[R4];
 #pragma unroll
-    for (int m = 0; m < R4; ++m) {
-      const int q = t + m * kSHDenseBlock, r = q / R4, part = q - r * R4;
-      if (q < nrows * R4) v[m] = __ldg(reinterpret_cast<const float4*>(params + s_idx[r + 1] * RL) + part);
-    }
-#pragma unroll
-    for (int m = 0; m < R4; ++m) {
-      const int q = t + m * kSHDenseBlock, r = q / R4, part = q - r * R4;
-      if (q < nrows * R4) s_row[r * S4 + part] = v[m];
+  for (int m = 0; m < R4; ++m) {  // R4 independent 16 B cp.async gathers in flight per thread, no staging registers
+    const int q = t + m * kSHDenseBlock, r = q / R4, part = q - r * R4;
+    if (q < nrows * R4) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_row[r * S4 + part]);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
+                   "l"(reinterpret_cast<const float4*>(params + s_idx[r + 1] * RL) + part) : "memory");
     }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   float gpx = 0.f, gpy = 0.f, gpz = 0.f;

@@ -1,0 +1,215 @@
+#!/usr/bin/env python
+"""Generates the golden fixtures of tests/golden/*.npz FROM THE REFERENCE ITSELF (needs /root/reference).
+
+  python tests/golden/make_golden.py [--only tile_map,raster,projection,sh] [--quick]
+
+Two sources, both the reference's own code, unmodified, imported from /root/reference:
+
+* the pure-torch implementation the reference's tests use as THEIR oracle
+  (taichi_splatting/torch_lib/projection.py ``apply``, torch_lib/spherical_harmonics.py ``evaluate_sh_at``):
+  outputs and autograd gradients in float64 -> projection.npz, sh.npz;
+* the reference's Taichi kernels executed by the emulator in ti_emu.py (Taichi itself is not installable
+  here): ``map_to_tiles`` (tile_overlaps / generate_sort_keys / find_ranges kernels + the OBB grid query),
+  ``rasterize_with_tiles`` forward and backward (rasterizer/forward.py, backward.py, incl. shared-memory
+  staging, warp votes and shuffle reductions), ``project_kernel`` and ``evaluate_sh_at_kernel`` forward
+  -> tile_map.npz, raster.npz and the ``ti_*`` entries of projection.npz / sh.npz.
+
+Inputs are produced by the reference's own generators (taichi_splatting/tests/random_data.py) with the seeds
+listed below and stored in the fixtures, so the tests in tests/test_golden.py need neither /root/reference nor
+the emulator.  Nothing from oracle/ or from the product package is used to make these files.
+"""
+import argparse
+import os
+import sys
+import time
+from pathlib import Path
+
+os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")   # the reference's @torch.compile helpers run eagerly (no Inductor here)
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE))
+
+import ti_emu  # noqa: E402
+
+ti_emu.install()
+
+from taichi_splatting.data_types import RasterConfig  # noqa: E402
+from taichi_splatting.mapper.tile_mapper import map_to_tiles  # noqa: E402
+from taichi_splatting.rasterizer.function import rasterize_with_tiles  # noqa: E402
+from taichi_splatting.misc.renderer2d import project_gaussians2d  # noqa: E402
+import taichi_splatting.perspective.projection as ti_proj  # noqa: E402
+import taichi_splatting.torch_lib.projection as torch_proj  # noqa: E402
+import taichi_splatting.torch_lib.spherical_harmonics as torch_sh  # noqa: E402
+import taichi_splatting.spherical_harmonics as ti_sh  # noqa: E402
+from taichi_splatting.tests.random_data import random_2d_gaussians, random_3d_gaussians, random_camera  # noqa: E402
+
+
+def np_(t):
+  return t.detach().cpu().numpy()
+
+
+def grad_(t):
+  return np_(t.grad if t.grad is not None else torch.zeros_like(t))   # no dependence (e.g. SH degree 0) = zero
+
+
+def scene2d(seed, n, image_size, channels, scale_factor, alpha_range=(0.1, 0.9)):
+  """The reference's 2D generator (tests/random_data.py:80-105) packed as rasterize() expects
+  (misc/renderer2d.py:17-33, examples/fit_image_gaussians.py:108-112)."""
+  torch.manual_seed(seed)
+  g = random_2d_gaussians(n, image_size, num_channels=channels, scale_factor=scale_factor, alpha_range=alpha_range)
+  packed = project_gaussians2d(g).to(torch.float32).contiguous()
+  return packed, g.z_depth.clamp(0, 1).to(torch.float32).contiguous(), g.feature.to(torch.float32).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------- tile map
+TILE_CASES = [  # seed, n, (w, h), tile_size, scale_factor, use_depth16
+  (0, 200, (70, 45), 8, 1.5, False),
+  (1, 300, (128, 96), 16, 1.5, False),
+  (2, 50, (33, 31), 16, 1.0, False),
+  (3, 400, (160, 100), 16, 3.0, False),
+  (4, 150, (64, 64), 32, 2.0, False),
+  (5, 250, (96, 64), 16, 1.5, True),
+  (6, 120, (40, 24), 8, 0.5, True),
+]
+
+
+def make_tile_map(out):
+  for i, (seed, n, size, ts, sf, d16) in enumerate(TILE_CASES):
+    g, depth, _ = scene2d(seed, n, size, 3, sf)
+    t0 = time.time()
+    o2p, ranges = map_to_tiles(g, depth, size, RasterConfig(tile_size=ts), use_depth16=d16)
+    print(f"tile_map case {i}: n={n} {size} tile {ts} depth16={d16} K={o2p.shape[0]} ({time.time() - t0:.1f}s)")
+    out.update({f"c{i}_gaussians": np_(g), f"c{i}_depth": np_(depth), f"c{i}_image_size": np.array(size),
+                f"c{i}_tile_size": np.array(ts), f"c{i}_use_depth16": np.array(int(d16)),
+                f"c{i}_overlap_to_point": np_(o2p), f"c{i}_tile_ranges": np_(ranges)})
+  out["num_cases"] = np.array(len(TILE_CASES))
+
+
+# ----------------------------------------------------------------------------------------------- rasterizer
+RASTER_CASES = [  # seed, n, (w, h), tile_size, pixel_stride, F, antialias, scale_factor
+  (0, 30, (16, 16), 8, (1, 1), 3, False, 1.5),
+  (1, 120, (16, 8), 8, (1, 1), 3, False, 1.5),     # tile lists longer than one block: stale shared slots (Q1)
+  (2, 60, (32, 32), 16, (2, 2), 3, False, 3.0),    # default tile / stride, 4 tiles
+  (3, 40, (16, 16), 8, (1, 1), 2, True, 1.5),      # antialiased pdf
+  (4, 90, (24, 13), 8, (1, 1), 1, False, 2.0),     # image not a multiple of the tile, F = 1
+  (5, 48, (16, 16), 16, (2, 2), 5, False, 4.0),    # F = 5 (depth + depth^2 + rgb)
+]
+QUICK_RASTER = [0, 3]
+
+
+def make_raster(out, quick=False):
+  cases = [c for i, c in enumerate(RASTER_CASES) if not quick or i in QUICK_RASTER]
+  for i, (seed, n, size, ts, stride, F, aa, sf) in enumerate(cases):
+    g, depth, feat = scene2d(seed, n, size, F, sf)
+    cfg = RasterConfig(tile_size=ts, pixel_stride=stride, antialias=aa, compute_visibility=True,
+                       compute_point_heuristic=True)
+    o2p, ranges = map_to_tiles(g, depth, size, cfg)
+    torch.manual_seed(1000 + seed)
+    grad_image = torch.rand(size[1], size[0], F)
+    gg, ff = g.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    t0 = time.time()
+    r = rasterize_with_tiles(gg, ff, o2p, ranges.view(-1, 2), size, cfg)
+    t1 = time.time()
+    (r.image * grad_image).sum().backward()
+    counts = ranges[..., 1] - ranges[..., 0]
+    print(f"raster case {i}: n={n} {size} tile {ts} stride {stride} F={F} aa={aa} max tile list {int(counts.max())} "
+          f"(fwd {t1 - t0:.0f}s bwd {time.time() - t1:.0f}s)")
+    out.update({f"c{i}_gaussians": np_(g), f"c{i}_features": np_(feat), f"c{i}_image_size": np.array(size),
+                f"c{i}_tile_size": np.array(ts), f"c{i}_pixel_stride": np.array(stride), f"c{i}_antialias": np.array(int(aa)),
+                f"c{i}_overlap_to_point": np_(o2p), f"c{i}_tile_ranges": np_(ranges), f"c{i}_grad_image": np_(grad_image),
+                f"c{i}_image": np_(r.image), f"c{i}_image_weight": np_(r.image_weight),
+                f"c{i}_visibility": np_(r.visibility), f"c{i}_point_heuristic": np_(r.point_heuristic),
+                f"c{i}_grad_gaussians": np_(gg.grad), f"c{i}_grad_features": np_(ff.grad)})
+  out["num_cases"] = np.array(len(cases))
+
+
+# ----------------------------------------------------------------------------------------------- projection
+PROJ_CASES = [  # seed, n, blur_cov  (generator arguments of tests/test_projection.py:24-34)
+  (0, 400, 0.0), (1, 700, 0.3), (2, 150, 0.3), (3, 1000, 0.0),
+]
+
+
+def make_projection(out):
+  for i, (seed, n, blur) in enumerate(PROJ_CASES):
+    torch.manual_seed(seed)
+    camera = random_camera()
+    gaussians = random_3d_gaussians(n=n, camera_params=camera, margin=0.5, scale_factor=0.1)
+    tensors32 = [gaussians.position, gaussians.log_scaling, gaussians.rotation, gaussians.alpha_logit,
+                 camera.T_camera_world, camera.projection]
+    tensors32 = [t.to(torch.float32).contiguous() for t in tensors32]
+    size, drange = tuple(int(x) for x in camera.image_size), tuple(float(x) for x in camera.depth_range)
+
+    # (a) the reference's torch implementation, float64, with autograd gradients
+    t64 = [t.to(torch.float64).clone().requires_grad_(True) for t in tensors32]
+    pts, depth, idx = torch_proj.apply(*t64, size, drange, blur_cov=blur)
+    torch.manual_seed(2000 + seed)
+    gp, gd = torch.randn_like(pts), torch.randn_like(depth)
+    ((pts * gp).sum() + (depth * gd).sum()).backward()
+    # (b) the reference's Taichi project_kernel (f32 and f64) under the emulator: forward only
+    ti32 = ti_proj.apply(*tensors32, size, drange, blur_cov=blur)
+    ti64 = ti_proj.apply(*[t.detach() for t in t64], size, drange, blur_cov=blur)
+    print(f"projection case {i}: n={n} blur={blur} visible torch {idx.shape[0]} taichi f32 {ti32[2].shape[0]} "
+          f"f64 {ti64[2].shape[0]}; max |taichi f64 - torch f64| = {(ti64[0] - pts).abs().max().item():.2e}")
+    names = ["position", "log_scaling", "rotation", "alpha_logit", "T_camera_world", "projection"]
+    for nm, t, t6 in zip(names, tensors32, t64):
+      out[f"c{i}_{nm}"] = np_(t)
+      out[f"c{i}_grad_{nm}"] = grad_(t6)
+    out.update({f"c{i}_image_size": np.array(size), f"c{i}_depth_range": np.array(drange), f"c{i}_blur_cov": np.array(blur),
+                f"c{i}_torch_points": np_(pts), f"c{i}_torch_depth": np_(depth), f"c{i}_torch_indexes": np_(idx),
+                f"c{i}_grad_out_points": np_(gp), f"c{i}_grad_out_depth": np_(gd),
+                f"c{i}_ti32_points": np_(ti32[0]), f"c{i}_ti32_depth": np_(ti32[1]), f"c{i}_ti32_indexes": np_(ti32[2]),
+                f"c{i}_ti64_points": np_(ti64[0]), f"c{i}_ti64_depth": np_(ti64[1]), f"c{i}_ti64_indexes": np_(ti64[2])})
+  out["num_cases"] = np.array(len(PROJ_CASES))
+
+
+# ----------------------------------------------------------------------------------------------- SH
+SH_CASES = [(0, 60, 3, 3), (1, 101, 3, 2), (2, 40, 1, 1), (3, 80, 2, 0), (4, 90, 3, 3)]  # seed, n, K, degree
+
+
+def make_sh(out):
+  for i, (seed, n, k, deg) in enumerate(SH_CASES):
+    torch.manual_seed(seed)
+    params = torch.rand(n, k, (deg + 1) ** 2)
+    points = torch.randn(n, 3)
+    cam = torch.randn(3)
+    idx = torch.randint(0, n, (max(n // 2, 1),))      # repeated indexes, as tests/test_spherical_harmonics.py
+    t64 = [t.to(torch.float64).clone().requires_grad_(True) for t in (params, points, cam)]
+    o = torch_sh.evaluate_sh_at(t64[0], t64[1], idx, t64[2])
+    torch.manual_seed(3000 + seed)
+    go = torch.randn_like(o)
+    (o * go).sum().backward()
+    ti32 = ti_sh.sh_function(deg, k, torch.float32).apply(params, points, idx, cam)
+    print(f"sh case {i}: n={n} K={k} degree={deg}; max |taichi f32 - torch f64| = "
+          f"{(ti32.double() - o).abs().max().item():.2e}")
+    out.update({f"c{i}_params": np_(params), f"c{i}_points": np_(points), f"c{i}_camera_pos": np_(cam),
+                f"c{i}_indexes": np_(idx), f"c{i}_torch_out": np_(o), f"c{i}_grad_out": np_(go),
+                f"c{i}_grad_params": grad_(t64[0]), f"c{i}_grad_points": grad_(t64[1]),
+                f"c{i}_grad_camera_pos": grad_(t64[2]), f"c{i}_ti32_out": np_(ti32)})
+  out["num_cases"] = np.array(len(SH_CASES))
+
+
+MAKERS = {"tile_map": make_tile_map, "projection": make_projection, "sh": make_sh, "raster": make_raster}
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--only", default=",".join(MAKERS))
+  ap.add_argument("--quick", action="store_true", help="raster: only the two cheapest cases")
+  args = ap.parse_args()
+  for name in args.only.split(","):
+    out = {}
+    t0 = time.time()
+    if name == "raster":
+      make_raster(out, quick=args.quick)
+    else:
+      MAKERS[name](out)
+    path = HERE / f"{name}.npz"
+    np.savez_compressed(path, **out)
+    print(f"wrote {path} ({path.stat().st_size / 1024:.0f} KiB, {time.time() - t0:.0f}s)")
+
+
+if __name__ == "__main__":
+  main()

@@ -1,0 +1,121 @@
+"""View-parallel path on CPU: two `gloo` ranks, replicated gaussians, views partitioned
+round-robin, ONE all-reduce of the flat gradient bucket per batch.  The per-view forward + backward is done by
+the CPU oracle here (the product kernels need a GPU; tests/test_gpu_renderer.py covers them), so this checks
+the host logic that bench.py and a trainer run at N > 1: partition_views, GradientBucket (autograd accumulates
+straight into the flat buffer), the collective, and that the result equals the single-process sum."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from taichi_gaussian_rasterizer_b200 import RasterConfig
+from taichi_gaussian_rasterizer_b200.distributed import GradientBucket, all_reduce_statistics, partition_views
+from util import rel_l2, scene3d
+
+NUM_VIEWS = 5   # odd on purpose: ranks get 3 and 2 views
+IMAGE_SIZE = (64, 48)
+
+
+def _free_port():
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    return s.getsockname()[1]
+
+
+def _scene():
+  from taichi_gaussian_rasterizer_b200.torch_lib.projection import join_rt, quat_to_mat
+  gaussians, camera = scene3d(0, 300, image_size=IMAGE_SIZE, scale_factor=1.0, sh_degree=1)
+  g = torch.Generator().manual_seed(7)
+  cameras = [camera]
+  for _ in range(NUM_VIEWS - 1):
+    axis = torch.nn.functional.normalize(torch.randn(3, generator=g), dim=0)
+    angle = (torch.rand(1, generator=g) * 2 - 1) * 0.05
+    q = torch.cat([axis * torch.sin(angle / 2), torch.cos(angle / 2)])
+    cameras.append(camera.transformed(join_rt(quat_to_mat(q), (torch.rand(3, generator=g) * 2 - 1) * 0.05)))
+  return gaussians, cameras
+
+
+def _render_view_loss(gaussians, camera, config):
+  """One view through the CPU oracle pipeline; returns (loss, visibility scattered to (N,))."""
+  import oracle
+  from oracle import torch_ref
+  pts, depth, idx = torch_ref.projection_apply(*gaussians.shape_tensors(), camera.T_camera_world, camera.projection,
+                                               camera.image_size, camera.depth_range, config.blur_cov,
+                                               config.clamp_margin, config.alpha_threshold)
+  feats = torch_ref.evaluate_sh_at(gaussians.feature, gaussians.position.detach(), idx, camera.camera_position)
+  ndc = torch_ref.ndc_depth(depth, camera.near_plane, camera.far_plane)
+  o2p, ranges = oracle.map_to_tiles(pts.detach().float(), ndc.detach().float(), camera.image_size, config)
+  out = oracle.rasterize_with_tiles(pts, feats, o2p, ranges.view(-1, 2), camera.image_size, config)
+  vis = torch.zeros(gaussians.position.shape[0], dtype=pts.dtype)
+  vis[idx] = out.visibility
+  return out.image.square().mean(), vis
+
+
+def _params(gaussians):
+  return [gaussians.position, gaussians.log_scaling, gaussians.rotation, gaussians.alpha_logit, gaussians.feature]
+
+
+def _accumulate(gaussians, cameras, view_ids, config):
+  gaussians.requires_grad_(True)
+  bucket = GradientBucket(_params(gaussians))
+  vis_total = torch.zeros(gaussians.position.shape[0])
+  for v in view_ids:
+    loss, vis = _render_view_loss(gaussians, cameras[v], config)
+    loss.backward()
+    vis_total += vis
+  return bucket, vis_total
+
+
+def _worker(rank, world, port, out_dir):
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    torch.set_num_threads(1)
+    config = RasterConfig(compute_visibility=True)
+    gaussians, cameras = _scene()
+    mine = partition_views(NUM_VIEWS, rank, world)
+    bucket, vis = _accumulate(gaussians, cameras, mine, config)
+    # autograd wrote into the flat bucket: param.grad are views of it
+    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in bucket.params)
+    bucket.all_reduce()
+    all_reduce_statistics([vis])
+    torch.save({"flat": bucket.flat.clone(), "vis": vis, "views": mine}, os.path.join(out_dir, f"rank{rank}.pt"))
+  finally:
+    dist.destroy_process_group()
+
+
+def test_partition_views_is_a_partition():
+  for n in (0, 1, 5, 64):
+    for world in (1, 2, 4, 8):
+      parts = [partition_views(n, r, world) for r in range(world)]
+      assert sorted(v for p in parts for v in p) == list(range(n))
+      assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_bucket_all_reduce_is_noop_without_process_group():
+  p = torch.zeros(4, 3, requires_grad=True)
+  b = GradientBucket([p])
+  (p.sum() * 2).backward()
+  assert b.all_reduce() is None
+  assert torch.equal(b.flat, torch.full((12,), 2.0)) and b.nbytes == 48
+
+
+@pytest.mark.timeout(600)
+def test_view_parallel_gradients_equal_serial_sum(tmp_path):
+  world = 2
+  mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+  results = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
+  assert results[0]["views"] == [0, 2, 4] and results[1]["views"] == [1, 3]
+  # every rank holds the same reduced bucket
+  assert torch.equal(results[0]["flat"], results[1]["flat"])
+  assert torch.equal(results[0]["vis"], results[1]["vis"])
+  # and it is the serial sum over all views (same tolerance as gradients: 1e-4 relative L2)
+  config = RasterConfig(compute_visibility=True)
+  gaussians, cameras = _scene()
+  bucket, vis = _accumulate(gaussians, cameras, list(range(NUM_VIEWS)), config)
+  assert bucket.flat.abs().sum() > 0
+  assert rel_l2(results[0]["flat"], bucket.flat) < 1e-4
+  assert rel_l2(results[0]["vis"], vis) < 1e-4
