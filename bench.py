@@ -55,44 +55,60 @@ def build_scene(n, image_size, sh_degree, scale_factor, alpha_range, seed, num_v
 
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-  FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+  """SM clock + throttle reasons sampled DURING the timed region (NVML in a thread, every 20 ms; nvidia-smi as a
+  fallback when pynvml is unavailable)."""
+  REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
   def __init__(self, index):
-    self.index, self.samples, self.proc = index, [], None
+    self.index, self.sm, self.mask, self.max_mhz = index, [], 0, None
+    self._stop = threading.Event()
+    self.thread = None
+    self.source = None
+
+  def _loop_nvml(self, nvml, handle):
+    while not self._stop.is_set():
+      try:
+        self.sm.append(float(nvml.nvmlDeviceGetClockInfo(handle, nvml.NVML_CLOCK_SM)))
+        self.mask |= int(nvml.nvmlDeviceGetCurrentClocksEventReasons(handle))
+      except Exception:
+        pass
+      self._stop.wait(0.02)
+
+  def _loop_smi(self):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+    while not self._stop.is_set():
+      try:
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             stdout=subprocess.PIPE, text=True, timeout=5).stdout.strip().split(",")
+        self.sm.append(float(out[0])); self.max_mhz = float(out[1]); self.mask |= int(out[2].strip(), 16)
+      except Exception:
+        pass
+      self._stop.wait(0.05)
 
   def start(self):
     try:
-      self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                    "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-      self.thread = threading.Thread(target=self._read, daemon=True)
-      self.thread.start()
+      import pynvml as nvml
+      nvml.nvmlInit()
+      visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+      phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+      handle = nvml.nvmlDeviceGetHandleByIndex(phys)
+      self.max_mhz = float(nvml.nvmlDeviceGetMaxClockInfo(handle, nvml.NVML_CLOCK_SM))
+      self.thread = threading.Thread(target=self._loop_nvml, args=(nvml, handle), daemon=True)
+      self.source = "nvml"
     except Exception:
-      self.proc = None
-
-  def _read(self):
-    for line in self.proc.stdout:
-      self.samples.append(line.strip())
+      self.thread = threading.Thread(target=self._loop_smi, daemon=True)
+      self.source = "nvidia-smi"
+    self.thread.start()
 
   def stop(self):
-    if self.proc is None:
-      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-    self.proc.terminate()
-    sm, mx, reasons = [], None, set()
-    for s in self.samples:
-      parts = [p.strip() for p in s.split(",")]
-      if len(parts) < 6:
-        continue
-      try:
-        sm.append(float(parts[0])); mx = float(parts[1])
-      except ValueError:
-        continue
-      for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
-        if v.lower().startswith("active"):
-          reasons.add(name)
-    sm.sort()
-    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-            "samples": len(sm)}
+    if self.thread is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler not started"], "samples": 0}
+    self._stop.set()
+    self.thread.join(timeout=6)
+    sm = sorted(self.sm)
+    reasons = sorted(n for n, bit in self.REASONS.items() if self.mask & bit)
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+            "samples": len(sm), "source": self.source}
 
 
 # ----------------------------------------------------------------------------------------------- ours
@@ -223,6 +239,12 @@ def run_ours(args):
   except Exception:
     pass
   peak_gbs, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json") if "hbm_gbs" in peaks else (6650.0, "fallback")
+  traffic, traffic_src = None, None
+  try:   # dram bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of this workload
+    t = json.loads((ROOT / "profiles" / "roofline_traffic.json").read_text())["raster_bwd_fast_kernel"]
+    traffic, traffic_src = t["dram_bytes_per_launch"], t["source"]
+  except Exception:
+    pass
   calls, bwd_ms = stage.get("gs_raster_bwd", (0, 0.0))
   bwd_avg_ms = bwd_ms / max(calls, 1)
   bwd_bytes = K * (32 + 4 * F) + 8 * px * F + V * (28 + 4 * F)   # SURVEY.md §8(d) raster_bwd
@@ -253,7 +275,8 @@ def run_ours(args):
     "gpu_launches": launches,
     "roofline": {"kernel": "raster_bwd_fast_kernel (gs_raster_bwd)", "bound": "hbm", "achieved": achieved,
                  "peak": peak_gbs, "peak_source": peak_src, "unit": "GB/s",
-                 "frac": achieved / peak_gbs if peak_gbs else None, "traffic": None,
+                 "frac": achieved / peak_gbs if peak_gbs else None, "traffic": traffic,
+                 "traffic_source": traffic_src,
                  "algorithmic_bytes": bwd_bytes, "avg_launch_ms": bwd_avg_ms,
                  "note": "instruction bound kernel (SURVEY.md §8d): HBM fraction is low by construction; "
                          "blend_evals_per_s is the informative figure",
