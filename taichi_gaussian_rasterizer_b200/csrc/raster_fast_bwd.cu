@@ -4,18 +4,24 @@
 // front-to-back replay that subtracts each blended term from the final forward image (R -= f w),
 // dL/dalpha = sum_c (f_c T - R_c / (1 - alpha)) G_c, threshold tested on the unclamped alpha and gradient
 // passed through the clamp, pixels stop at saturate_threshold.  Machine mapping:
-//   * one CTA per 16x16 tile, 2 warps, each warp owns a 16x8 pixel block, each lane a 2x2 quad (the
-//     reference's default pixel_stride; the quad amortises the per gaussian warp reduction over 4 pixels);
+//   * one CTA per 16x16 tile, 2 warps; a warp owns a 16x8 region made of four 8x4 sub-blocks and a lane owns the
+//     same pixel of each sub-block, so a splat that reaches one or two sub-blocks costs one or two evaluations
+//     per lane instead of four (the reference's 2x2 quads always pay four);
 //   * cp.async double-buffered staging of 32 B records + padded feature rows, batches of 64;
-//   * lane-parallel ellipse / pixel-block cull before the per pixel work (see raster_fast.cuh);
-//   * the 7 + F (+2) per gaussian partial sums are reduced across the warp with a transposed butterfly
-//     (16 shuffles for up to 16 values instead of 5 per value); the lane that ends up owning a value
-//     issues one red.global.add for it — one reduction per (gaussian, warp), no shared-memory atomics
-//     and no block barrier inside the batch.
-// Per pixel state lives in registers; F is a template parameter (1..7 here, wider F takes raster_generic.cu).
+//   * lane-parallel cull: 32 gaussians at a time, one per lane, each tested against the four sub-blocks (exact
+//     minimum of the ellipse's quadratic form over the block) -> four ballot masks; a sub-block is evaluated only
+//     if its bit is set (warp-uniform branch);
+//   * per pixel state is {W, G_c, RG = sum_c R_c G_c}: the replay needs the remaining features only through R . G
+//     (dL/dalpha = T (f . G) - (R . G) / (1 - alpha), and R_c -= f_c w  <=>  RG -= (f . G) w), which halves the
+//     per hit arithmetic and the register state compared with carrying R_c;
+//   * the 7 + F (+2) per gaussian partial sums are reduced across the warp with a transposed butterfly (12 shuffles
+//     for 10 values instead of 50); the lanes that end up owning a value issue one red.global.add each — one
+//     reduction per (gaussian, warp), no shared-memory atomics and no block barrier inside the batch.
+// A gaussian-parallel "hit record" variant (records appended to shared memory, one lane per gaussian folding
+// them, no shuffles) was built and measured in round 1: same instruction count, lower issue rate (1.74 vs 1.58 ms
+// on the bench workload), so it was dropped (kernel table).
+// F is a template parameter (1..7 here, wider F takes raster_generic.cu).
 #include "raster_fast.cuh"
-
-#include <stdlib.h>
 
 namespace gs {
 
@@ -126,17 +132,20 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
     own_base = heuristic + (own - 7 - F); own_stride = 2;
   }
 
-  float W[NSUB], R[NSUB][F], Gd[NSUB][F];
+  // Per pixel state: W, the image gradient G and RG = sum_c R_c G_c.  The replay only ever needs the remaining
+  // features R through R . G (dL/dalpha = T (f . G) - (R . G) / (1 - alpha)), and R_c -= f_c w means RG -= (f . G) w.
+  float W[NSUB], RG[NSUB], Gd[NSUB][F];
 #pragma unroll
   for (int i = 0; i < NSUB; ++i) {
     const int px = x0 + 8 * (i & 1), py = y0 + 4 * (i >> 1);
     const bool inb = px < p.image_width && py < p.image_height;
     W[i] = inb ? 0.f : 1.f;
+    RG[i] = 0.f;
     const int64_t pix = (int64_t)py * p.image_width + px;
 #pragma unroll
     for (int c = 0; c < F; ++c) {
-      R[i][c] = inb ? image[pix * F + c] : 0.f;
       Gd[i][c] = inb ? grad_image[pix * F + c] : 0.f;
+      RG[i] = fmaf(inb ? image[pix * F + c] : 0.f, Gd[i][c], RG[i]);
     }
   }
 
@@ -233,14 +242,14 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
                 const float w = alpha * Ti;
                 W[i] += w;
                 const float rinv = fast_rcp(1.f - alpha);
-                float ag = 0.f;
+                float fG = 0.f;
 #pragma unroll
                 for (int c = 0; c < F; ++c) {
-                  R[i][c] = fmaf(-f[c], w, R[i][c]);
-                  const float diff = fmaf(f[c], Ti, -R[i][c] * rinv);
-                  ag = fmaf(diff, Gd[i][c], ag);
+                  fG = fmaf(f[c], Gd[i][c], fG);
                   gf[c] = fmaf(w, Gd[i][c], gf[c]);
                 }
+                RG[i] = fmaf(-fG, w, RG[i]);
+                const float ag = fmaf(fG, Ti, -RG[i] * rinv);
                 const float aag = a0 * ag;
                 const float g = aag * pgauss;
                 const float a = g * tx * isx, bq = g * ty * isy;
@@ -275,14 +284,6 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
   cp_async_wait<0>();
 }
 
-static int bwd_nsub() {
-  static int v = [] {
-    const char* e = getenv("GS_BWD_NSUB");
-    return (e && atoi(e) == 8) ? 8 : 4;
-  }();
-  return v;
-}
-
 template <int F, int FP>
 static int launch_bwd_fast(const GsRasterParams& p, const RasterArgs& a, const float4* rec, const float* featP,
                            cudaStream_t st) {
@@ -292,8 +293,8 @@ static int launch_bwd_fast(const GsRasterParams& p, const RasterArgs& a, const f
   raster_bwd_fast_kernel<F, FP, HEURV, NSUBV><<<tiles, (8 / NSUBV) * 32, 0, st>>>(                              \
       p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,   \
       (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr)
-  if (bwd_nsub() == 8) { if (heur) GS_BWD_LAUNCH(true, 8); else GS_BWD_LAUNCH(false, 8); }
-  else { if (heur) GS_BWD_LAUNCH(true, 4); else GS_BWD_LAUNCH(false, 4); }
+  // NSUB = 4 (two warps per tile) measured faster than NSUB = 8 (one warp per tile, 96 registers): 1.58 vs 1.70 ms
+  if (heur) GS_BWD_LAUNCH(true, 4); else GS_BWD_LAUNCH(false, 4);
 #undef GS_BWD_LAUNCH
   GS_LAUNCH_CHECK();
   return GS_OK;
