@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""Runs BASELINE.json's five configurations once each on one GPU and prints one JSON line per configuration
+(fwd+bwd ms/frame with per-stage device times, V, K).  These are the parity-test configurations at FULL size:
+they show that every one runs through the product path and what it costs; `bench.py` is the contract benchmark
+(config quoted by the metric).  Usage: python benchmarks/configs.py [--only c1,c2,...] [--steps 5]
+"""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from taichi_gaussian_rasterizer_b200 import RasterConfig, _native, rasterize, render_gaussians  # noqa: E402
+from taichi_gaussian_rasterizer_b200.misc.renderer2d import project_gaussians2d  # noqa: E402
+from taichi_gaussian_rasterizer_b200.synthetic import random_2d_gaussians, random_3d_gaussians, random_camera  # noqa: E402
+
+
+def timed(fn, steps, warmup=3):
+  for _ in range(warmup):
+    fn()
+  torch.cuda.synchronize()
+  timer = _native.set_stage_timer(_native.StageTimer())
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for _ in range(steps):
+    info = fn()
+  b.record()
+  torch.cuda.synchronize()
+  _native.set_stage_timer(None)
+  stages = {k: round(v[1] / steps, 4) for k, v in sorted(timer.summary().items())}
+  return a.elapsed_time(b) / steps, stages, info
+
+
+def c1(dev):
+  """fit_image_gaussians-style 2D fit: 20k gaussians, 1024x1024, tile 16, stats on (examples/fit_image_gaussians.py)."""
+  torch.manual_seed(0)
+  size = (1024, 1024)
+  g = random_2d_gaussians(20_000, size, num_channels=3, scale_factor=0.5, alpha_range=(0.5, 1.0)).to(device=dev)
+  g.requires_grad_(True)
+  target = torch.rand(size[1], size[0], 3, device=dev)
+  cfg = RasterConfig(compute_point_heuristic=True, compute_visibility=True, tile_size=16, pixel_stride=(2, 2),
+                     antialias=True, blur_cov=0.0)
+
+  def step():
+    for t in (g.position, g.log_scaling, g.rotation, g.alpha_logit, g.feature):
+      t.grad = None
+    packed = project_gaussians2d(g)
+    r = rasterize(packed, g.z_depth.clamp(0, 1), g.feature, size, cfg)
+    loss = torch.nn.functional.mse_loss(torch.sigmoid(r.image), target)
+    loss.backward()
+    return {"N": 20_000, "image": size}
+  return step
+
+
+def scene3d(n, size, dev, sh_degree=None, channels=3, scale_factor=1.0, seed=0, bimodal=False):
+  torch.manual_seed(seed)
+  cam = random_camera(image_size=size)
+  g = random_3d_gaussians(n, cam, scale_factor=scale_factor, sh_degree=sh_degree, num_channels=channels)
+  if bimodal:   # Mip-NeRF360-like: log-normal scales (sigma_ln = 1), opacity mass near 0.05 and 0.95
+    g.log_scaling = g.log_scaling + torch.randn(n, 1)
+    u = torch.rand(n)
+    alpha = torch.where(u < 0.5, 0.02 + 0.08 * torch.rand(n), 0.9 + 0.09 * torch.rand(n))
+    g.alpha_logit = torch.logit(alpha).unsqueeze(1)
+  g = g.to(device=dev)
+  g.requires_grad_(True)
+  return g, cam.to(device=dev)
+
+
+def render_step(g, cam, cfg, **kw):
+  def step():
+    for t in (g.position, g.log_scaling, g.rotation, g.alpha_logit, g.feature):
+      t.grad = None
+    r = render_gaussians(g, cam, cfg, **kw)
+    loss = r.image.abs().mean()
+    if r.depth is not None:
+      loss = loss + r.depth.mean() * 1e-3
+    loss.backward()
+    return {"V": int(r.points_in_view.shape[0])}
+  return step
+
+
+def c2(dev):
+  """render_gaussians 3D: 1M gaussians, SH degree 3, 1920x1080."""
+  g, cam = scene3d(1_000_000, (1920, 1080), dev, sh_degree=3)
+  return render_step(g, cam, RasterConfig(), use_sh=True)
+
+
+def c3(dev):
+  """bicycle-scale: 6M gaussians, log-normal scales / bimodal opacity, 2048x1365, visibility + split/prune stats."""
+  g, cam = scene3d(6_000_000, (2048, 1365), dev, sh_degree=3, bimodal=True)
+  return render_step(g, cam, RasterConfig(compute_visibility=True, compute_point_heuristic=True), use_sh=True)
+
+
+def c4(dev):
+  """feature lifting: 2M gaussians, 32-channel features + depth / depth variance, 3840x2160."""
+  g, cam = scene3d(2_000_000, (3840, 2160), dev, channels=32)
+  return render_step(g, cam, RasterConfig(), use_sh=False, render_depth=True)
+
+
+def c5(dev):
+  """one rank's share of the batched multi-view step: 8 of 64 cameras x 3M gaussians, 1600x1064 (see bench.py --gpus)."""
+  g, cam = scene3d(3_000_000, (1600, 1064), dev, sh_degree=3, scale_factor=1.5)
+  return render_step(g, cam, RasterConfig(), use_sh=True)
+
+
+CONFIGS = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5}
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--only", default=",".join(CONFIGS))
+  ap.add_argument("--steps", type=int, default=5)
+  args = ap.parse_args()
+  dev = torch.device("cuda:0")
+  for name in args.only.split(","):
+    try:
+      step = CONFIGS[name](dev)
+      ms, stages, info = timed(step, args.steps)
+      print(json.dumps({"config": name, "what": CONFIGS[name].__doc__.strip(), "ms_per_frame_fwd_bwd": round(ms, 3),
+                        "stage_ms": stages, **info, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2)}),
+            flush=True)
+    except Exception as e:   # noqa: BLE001 - report and continue with the next configuration
+      print(json.dumps({"config": name, "error": f"{type(e).__name__}: {e}"}), flush=True)
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
+
+
+if __name__ == "__main__":
+  main()

@@ -10,7 +10,7 @@ constexpr int kFastTile = 16;
 constexpr int kFastTileArea = kFastTile * kFastTile;
 
 // padded feature row length used by the fast kernels for a given F (0 = unsupported)
-inline int fast_feature_pad(int F) { return F <= 4 ? 4 : (F <= 8 ? 8 : 0); }
+inline int fast_feature_pad(int F) { return F <= 4 ? 4 : F <= 8 ? 8 : F <= 16 ? 16 : F <= 36 ? 36 : F <= 64 ? 64 : 0; }
 
 // Workspace layout (all 256 B aligned):
 //   recF  V x 2 float4 : {mx, my, a1x, a1y} {a2x, a2y, log2(alpha), idx}       (forward records)
@@ -73,5 +73,8 @@ __device__ __forceinline__ bool block_may_touch(float mx, float my, float a1x, f
 }
 
 int raster_fast_pack(const GsRasterParams& p, const RasterArgs& a, bool forward, bool features, cudaStream_t st);
+
+// raster_fast_bwd_wide.cu: backward for 8..64 feature channels (one pixel per lane, image gradient in registers)
+int raster_bwd_wide(const GsRasterParams& p, const RasterArgs& a, const float4* rec, const float* featP, cudaStream_t st);
 
 }  // namespace gs

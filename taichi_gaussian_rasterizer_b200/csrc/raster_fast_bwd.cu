@@ -303,13 +303,13 @@ static int launch_bwd_fast(const GsRasterParams& p, const RasterArgs& a, const f
 bool raster_bwd_fast_supported(const GsRasterParams& p) { return raster_fast_supported(p) && p.num_features <= 7; }
 
 int raster_bwd_fast(const GsRasterParams& p, const RasterArgs& a, cudaStream_t st) {
-  if (p.num_features > 7) return raster_bwd_generic(p, a, st);
   int rc = raster_fast_pack(p, a, /*forward=*/false, /*features=*/!p.workspace_holds_packed, st);
   if (rc != GS_OK) return rc;
   const FastLayout L = fast_layout(p);
   unsigned char* ws = (unsigned char*)a.workspace;
   const float4* rec = (const float4*)(ws + L.off_recB);
   const float* featP = (const float*)(ws + L.off_feat);
+  if (p.num_features > 7) return raster_bwd_wide(p, a, rec, featP, st);  // 8..64 channels: one pixel per lane
   switch (p.num_features) {
     case 1: return launch_bwd_fast<1, 4>(p, a, rec, featP, st);
     case 2: return launch_bwd_fast<2, 4>(p, a, rec, featP, st);

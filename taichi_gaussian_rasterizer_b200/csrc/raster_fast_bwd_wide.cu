@@ -1,0 +1,249 @@
+// raster_fast_bwd_wide.cu — backward rasterizer for WIDE feature vectors (8..64 channels; f32, alpha blending,
+// tile 16), e.g. BASELINE.json's feature-lifting configuration: depth + depth^2 + 32 features = 34 channels.
+//
+// Same arithmetic contract as raster_fast_bwd.cu (rasterizer/backward.py:52-228 of the reference).  With F
+// channels the per pixel state of the narrow kernel (4 pixels per lane) no longer fits in registers, so the
+// mapping is the forward kernel's: one CTA per 16x16 tile, 8 warps, a warp owns an 8x4 block, a lane ONE pixel.
+//   * per pixel state in registers: W, RG = sum_c R_c G_c and the pixel's image gradient G[FP]; the replay needs
+//     the remaining features only through R . G (see raster_fast_bwd.cu), so R itself is never materialised —
+//     the reference keeps 2 x 4 x F floats per thread (backward.py:43-44,101-102);
+//   * tile lists staged in batches of 32 through shared memory with cp.async double buffering (records + padded
+//     feature rows, the 16 B chunks spread over the whole CTA); lane-parallel ellipse / block cull per warp;
+//   * a lane is hit at most once per gaussian, so its feature-gradient contribution is just w G_c: the 7 (+2)
+//     geometry sums and the F feature sums are reduced with transposed butterflies in groups of at most 32 values
+//     (about one shuffle per value) and committed by the owning lanes with red.global.add.
+// FP (padded channel count: 16, 36, 64) is a template parameter, F a runtime value; padded channels carry zeros.
+#include "raster_fast.cuh"
+
+namespace gs {
+
+constexpr int kWideBatch = 32;
+constexpr int kWideThreads = 256;
+
+template <int N, int OFF>
+__device__ __forceinline__ void wide_reduce_step(float* v, int lane) {
+  if constexpr (OFF >= 1) {
+    if constexpr (N > 1) {
+      constexpr int H = (N + 1) / 2;
+      const bool upper = (lane & OFF) != 0;
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const float hi = (i + H < N) ? v[i + H] : 0.f;
+        const float send = upper ? v[i] : hi;
+        const float keep = upper ? hi : v[i];
+        v[i] = keep + __shfl_xor_sync(kFull, send, OFF);
+      }
+      wide_reduce_step<H, OFF / 2>(v, lane);
+    } else {
+      v[0] += __shfl_xor_sync(kFull, v[0], OFF);
+      wide_reduce_step<1, OFF / 2>(v, lane);
+    }
+  }
+}
+
+// value index (0..NV-1) whose warp total ends up in v[0] of this lane after wide_reduce_step<NV, 16>, or -1
+template <int NV>
+__device__ __forceinline__ int wide_reduce_owner(int lane) {
+  static_assert(NV <= 32, "one value per lane at most");
+  int base = 0, cnt = NV, n = NV;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    if (n > 1) {
+      const int half = (n + 1) / 2;
+      if (lane & off) { base += half; cnt = max(cnt - half, 0); }
+      else cnt = min(cnt, half);
+      n = half;
+    } else if (lane & off) {
+      cnt = 0;
+    }
+  }
+  return cnt == 1 ? base : -1;
+}
+
+template <int FP, bool HEUR>
+__global__ void __launch_bounds__(kWideThreads)
+raster_bwd_wide_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
+                       const float* __restrict__ featP, const int32_t* __restrict__ ranges,
+                       const int32_t* __restrict__ o2p, const float* __restrict__ image,
+                       const float* __restrict__ grad_image, float* __restrict__ grad_pts,
+                       float* __restrict__ grad_feat, float* __restrict__ heuristic) {
+  constexpr int NG = 7 + (HEUR ? 2 : 0);             // geometry (+ heuristic) values
+  constexpr int C0 = FP < 32 ? FP : 32;              // first feature group
+  constexpr int C1 = FP - C0;                        // second feature group (0, 4 or 32)
+  __shared__ __align__(16) float4 s_r0[2][kWideBatch];
+  __shared__ __align__(16) float4 s_r1[2][kWideBatch];
+  __shared__ __align__(16) float s_feat[2][kWideBatch][FP];
+
+  const int tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int tw = (p.image_width + kFastTile - 1) / kFastTile;
+  const int F = p.num_features;
+  const int wx0 = (tile % tw) * kFastTile + (warp & 1) * 8;
+  const int wy0 = (tile / tw) * kFastTile + (warp >> 1) * 4;
+  const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
+  const bool inb = px < p.image_width && py < p.image_height;
+  const float pxf = (float)px + 0.5f, pyf = (float)py + 0.5f;
+  const float bx0 = (float)wx0 + 0.5f, bx1 = (float)wx0 + 7.5f, by0 = (float)wy0 + 0.5f, by1 = (float)wy0 + 3.5f;
+  const float thr = (float)p.alpha_threshold, cmax = (float)p.clamp_max_alpha, sat = (float)p.saturate_threshold;
+  const float l2thr = log2f(thr);
+  const bool pg = p.points_requires_grad && grad_pts != nullptr;
+  const bool fg = p.features_requires_grad && grad_feat != nullptr;
+
+  const int own_g = wide_reduce_owner<NG>(lane);
+  const int own_0 = wide_reduce_owner<C0>(lane);
+  const int own_1 = C1 > 0 ? wide_reduce_owner<(C1 > 0 ? C1 : 1)>(lane) : -1;
+
+  float G[FP];
+  float W = inb ? 0.f : 1.f, RG = 0.f;
+  {
+    const int64_t pix = (int64_t)py * p.image_width + px;
+#pragma unroll
+    for (int c = 0; c < FP; ++c) {
+      const bool ok = inb && c < F;
+      G[c] = ok ? grad_image[pix * F + c] : 0.f;
+      RG = fmaf(ok ? image[pix * F + c] : 0.f, G[c], RG);
+    }
+  }
+
+  const int start = ranges[2 * tile], end = ranges[2 * tile + 1];
+  const int C = end - start;
+  const int nb = (C + kWideBatch - 1) / kWideBatch;
+
+  auto issue_load = [&](int b) {
+    const int buf = b & 1;
+    if (t < kWideBatch) {
+      const int v = b * kWideBatch + t;
+      if (v < C) {
+        const int idx = o2p[start + v];
+        cp_async16(&s_r0[buf][t], rec + 2 * (int64_t)idx);
+        cp_async16(&s_r1[buf][t], rec + 2 * (int64_t)idx + 1);
+      }
+    }
+    constexpr int CH = FP / 4;
+#pragma unroll
+    for (int q0 = 0; q0 < kWideBatch * CH; q0 += kWideThreads) {
+      const int q = q0 + t;
+      const int slot = q / CH, part = q - slot * CH;
+      const int v = b * kWideBatch + slot;
+      if (q < kWideBatch * CH && v < C) {
+        const int idx = o2p[start + v];
+        cp_async16(&s_feat[buf][slot][part * 4], featP + (int64_t)idx * FP + part * 4);
+      }
+    }
+    cp_async_commit();
+  };
+
+  bool warp_done = __all_sync(kFull, W >= sat);
+  if (nb > 0) issue_load(0);
+  for (int b = 0; b < nb; ++b) {
+    const int buf = b & 1;
+    if (b + 1 < nb) {
+      issue_load(b + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int n_in = min(kWideBatch, C - b * kWideBatch);
+    if (!warp_done) {
+      bool touch = false;
+      if (lane < n_in) {
+        const float4 r0 = s_r0[buf][lane], r1 = s_r1[buf][lane];
+        const float cx = kSqrtHalfLog2e * r1.x, cy = kSqrtHalfLog2e * r1.y;
+        touch = block_may_touch(r0.x, r0.y, r0.z * cx, r0.w * cx, -r0.w * cy, r0.z * cy, log2f(r1.z) - l2thr, bx0, bx1,
+                                by0, by1);
+      }
+      unsigned mask = __ballot_sync(kFull, touch);
+      while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float4 r0 = s_r0[buf][j], r1 = s_r1[buf][j];
+        const float mx = r0.x, my = r0.y, ax = r0.z, ay = r0.w, isx = r1.x, isy = r1.y, a0 = r1.z;
+        const float dx = pxf - mx, dy = pyf - my;
+        const float tx = fmaf(dy, ay, dx * ax) * isx;
+        const float ty = fmaf(dy, ax, -dx * ay) * isy;
+        const float pgauss = fast_ex2(-kHalfLog2e * fmaf(ty, ty, tx * tx));
+        float alpha = a0 * pgauss;
+        const bool hit = alpha > thr && W < sat;
+        if (!__any_sync(kFull, hit)) continue;
+
+        float vg[NG];
+#pragma unroll
+        for (int k = 0; k < NG; ++k) vg[k] = 0.f;
+        float wl = 0.f;  // this lane's blend weight for the gaussian (0 when not hit)
+        if (hit) {
+          alpha = fminf(alpha, cmax);
+          const float Ti = 1.f - W;
+          wl = alpha * Ti;
+          W += wl;
+          const float rinv = fast_rcp(1.f - alpha);
+          float fG = 0.f;
+#pragma unroll
+          for (int c = 0; c < FP; c += 4) {
+            const float4 f4 = *reinterpret_cast<const float4*>(&s_feat[buf][j][c]);
+            fG = fmaf(f4.x, G[c], fG); fG = fmaf(f4.y, G[c + 1], fG);
+            fG = fmaf(f4.z, G[c + 2], fG); fG = fmaf(f4.w, G[c + 3], fG);
+          }
+          RG = fmaf(-fG, wl, RG);
+          const float ag = fmaf(fG, Ti, -RG * rinv);
+          const float aag = a0 * ag;
+          const float g = aag * pgauss;
+          const float a = g * tx * isx, bq = g * ty * isy;
+          vg[0] = fmaf(ax, a, -ay * bq); vg[1] = fmaf(ay, a, ax * bq);
+          vg[2] = -fmaf(a, dx, bq * dy); vg[3] = fmaf(bq, dx, -a * dy);
+          vg[4] = a * tx; vg[5] = bq * ty; vg[6] = pgauss * ag;
+          if (HEUR) { vg[7] = aag * aag; vg[8] = fabsf(vg[0]) + fabsf(vg[1]); }
+        }
+        const int64_t idx = __float_as_int(r1.w);
+        wide_reduce_step<NG, 16>(vg, lane);
+        if (own_g >= 0) {
+          if (own_g < 7) { if (pg) atomicAdd(grad_pts + idx * 7 + own_g, vg[0]); }
+          else if (HEUR) atomicAdd(heuristic + idx * 2 + (own_g - 7), vg[0]);
+        }
+        if (fg) {
+          {
+            float v[C0];
+#pragma unroll
+            for (int c = 0; c < C0; ++c) v[c] = wl * G[c];
+            wide_reduce_step<C0, 16>(v, lane);
+            if (own_0 >= 0 && own_0 < F) atomicAdd(grad_feat + idx * F + own_0, v[0]);
+          }
+          if constexpr (C1 > 0) {
+            float v[C1];
+#pragma unroll
+            for (int c = 0; c < C1; ++c) v[c] = wl * G[C0 + c];
+            wide_reduce_step<C1, 16>(v, lane);
+            if (own_1 >= 0 && C0 + own_1 < F) atomicAdd(grad_feat + idx * F + C0 + own_1, v[0]);
+          }
+        }
+      }
+      warp_done = __all_sync(kFull, W >= sat);
+    }
+    if (__syncthreads_and(warp_done)) break;
+  }
+  cp_async_wait<0>();
+}
+
+int raster_bwd_wide(const GsRasterParams& p, const RasterArgs& a, const float4* rec, const float* featP,
+                    cudaStream_t st) {
+  const int tiles = tiles_wide(p) * tiles_high(p);
+  const bool heur = p.compute_point_heuristic && a.point_heuristic != nullptr;
+#define GS_WIDE_LAUNCH(FPV, HEURV)                                                                                  \
+  raster_bwd_wide_kernel<FPV, HEURV><<<tiles, kWideThreads, 0, st>>>(                                              \
+      p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,      \
+      (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr)
+#define GS_WIDE_CASE(FPV) \
+  case FPV: if (heur) GS_WIDE_LAUNCH(FPV, true); else GS_WIDE_LAUNCH(FPV, false); break
+  switch (fast_feature_pad(p.num_features)) {
+    GS_WIDE_CASE(8);
+    GS_WIDE_CASE(16);
+    GS_WIDE_CASE(36);
+    GS_WIDE_CASE(64);
+    default: GS_UNSUPPORTED("rasterizer backward (wide): %d feature channels", p.num_features);
+  }
+#undef GS_WIDE_CASE
+#undef GS_WIDE_LAUNCH
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+}  // namespace gs

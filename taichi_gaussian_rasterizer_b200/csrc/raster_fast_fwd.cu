@@ -19,7 +19,6 @@
 
 namespace gs {
 
-constexpr int kFwdBatch = 128;
 constexpr int kFwdThreads = 256;
 
 // ------------------------------------------------------------------------------------------------ pack
@@ -59,23 +58,30 @@ int raster_fast_pack(const GsRasterParams& p, const RasterArgs& a, bool forward,
   float4* recB = forward ? nullptr : (float4*)(ws + L.off_recB);
   float* featP = features ? (float*)(ws + L.off_feat) : nullptr;
   const int64_t blocks = ceil_div(p.num_points, 256);
-  if (L.FP == 4)
-    raster_pack_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(p.num_points, p.num_features, (const float*)a.gaussians2d,
-                                                           (const float*)a.features, recF, featP, recB);
-  else
-    raster_pack_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(p.num_points, p.num_features, (const float*)a.gaussians2d,
-                                                           (const float*)a.features, recF, featP, recB);
+#define GS_PACK(FPV)                                                                                          \
+  raster_pack_kernel<FPV><<<(unsigned)blocks, 256, 0, st>>>(p.num_points, p.num_features, (const float*)a.gaussians2d, \
+                                                            (const float*)a.features, recF, featP, recB)
+  switch (L.FP) {
+    case 4: GS_PACK(4); break;
+    case 8: GS_PACK(8); break;
+    case 16: GS_PACK(16); break;
+    case 36: GS_PACK(36); break;
+    default: GS_PACK(64); break;
+  }
+#undef GS_PACK
   GS_LAUNCH_CHECK();
   return GS_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int FP, bool VIS>
+// BATCH = staged tile-list entries per buffer: 128 for narrow features, 64 for FP >= 16 (shared memory budget).
+template <int FP, bool VIS, int BATCH>
 __global__ void __launch_bounds__(kFwdThreads)
 raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
                        const float* __restrict__ featP, const int32_t* __restrict__ ranges,
                        const int32_t* __restrict__ o2p, float* __restrict__ image, float* __restrict__ image_alpha,
                        float* __restrict__ visibility) {
+  constexpr int kFwdBatch = BATCH;
   __shared__ __align__(16) float4 s_r0[2][kFwdBatch];
   __shared__ __align__(16) float4 s_r1[2][kFwdBatch];
   __shared__ __align__(16) float s_feat[2][kFwdBatch][FP];
@@ -108,18 +114,41 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
 
   auto issue_load = [&](int b) {
     const int buf = b & 1;
-    const int slot = t & (kFwdBatch - 1);
-    const int v = b * kFwdBatch + slot;
-    if (v < total) {
-      const int k = v < C ? v : v - kFastTileArea;
-      const int idx = o2p[start + k];
-      if (t < kFwdBatch) {
-        cp_async16(&s_r0[buf][slot], rec + 2 * (int64_t)idx);
-        cp_async16(&s_r1[buf][slot], rec + 2 * (int64_t)idx + 1);
-        if (VIS) s_vis[buf][slot] = 0.f;
-      } else {
+    if constexpr (BATCH * 2 == kFwdThreads) {  // narrow rows: first half of the CTA gathers records, second half features
+      const int slot = t & (kFwdBatch - 1);
+      const int v = b * kFwdBatch + slot;
+      if (v < total) {
+        const int k = v < C ? v : v - kFastTileArea;
+        const int idx = o2p[start + k];
+        if (t < kFwdBatch) {
+          cp_async16(&s_r0[buf][slot], rec + 2 * (int64_t)idx);
+          cp_async16(&s_r1[buf][slot], rec + 2 * (int64_t)idx + 1);
+          if (VIS) s_vis[buf][slot] = 0.f;
+        } else {
 #pragma unroll
-        for (int c = 0; c < FP; c += 4) cp_async16(&s_feat[buf][slot][c], featP + (int64_t)idx * FP + c);
+          for (int c = 0; c < FP; c += 4) cp_async16(&s_feat[buf][slot][c], featP + (int64_t)idx * FP + c);
+        }
+      }
+    } else {  // wide rows: records by the first BATCH threads, the 16 B feature chunks spread over the whole CTA
+      if (t < kFwdBatch) {
+        const int v = b * kFwdBatch + t;
+        if (v < total) {
+          const int idx = o2p[start + (v < C ? v : v - kFastTileArea)];
+          cp_async16(&s_r0[buf][t], rec + 2 * (int64_t)idx);
+          cp_async16(&s_r1[buf][t], rec + 2 * (int64_t)idx + 1);
+          if (VIS) s_vis[buf][t] = 0.f;
+        }
+      }
+      constexpr int CH = FP / 4;
+#pragma unroll
+      for (int q0 = 0; q0 < kFwdBatch * CH; q0 += kFwdThreads) {
+        const int q = q0 + t;
+        const int slot = q / CH, part = q - slot * CH;
+        const int v = b * kFwdBatch + slot;
+        if (q < kFwdBatch * CH && v < total) {
+          const int idx = o2p[start + (v < C ? v : v - kFastTileArea)];
+          cp_async16(&s_feat[buf][slot][part * 4], featP + (int64_t)idx * FP + part * 4);
+        }
       }
     }
     cp_async_commit();
@@ -209,12 +238,21 @@ int raster_fwd_fast(const GsRasterParams& p, const RasterArgs& a, cudaStream_t s
   const float* featP = (const float*)(ws + L.off_feat);
   const int tiles = tiles_wide(p) * tiles_high(p);
   const bool vis = p.compute_visibility && a.visibility != nullptr;
-#define GS_FWD_LAUNCH(FPV, VISV)                                                                             \
-  raster_fwd_fast_kernel<FPV, VISV><<<tiles, kFwdThreads, 0, st>>>(p, rec, featP, a.tile_ranges,             \
-                                                                   a.overlap_to_point, (float*)a.image,      \
-                                                                   (float*)a.image_alpha, (float*)a.visibility)
-  if (L.FP == 4) { if (vis) GS_FWD_LAUNCH(4, true); else GS_FWD_LAUNCH(4, false); }
-  else { if (vis) GS_FWD_LAUNCH(8, true); else GS_FWD_LAUNCH(8, false); }
+#define GS_FWD_LAUNCH(FPV, VISV, BATCHV)                                                                           \
+  raster_fwd_fast_kernel<FPV, VISV, BATCHV><<<tiles, kFwdThreads, 0, st>>>(p, rec, featP, a.tile_ranges,            \
+                                                                           a.overlap_to_point, (float*)a.image,     \
+                                                                           (float*)a.image_alpha, (float*)a.visibility)
+#define GS_FWD_CASE(FPV, BATCHV) \
+  case FPV: if (vis) GS_FWD_LAUNCH(FPV, true, BATCHV); else GS_FWD_LAUNCH(FPV, false, BATCHV); break
+  switch (L.FP) {
+    GS_FWD_CASE(4, 128);
+    GS_FWD_CASE(8, 128);
+    GS_FWD_CASE(16, 64);
+    GS_FWD_CASE(36, 64);
+    GS_FWD_CASE(64, 64);
+    default: GS_UNSUPPORTED("rasterizer forward (fast): %d feature channels", p.num_features);
+  }
+#undef GS_FWD_CASE
 #undef GS_FWD_LAUNCH
   GS_LAUNCH_CHECK();
   return GS_OK;

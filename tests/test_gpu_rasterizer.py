@@ -81,10 +81,21 @@ def test_feature_widths_fast(cuda_device, channels):
   compare_forward_backward(cuda_device, 10 + channels, 1500, (160, 112), cfg, channels=channels, scale=2.0)
 
 
-@pytest.mark.parametrize("channels", [12, 34])
-def test_wide_features_generic(cuda_device, channels):
+@pytest.mark.parametrize("channels,stats", [(8, False), (9, True), (12, False), (16, True), (17, False), (34, False),
+                                            (34, True), (36, False), (37, False), (64, True)])
+def test_wide_features(cuda_device, channels, stats):
+  """8..64 channels take the wide kernels (forward FP 16/36/64, backward one pixel per lane); 34 channels is
+  BASELINE.json's feature-lifting configuration (depth, depth^2, 32 features)."""
+  cfg = RasterConfig(compute_visibility=stats, compute_point_heuristic=stats)
+  # same scene size as test_feature_widths_fast: one alpha_threshold decision that flips between ex2.approx and
+  # libm exp moves a pixel by ~0.4 %, which alone is 4e-5 relative L2 of a 96x80 image but 1e-5 of this one
+  compare_forward_backward(cuda_device, 20 + channels, 1500, (160, 112), cfg, channels=channels, scale=2.0)
+
+
+def test_wide_features_multi_group_tile(cuda_device):
+  """wide kernels on tiles with several hundred overlaps (many batches, saturation exits)"""
   cfg = RasterConfig()
-  compare_forward_backward(cuda_device, 20 + channels, 800, (96, 80), cfg, channels=channels, scale=2.0)
+  compare_forward_backward(cuda_device, 77, 3000, (64, 48), cfg, channels=34, scale=6.0)
 
 
 @pytest.mark.parametrize("ts,stride", [(8, (1, 1)), (8, (2, 1)), (32, (2, 2)), (32, (4, 4))])
