@@ -115,6 +115,7 @@ class ClockSampler:
 KERNELS_PER_CALL = {  # kernels launched by each entry point (memsets not counted)
   "gs_project_fwd": 1, "gs_project_bwd": 1, "gs_sh_fwd": 1, "gs_sh_bwd": 1, "gs_tile_count": 1, "gs_full_cumsum": 1,
   "gs_tile_emit_keys": 1, "gs_find_ranges": 1, "gs_raster_fwd": 2, "gs_raster_bwd": 2,
+  "gs_depth_keys": 1, "gs_tile_count_perm": 1, "gs_tile_emit_tiles": 1, "gs_find_ranges_tiles": 1,
 }
 
 
@@ -252,9 +253,10 @@ def run_ours(args):
   fwd_calls, fwd_ms = stage.get("gs_raster_fwd", (0, 0.0))
   stage_ms = {k: round(v[1] / args.steps / views, 4) for k, v in sorted(stage.items())}
   launches = sum(KERNELS_PER_CALL.get(k, 0) * v[0] for k, v in stage.items())
+  # two sorts per frame (depth keys: 32 bits; tile ids: tile_bits), each = histogram + scan + one kernel per 8 bit pass
   sort_calls = stage.get("gs_radix_sort_pairs", (0, 0.0))[0]
   tile_bits = max(1, (int(ranges.shape[0] * ranges.shape[1]) - 1).bit_length())
-  launches += sort_calls * (2 + -(-(32 + tile_bits) // 8))
+  launches += (sort_calls // 2) * ((2 + 4) + (2 + -(-tile_bits // 8)))
   launches = launches // max(args.steps, 1)
 
   out = {

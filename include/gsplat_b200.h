@@ -134,6 +134,19 @@ int gs_radix_sort_pairs(int64_t n, int32_t key_bytes, const void* keys_in, const
 int gs_find_ranges(const GsTileParams* p, int64_t num_overlaps, const void* sorted_keys,
                    int32_t* tile_ranges, void* stream);
 
+/* Depth-first tile mapping: produces exactly the overlap_to_point / tile_ranges of
+ * count -> emit_keys -> sort(32 + tile bits) -> find_ranges (mapper/tile_mapper.py:146-196) with a third of the sort
+ * traffic: (1) gs_depth_keys: u32 depth key (f32 bits, or depth16) + index per gaussian; sort them (stable) to get
+ * `perm`; (2) gs_tile_count_perm / gs_tile_emit_tiles visit the gaussians in that order and emit bare tile ids;
+ * (3) a stable sort on the tile id bits only; (4) gs_find_ranges_tiles.  perm (V) int32, tile_ids (K) u32. */
+int gs_depth_keys(const GsTileParams* p, const float* depth, uint32_t* keys, int32_t* values, void* stream);
+int gs_tile_count_perm(const GsTileParams* p, const float* gaussians, const int32_t* perm, int32_t* counts,
+                       void* stream);
+int gs_tile_emit_tiles(const GsTileParams* p, const float* gaussians, const int32_t* perm, const int32_t* cum,
+                       uint32_t* tile_ids, int32_t* values, void* stream);
+int gs_find_ranges_tiles(const GsTileParams* p, int64_t num_overlaps, const uint32_t* sorted_tile_ids,
+                         int32_t* tile_ranges, void* stream);
+
 /* ------------------------------------------------------------------ rasterizer
  * replaces _forward_kernel (rasterizer/forward.py:24-137) and _backward_kernel
  * (rasterizer/backward.py:52-228). */

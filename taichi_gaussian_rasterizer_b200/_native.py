@@ -20,6 +20,7 @@ EXPORTS = [
   "gs_sh_fwd", "gs_sh_bwd",
   "gs_tile_count", "gs_full_cumsum_workspace_bytes", "gs_full_cumsum", "gs_tile_emit_keys",
   "gs_radix_sort_pairs_workspace_bytes", "gs_radix_sort_pairs", "gs_find_ranges",
+  "gs_depth_keys", "gs_tile_count_perm", "gs_tile_emit_tiles", "gs_find_ranges_tiles",
   "gs_raster_workspace_bytes", "gs_raster_fwd", "gs_raster_bwd",
 ]
 

@@ -127,26 +127,33 @@ __device__ __forceinline__ TileQuery shfl_query(const TileQuery& q, int src) {
   return r;
 }
 
-// EMIT = false: counts[i] = number of overlapped tiles.  EMIT = true: write keys / values at cum[i].
-template <bool EMIT, typename KeyT>
+// MODE 0: counts[i] = number of overlapped tiles.  MODE 1: write (tile, depth) keys / values at cum[i].
+// MODE 2: write bare tile ids (u32) / values at cum[i] (depth-first pipeline: the gaussians are visited in depth
+// order through `perm`, so a stable sort on the tile id alone yields the (tile, depth, index) order).
+// perm (optional): slot i works on gaussian perm[i]; values always hold the gaussian index.
+template <int MODE, typename KeyT>
 __global__ void __launch_bounds__(kTileBlock)
 tile_query_kernel(const __grid_constant__ GsTileParams p, int img_w, int img_h, const float* __restrict__ g,
-                  const float* __restrict__ depth, const int32_t* __restrict__ cum, int32_t* __restrict__ counts,
-                  KeyT* __restrict__ keys, int32_t* __restrict__ values) {
-  const int64_t i = (int64_t)blockIdx.x * kTileBlock + threadIdx.x;
+                  const float* __restrict__ depth, const int32_t* __restrict__ perm, const int32_t* __restrict__ cum,
+                  int32_t* __restrict__ counts, KeyT* __restrict__ keys, int32_t* __restrict__ values) {
+  constexpr bool EMIT = MODE != 0;
+  const int64_t slot = (int64_t)blockIdx.x * kTileBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int ts = p.tile_size;
   const int tiles_wide = img_w / ts;
-  const bool valid = i < p.num_points;
+  const bool valid = slot < p.num_points;
 
   TileQuery qy;
   qy.span_x = qy.span_y = 0;
   float d = 0.f;
   int64_t base = 0;
+  int64_t i = slot;
   if (valid) {
+    if (perm) i = perm[slot];
     const float* gi = g + 7 * i;
     qy = obb_query(gi[0], gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], img_w, img_h, ts, (float)p.alpha_threshold);
-    if (EMIT) { d = depth[i]; base = cum[i]; }
+    if (MODE == 1) d = depth[i];
+    if (EMIT) base = cum[slot];
   }
   const int n = span_count(qy);
   int count = 0;
@@ -157,7 +164,8 @@ tile_query_kernel(const __grid_constant__ GsTileParams p, int img_w, int img_h, 
         if (test_tile(qy, tu, tv, ts)) {
           if (EMIT) {
             int tile_id = (tu + qy.min_x) + (tv + qy.min_y) * tiles_wide;
-            keys[base + count] = sizeof(KeyT) == 8 ? (KeyT)make_key64(d, tile_id) : (KeyT)make_key32(d, tile_id);
+            keys[base + count] = MODE == 2 ? (KeyT)tile_id
+                                 : sizeof(KeyT) == 8 ? (KeyT)make_key64(d, tile_id) : (KeyT)make_key32(d, tile_id);
             values[base + count] = (int32_t)i;
           }
           ++count;
@@ -185,14 +193,15 @@ tile_query_kernel(const __grid_constant__ GsTileParams p, int img_w, int img_h, 
       if (EMIT && hit) {
         const int r = running + __popc(hm & ((1u << lane) - 1u));
         int tile_id = (tu + q.min_x) + (tv + q.min_y) * tiles_wide;
-        keys[bq + r] = sizeof(KeyT) == 8 ? (KeyT)make_key64(dq, tile_id) : (KeyT)make_key32(dq, tile_id);
+        keys[bq + r] = MODE == 2 ? (KeyT)tile_id
+                       : sizeof(KeyT) == 8 ? (KeyT)make_key64(dq, tile_id) : (KeyT)make_key32(dq, tile_id);
         values[bq + r] = (int32_t)iq;
       }
       running += __popc(hm);
     }
     if (lane == src) count = running;
   }
-  if (!EMIT && valid) counts[i] = count;
+  if (!EMIT && valid) counts[slot] = count;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -210,6 +219,17 @@ __global__ void find_ranges_kernel(int64_t n, const KeyT* __restrict__ keys, int
     ranges[2 * tile + 1] = (int32_t)(i + 1);
     if (next < max_tile) ranges[2 * next] = (int32_t)(i + 1);
   }
+}
+
+// u32 sort keys of the depth-first pipeline: the f32 bit pattern of the depth (mapper/tile_mapper.py:34-40) or
+// the 16 bit quantisation (:53-59); values = gaussian index.
+__global__ void depth_keys_kernel(int64_t n, int use_depth16, const float* __restrict__ depth,
+                                  uint32_t* __restrict__ keys, int32_t* __restrict__ values) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float d = depth[i];
+  keys[i] = use_depth16 ? (make_key32(d, 0) & 0xffffu) : (uint32_t)(make_key64(d, 0) & 0xffffffffull);
+  values[i] = (int32_t)i;
 }
 
 }  // namespace gs
@@ -287,8 +307,8 @@ int gs_tile_count(const GsTileParams* p, const float* gaussians, int32_t* counts
   int ts = p->tile_size;
   int img_w = (int)ceil_div(p->image_width, ts) * ts, img_h = (int)ceil_div(p->image_height, ts) * ts;
   int64_t blocks = ceil_div(p->num_points, kTileBlock);
-  tile_query_kernel<false, uint64_t><<<(unsigned)blocks, kTileBlock, 0, (cudaStream_t)stream>>>(
-      *p, img_w, img_h, gaussians, nullptr, nullptr, counts, nullptr, nullptr);
+  tile_query_kernel<0, uint64_t><<<(unsigned)blocks, kTileBlock, 0, (cudaStream_t)stream>>>(
+      *p, img_w, img_h, gaussians, nullptr, nullptr, nullptr, counts, nullptr, nullptr);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }
@@ -303,11 +323,11 @@ int gs_tile_emit_keys(const GsTileParams* p, const float* gaussians, const float
   int img_w = (int)ceil_div(p->image_width, ts) * ts, img_h = (int)ceil_div(p->image_height, ts) * ts;
   int64_t blocks = ceil_div(p->num_points, kTileBlock);
   if (p->use_depth16)
-    tile_query_kernel<true, uint32_t><<<(unsigned)blocks, kTileBlock, 0, (cudaStream_t)stream>>>(
-        *p, img_w, img_h, gaussians, depth, cum, nullptr, (uint32_t*)keys, values);
+    tile_query_kernel<1, uint32_t><<<(unsigned)blocks, kTileBlock, 0, (cudaStream_t)stream>>>(
+        *p, img_w, img_h, gaussians, depth, nullptr, cum, nullptr, (uint32_t*)keys, values);
   else
-    tile_query_kernel<true, uint64_t><<<(unsigned)blocks, kTileBlock, 0, (cudaStream_t)stream>>>(
-        *p, img_w, img_h, gaussians, depth, cum, nullptr, (uint64_t*)keys, values);
+    tile_query_kernel<1, uint64_t><<<(unsigned)blocks, kTileBlock, 0, (cudaStream_t)stream>>>(
+        *p, img_w, img_h, gaussians, depth, nullptr, cum, nullptr, (uint64_t*)keys, values);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }
@@ -329,6 +349,63 @@ int gs_find_ranges(const GsTileParams* p, int64_t num_overlaps, const void* sort
   else
     find_ranges_kernel<uint64_t, 32><<<(unsigned)blocks, 256, 0, st>>>(num_overlaps, (const uint64_t*)sorted_keys,
                                                                       tile_ranges);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+// ---- depth-first tile mapping (same outputs as count -> emit_keys -> sort on 32 + tile bits -> find_ranges):
+// sort the V gaussians by depth key once, visit them in that order, then a stable sort on the tile id only.
+int gs_depth_keys(const GsTileParams* p, const float* depth, uint32_t* keys, int32_t* values, void* stream) {
+  int rc = check_tile_params(p, "gs_depth_keys");
+  if (rc != GS_OK) return rc;
+  if (p->num_points == 0) return GS_OK;
+  GS_CHECK_ARG(depth && keys && values, "gs_depth_keys: null tensor");
+  depth_keys_kernel<<<(unsigned)ceil_div(p->num_points, 256), 256, 0, (cudaStream_t)stream>>>(
+      p->num_points, p->use_depth16, depth, keys, values);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+int gs_tile_count_perm(const GsTileParams* p, const float* gaussians, const int32_t* perm, int32_t* counts,
+                       void* stream) {
+  int rc = check_tile_params(p, "gs_tile_count_perm");
+  if (rc != GS_OK) return rc;
+  if (p->num_points == 0) return GS_OK;
+  GS_CHECK_ARG(gaussians && perm && counts, "gs_tile_count_perm: null tensor");
+  int ts = p->tile_size;
+  int img_w = (int)ceil_div(p->image_width, ts) * ts, img_h = (int)ceil_div(p->image_height, ts) * ts;
+  tile_query_kernel<0, uint32_t><<<(unsigned)ceil_div(p->num_points, kTileBlock), kTileBlock, 0, (cudaStream_t)stream>>>(
+      *p, img_w, img_h, gaussians, nullptr, perm, nullptr, counts, nullptr, nullptr);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+int gs_tile_emit_tiles(const GsTileParams* p, const float* gaussians, const int32_t* perm, const int32_t* cum,
+                       uint32_t* tile_ids, int32_t* values, void* stream) {
+  int rc = check_tile_params(p, "gs_tile_emit_tiles");
+  if (rc != GS_OK) return rc;
+  if (p->num_points == 0) return GS_OK;
+  GS_CHECK_ARG(gaussians && perm && cum && tile_ids && values, "gs_tile_emit_tiles: null tensor");
+  int ts = p->tile_size;
+  int img_w = (int)ceil_div(p->image_width, ts) * ts, img_h = (int)ceil_div(p->image_height, ts) * ts;
+  tile_query_kernel<2, uint32_t><<<(unsigned)ceil_div(p->num_points, kTileBlock), kTileBlock, 0, (cudaStream_t)stream>>>(
+      *p, img_w, img_h, gaussians, nullptr, perm, cum, nullptr, tile_ids, values);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+int gs_find_ranges_tiles(const GsTileParams* p, int64_t num_overlaps, const uint32_t* sorted_tile_ids,
+                         int32_t* tile_ranges, void* stream) {
+  int rc = check_tile_params(p, "gs_find_ranges_tiles");
+  if (rc != GS_OK) return rc;
+  GS_CHECK_ARG(tile_ranges != nullptr && num_overlaps >= 0, "gs_find_ranges_tiles: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t tiles = ceil_div(p->image_width, p->tile_size) * ceil_div(p->image_height, p->tile_size);
+  GS_CUDA(cudaMemsetAsync(tile_ranges, 0, (size_t)tiles * 2 * sizeof(int32_t), st));
+  if (num_overlaps == 0) return GS_OK;
+  GS_CHECK_ARG(sorted_tile_ids != nullptr, "gs_find_ranges_tiles: null keys");
+  find_ranges_kernel<uint32_t, 0><<<(unsigned)ceil_div(num_overlaps, 256), 256, 0, st>>>(num_overlaps, sorted_tile_ids,
+                                                                                       tile_ranges);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }

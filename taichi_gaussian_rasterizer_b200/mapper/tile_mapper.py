@@ -1,11 +1,21 @@
 """Maps 2D gaussians to the image tiles they overlap, sorted front to back per tile.
 
 Operator surface of taichi_splatting/mapper/tile_mapper.py: ``map_to_tiles`` (:202-223) and
-``pad_to_tile`` (:18-22).  Stages (csrc/geom_kernels.cu, csrc/scan_sort.cu): OBB overlap count per
-gaussian -> exclusive scan -> (tile, depth) key emission -> stable onesweep radix sort on the
-significant key bits -> tile range detection.  The only host read-back is the overlap total K,
-which sizes the key buffers (the reference synchronises the whole device twice here,
-cuda_lib/full_cumsum.cu:45 and cuda_lib/radix_sort_pairs.cu:27).
+``pad_to_tile`` (:18-22).  The reference counts overlaps per gaussian, scans, emits one 64 bit
+(tile, depth) key per overlap and radix-sorts the K keys on 48 bits (6 passes over 12 B pairs).  The
+same total order (tile, depth bits, gaussian index) is produced here "depth first" with a third of the
+traffic (csrc/geom_kernels.cu, csrc/scan_sort.cu):
+
+  1. stable radix sort of the V gaussians by their 32 bit depth key (f32 bits, or depth16) -> ``perm``;
+  2. OBB overlap count in that order -> exclusive scan -> emit bare tile ids + gaussian index in that
+     order (each tile receives its gaussians already sorted by (depth, index));
+  3. stable radix sort of the K (tile id, index) pairs on the ceil(log2 T) tile bits only (2 passes);
+  4. tile range detection.
+
+``map_to_tiles_staged`` keeps the reference's stage order (count -> scan -> 64 bit keys -> sort ->
+ranges) on the same kernels; both are bit-identical (tests/test_gpu_tile_mapper.py).  The only host
+read-back is the overlap total K, which sizes the key buffers (the reference synchronises the whole
+device twice here, cuda_lib/full_cumsum.cu:45 and cuda_lib/radix_sort_pairs.cu:27).
 """
 import ctypes
 import math
@@ -38,6 +48,17 @@ def _tile_params(n, image_size, config, use_depth16):
                         float(config.alpha_threshold))
 
 
+def _check_inputs(gaussians, depth, image_size, config):
+  assert gaussians.ndim == 2 and gaussians.shape[1] == 7, f"gaussians must be Nx7 got {gaussians.shape}"
+  assert depth.ndim == 2 and depth.shape[1] == 1, f"depths must be Nx1, got {depth.shape}"
+  assert gaussians.shape[0] == depth.shape[0]
+  N.require_cuda(gaussians, depth)
+  shape = tile_shape(image_size, config.tile_size)
+  assert shape[0] * shape[1] < MAX_TILE, \
+    f"tile dimensions {shape} for image size {image_size} exceed maximum tile count (16 bit id), try increasing tile_size"
+  return shape
+
+
 @beartype
 def map_to_tiles(gaussians: torch.Tensor, depth: torch.Tensor,
                  image_size: Tuple[Integral, Integral],
@@ -45,6 +66,59 @@ def map_to_tiles(gaussians: torch.Tensor, depth: torch.Tensor,
                  use_depth16: bool = False
                  ) -> Tuple[torch.Tensor, torch.Tensor]:
   """ maps gaussians to tiles, sorted by depth (front to back):
+    Parameters:
+     gaussians: (N, 7) torch.Tensor of packed gaussians (float32)
+     depth: (N, 1)  torch.Tensor of depths (float32, >= 0)
+     image_size: (2, ) tuple of ints, (width, height)
+     config: RasterConfig (tile_size, alpha_threshold)
+
+    Returns:
+     overlap_to_point: (K, ) int32, maps overlap index to point index
+     tile_ranges: (TH, TW, 2) int32, maps tile index to its [start, end) range of overlap indices
+  """
+  shape = _check_inputs(gaussians, depth, image_size, config)
+  with torch.no_grad():
+    device = gaussians.device
+    g = gaussians.detach().to(torch.float32).contiguous()   # the tile mapper is f32 (tile_mapper.py:12)
+    d = depth.detach().to(torch.float32).contiguous()
+    n = g.shape[0]
+    stream = N.stream_ptr(device)
+    p = _tile_params(n, image_size, config, use_depth16)
+    tile_ranges = torch.empty((*shape, 2), dtype=torch.int32, device=device)
+
+    total = 0
+    if n > 0:
+      depth_keys = torch.empty((n,), dtype=torch.int32, device=device)   # bit patterns of u32 keys
+      iota = torch.empty((n,), dtype=torch.int32, device=device)
+      N.call("gs_depth_keys", ctypes.byref(p), N.ptr(d), N.ptr(depth_keys), N.ptr(iota), stream)
+      _, perm = radix_sort_pairs(depth_keys, iota, 0, 16 if use_depth16 else 32)
+      counts = torch.empty((n,), dtype=torch.int32, device=device)
+      N.call("gs_tile_count_perm", ctypes.byref(p), N.ptr(g), N.ptr(perm), N.ptr(counts), stream)
+      cum = full_cumsum_device(counts)
+      total = int(cum[-1].item())   # host read-back of K
+
+    if total > 0:
+      tile_ids = torch.empty((total,), dtype=torch.int32, device=device)
+      values = torch.empty((total,), dtype=torch.int32, device=device)
+      N.call("gs_tile_emit_tiles", ctypes.byref(p), N.ptr(g), N.ptr(perm), N.ptr(cum), N.ptr(tile_ids), N.ptr(values),
+             stream)
+      tile_bits = max(1, (shape[0] * shape[1] - 1).bit_length())
+      tile_ids, overlap_to_point = radix_sort_pairs(tile_ids, values, 0, tile_bits)
+    else:
+      tile_ids = None
+      overlap_to_point = torch.empty((0,), dtype=torch.int32, device=device)
+
+    N.call("gs_find_ranges_tiles", ctypes.byref(p), ctypes.c_int64(total), N.ptr(tile_ids), N.ptr(tile_ranges), stream)
+    return overlap_to_point, tile_ranges
+
+
+@beartype
+def map_to_tiles_staged(gaussians: torch.Tensor, depth: torch.Tensor,
+                        image_size: Tuple[Integral, Integral],
+                        config: RasterConfig,
+                        use_depth16: bool = False
+                        ) -> Tuple[torch.Tensor, torch.Tensor]:
+  """ map_to_tiles in the reference's stage order (one 64 bit key per overlap, one K-sized sort); same result.
     Parameters:
      gaussians: (N, 7) torch.Tensor of packed gaussians (float32)
      depth: (N, 1)  torch.Tensor of depths (float32, >= 0)

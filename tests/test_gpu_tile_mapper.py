@@ -5,6 +5,7 @@ import torch
 
 import oracle
 from taichi_gaussian_rasterizer_b200 import RasterConfig, map_to_tiles
+from taichi_gaussian_rasterizer_b200.mapper.tile_mapper import map_to_tiles_staged
 from util import scene2d
 
 pytestmark = pytest.mark.gpu
@@ -18,6 +19,9 @@ def check(cuda_device, g, depth, size, cfg, depth16=False):
   assert o2p.shape == o2p_ref.shape, f"K differs: {o2p.shape} vs {o2p_ref.shape}"
   assert torch.equal(ranges.cpu(), ranges_ref)
   assert torch.equal(o2p.cpu(), o2p_ref)
+  # the reference's stage order (64 bit keys, one K-sized sort) on the same kernels gives the same bits
+  o2p_s, ranges_s = map_to_tiles_staged(g.to(cuda_device), depth.to(cuda_device), size, cfg, use_depth16=depth16)
+  assert torch.equal(o2p_s, o2p) and torch.equal(ranges_s, ranges)
   return o2p, ranges
 
 
@@ -87,3 +91,5 @@ def test_large_scene_properties(cuda_device):
   assert bool(((d[1:] >= d[:-1]) | ~same_tile).all())
   counts = oracle.tile_counts(g, size, cfg)
   assert int(counts.sum()) == K
+  o2p_s, ranges_s = map_to_tiles_staged(g.to(cuda_device), depth.to(cuda_device), size, cfg)
+  assert torch.equal(o2p_s, o2p) and torch.equal(ranges_s, ranges)
