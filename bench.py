@@ -162,6 +162,10 @@ def run_ours(args):
   stats = {}
 
   def step(from_host: bool):
+    with bucket.fused_accumulation():
+      return _step(from_host)
+
+  def _step(from_host: bool):
     bucket.zero_()
     total = torch.zeros((), device=device)
     for i in range(views):

@@ -84,6 +84,10 @@ typedef struct GsSHParams {
                                     gs_sh_bwd write dense gradient rows without atomics.  0 = no assumption. */
   int64_t num_points;      /* M */
   int64_t num_indexes;     /* V */
+  int32_t accumulate_params; /* gs_sh_bwd: grad_params += instead of = (rows outside `indexes` untouched, no zero
+                                fill); needs indexes_sorted_unique, f32, K = 3, D in {4, 16}; fuses the optimizer-side
+                                gradient accumulation of a multi-view batch into the kernel.  0 = overwrite. */
+  int32_t reserved_;
 } GsSHParams;
 
 /* params (M,K,D) positions (M,3) indexes (V) int64 camera_pos (3) -> out (V,K) */

@@ -178,7 +178,7 @@ sh_bwd_kernel(const __grid_constant__ GsSHParams p, const T* __restrict__ params
 // grad_positions need no memset and no atomics: 2 x 4 K D bytes per gaussian of traffic in total.
 constexpr int kSHDenseBlock = 128;
 
-template <int K, int D, bool FILL>
+template <int K, int D, bool FILL, bool ACC>
 __global__ void __launch_bounds__(kSHDenseBlock, 6)
 sh_bwd_dense_kernel(const __grid_constant__ GsSHParams p, const float* __restrict__ params,
                     const float* __restrict__ positions, const int64_t* __restrict__ indexes,
@@ -261,7 +261,15 @@ sh_bwd_dense_kernel(const __grid_constant__ GsSHParams p, const float* __restric
 #pragma unroll
   for (int m = 0; m < R4; ++m) {
     const int q = t + m * kSHDenseBlock, r = q / R4, part = q - r * R4;
-    if (q < nrows * R4) reinterpret_cast<float4*>(grad_params + s_idx[r + 1] * RL)[part] = s_row[r * S4 + part];
+    if (q < nrows * R4) {
+      float4* dst = reinterpret_cast<float4*>(grad_params + s_idx[r + 1] * RL) + part;
+      float4 v = s_row[r * S4 + part];
+      if (ACC) {  // accumulate into the caller's gradient buffer (multi-view batches)
+        const float4 o = *dst;
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      *dst = v;
+    }
   }
 
   if (FILL) {  // zero the rows of culled gaussians in (previous visible index, this block's last index] (+ the tail)
@@ -541,8 +549,13 @@ int gs_sh_bwd(const GsSHParams* p, const void* params, const void* positions, co
   const size_t es = p->dtype == GS_F32 ? 4 : 8;
   const bool dense = p->indexes_sorted_unique && p->dtype == GS_F32 && grad_params != nullptr && p->num_indexes > 0 &&
                      p->num_channels == 3 && (p->num_coeffs == 16 || p->num_coeffs == 4);
-  const bool fill = dense && 2 * p->num_indexes >= p->num_points;  // mostly visible: the kernel zero-fills the gaps
-  if (grad_params && !fill)
+  const bool acc = p->accumulate_params != 0;
+  if (acc && !dense) {
+    set_error("gs_sh_bwd: accumulate_params needs the dense path (indexes_sorted_unique, f32, K = 3, D = 4 or 16)");
+    return GS_ERR_UNSUPPORTED;
+  }
+  const bool fill = dense && !acc && 2 * p->num_indexes >= p->num_points;  // mostly visible: zero-fill the gaps in-kernel
+  if (grad_params && !fill && !acc)
     GS_CUDA(cudaMemsetAsync(grad_params, 0, (size_t)p->num_points * p->num_channels * p->num_coeffs * es, st));
   if (grad_positions && !fill) GS_CUDA(cudaMemsetAsync(grad_positions, 0, (size_t)p->num_points * 3 * es, st));
   if (grad_camera_pos) GS_CUDA(cudaMemsetAsync(grad_camera_pos, 0, 3 * es, st));
@@ -550,12 +563,15 @@ int gs_sh_bwd(const GsSHParams* p, const void* params, const void* positions, co
   GS_CHECK_ARG(params && positions && indexes && camera_pos && grad_out, "gs_sh_bwd: null tensor");
   if (dense) {
     const unsigned blocks = (unsigned)ceil_div(p->num_indexes, kSHDenseBlock);
-#define GS_SH_DENSE(DD, FILLV)                                                                                   \
-    sh_bwd_dense_kernel<3, DD, FILLV><<<blocks, kSHDenseBlock, 0, st>>>(                                         \
+#define GS_SH_DENSE(DD, FILLV, ACCV)                                                                             \
+    sh_bwd_dense_kernel<3, DD, FILLV, ACCV><<<blocks, kSHDenseBlock, 0, st>>>(                                   \
         *p, (const float*)params, (const float*)positions, indexes, (const float*)camera_pos,                   \
         (const float*)grad_out, (float*)grad_params, (float*)grad_positions, (float*)grad_camera_pos)
-    if (p->num_coeffs == 16) { if (fill) GS_SH_DENSE(16, true); else GS_SH_DENSE(16, false); }
-    else { if (fill) GS_SH_DENSE(4, true); else GS_SH_DENSE(4, false); }
+    if (p->num_coeffs == 16) {
+      if (acc) GS_SH_DENSE(16, false, true); else if (fill) GS_SH_DENSE(16, true, false); else GS_SH_DENSE(16, false, false);
+    } else {
+      if (acc) GS_SH_DENSE(4, false, true); else if (fill) GS_SH_DENSE(4, true, false); else GS_SH_DENSE(4, false, false);
+    }
 #undef GS_SH_DENSE
     GS_LAUNCH_CHECK();
     return GS_OK;

@@ -7,6 +7,7 @@ accumulates dense gradients locally and the ranks sum them ONCE per batch with a
 one flat bucket (NCCL over NVLink on the B200 box, gloo in the CPU tests).  Camera gradients are per
 view and stay local.
 """
+from contextlib import contextmanager
 from typing import Iterable, List, Optional, Sequence
 
 import torch
@@ -36,6 +37,22 @@ class GradientBucket:
 
   def zero_(self):
     self.flat.zero_()
+
+  @contextmanager
+  def fused_accumulation(self):
+    """Inside this context the spherical-harmonics backward adds its dense (N, 3, D) gradient straight into the
+    bucket (in the kernel) instead of materialising it for autograd to add: with V views per batch that removes
+    V - 1 read-modify-write passes over the largest gradient (576 MB at 3 M gaussians, SH degree 3).  Results are
+    the same sums; parameters the kernels cannot serve this way keep the normal autograd accumulation."""
+    from . import spherical_harmonics as sh
+    served = [p for p in self.params if p.is_cuda and p.dim() == 3 and p.grad is not None]
+    for p in served:
+      sh.register_grad_sink(p, p.grad)
+    try:
+      yield self
+    finally:
+      for p in served:
+        sh.unregister_grad_sink(p)
 
   @property
   def nbytes(self) -> int:

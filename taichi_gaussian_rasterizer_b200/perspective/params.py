@@ -61,7 +61,17 @@ class CameraParams:
 
   @property
   def camera_position(self):
-    return torch.inverse(self.T_camera_world)[0:3, 3]
+    """World position of the camera centre: ``inverse(T_camera_world)[:3, 3]`` (params.py:75-78 of the reference).
+    T_camera_world is an affine view matrix [A | t; 0 0 0 1] (the projection only ever reads its first three rows,
+    perspective/projection.py:212), so the position is -A^-1 t; A^-1 is formed from cross products.  Unlike
+    ``torch.inverse`` on a CUDA tensor this launches no LU factorisation and does not synchronise the host
+    (the info check of linalg.inv costs a device round trip per frame), and it stays differentiable."""
+    A, t = self.T_camera_world[0:3, 0:3], self.T_camera_world[0:3, 3]
+    c0 = torch.linalg.cross(A[1], A[2])
+    c1 = torch.linalg.cross(A[2], A[0])
+    c2 = torch.linalg.cross(A[0], A[1])
+    det = torch.dot(A[0], c0)
+    return -(torch.stack([c0, c1, c2], dim=1) @ t) / det
 
   def transformed(self, t: torch.Tensor) -> 'CameraParams':
     return replace(self, T_camera_world=t @ self.T_camera_world)

@@ -151,11 +151,14 @@ def render_gaussians(
   Returns:
     Rendering - rendered image, with optional depth / depth variance and per point statistics
   """
+  # issued before the projection so that these few tiny launches overlap with it instead of sitting behind the
+  # host read-back of the visible count
+  camera_position = camera_params.camera_position if use_sh else None
   gaussians2d, depths, indexes = project_to_image(gaussians, camera_params, config)
 
   if use_sh:
     features = evaluate_sh_at(gaussians.feature, gaussians.position.detach(), indexes,
-                              camera_params.camera_position, indexes_sorted_unique=True)  # visible set: ascending
+                              camera_position, indexes_sorted_unique=True)  # visible set: ascending
   else:
     features = gaussians.feature[indexes]
     assert len(features.shape) == 2, f"Features must be (N, C) if use_sh=False, got {features.shape}"

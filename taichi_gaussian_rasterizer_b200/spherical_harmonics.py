@@ -13,6 +13,20 @@ from beartype import beartype
 from . import _native as N
 
 
+# Gradient sinks: parameter storage (data_ptr) -> buffer that the backward accumulates into IN the kernel instead
+# of returning a fresh dense gradient for autograd to add (distributed.GradientBucket.fused_accumulation()).
+_grad_sinks = {}
+
+
+def register_grad_sink(param: torch.Tensor, buffer: torch.Tensor):
+  assert buffer.shape == param.shape and buffer.dtype == param.dtype and buffer.is_contiguous()
+  _grad_sinks[param.data_ptr()] = buffer
+
+
+def unregister_grad_sink(param: torch.Tensor):
+  _grad_sinks.pop(param.data_ptr(), None)
+
+
 def check_sh_degree(sh_features):
   assert len(sh_features.shape) == 3, f"SH features must have 3 dimensions, got {sh_features.shape}"
   n_sh = sh_features.shape[2]
@@ -28,11 +42,12 @@ class _SHFunction(torch.autograd.Function):
   def forward(ctx, params, points, indexes, camera_pos, sorted_unique=False):
     m, k, d = params.shape
     v = indexes.shape[0]
-    p = N.GsSHParams(N.dtype_code(params.dtype), k, d, int(bool(sorted_unique)), m, v)
+    p = N.GsSHParams(N.dtype_code(params.dtype), k, d, int(bool(sorted_unique)), m, v, 0, 0)
     out = torch.empty((v, k), dtype=params.dtype, device=params.device)
     N.call("gs_sh_fwd", ctypes.byref(p), N.ptr(params), N.ptr(points), N.ptr(indexes), N.ptr(camera_pos),
                               N.ptr(out), N.stream_ptr(params.device))
     ctx.p = p
+    ctx.sorted_unique = bool(sorted_unique)
     ctx.mark_non_differentiable(indexes)
     ctx.save_for_backward(params, points, indexes, camera_pos)
     return out
@@ -41,6 +56,16 @@ class _SHFunction(torch.autograd.Function):
   def backward(ctx, doutput):
     params, points, indexes, camera_pos = ctx.saved_tensors
     need = ctx.needs_input_grad
+    sink = _grad_sinks.get(params.data_ptr()) if need[0] else None
+    if sink is not None and ctx.sorted_unique and params.dtype == torch.float32 and params.shape[1] == 3 \
+        and params.shape[2] in (4, 16):
+      # fused accumulation: the kernel adds into the sink, autograd gets no gradient for `params`
+      p = N.GsSHParams(ctx.p.dtype, ctx.p.num_channels, ctx.p.num_coeffs, 1, ctx.p.num_points, ctx.p.num_indexes, 1, 0)
+      g_points = torch.empty_like(points) if need[1] else None
+      g_cam = torch.empty_like(camera_pos) if need[3] else None
+      N.call("gs_sh_bwd", ctypes.byref(p), N.ptr(params), N.ptr(points), N.ptr(indexes), N.ptr(camera_pos),
+             N.ptr(doutput.contiguous()), N.ptr(sink), N.ptr(g_points), N.ptr(g_cam), N.stream_ptr(params.device))
+      return None, g_points, None, g_cam, None
     g_params = torch.empty_like(params) if need[0] else None
     g_points = torch.empty_like(points) if need[1] else None
     g_cam = torch.empty_like(camera_pos) if need[3] else None

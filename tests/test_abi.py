@@ -32,14 +32,14 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
   lib = _native.lib()
-  assert lib.gs_abi_version() == 1
+  assert lib.gs_abi_version() == 2
   assert isinstance(lib.gs_last_error_string(), bytes)
 
 
 def test_struct_sizes_match_header():
   # natural alignment of the POD parameter blocks (checked against sizeof in the C++ build by layout)
   assert ctypes.sizeof(_native.GsProjectParams) == 64
-  assert ctypes.sizeof(_native.GsSHParams) == 32
+  assert ctypes.sizeof(_native.GsSHParams) == 40
   assert ctypes.sizeof(_native.GsTileParams) == 32
   assert ctypes.sizeof(_native.GsRasterParams) == 112
 
