@@ -76,7 +76,7 @@ constexpr int kMaxPasses = 8;
 constexpr unsigned kSortFlagAgg = 1u << 30, kSortFlagPrefix = 2u << 30, kSortValueMask = (1u << 30) - 1u;
 
 template <typename KeyT> struct SortCfg;
-template <> struct SortCfg<uint32_t> { static constexpr int kItems = 22; };
+template <> struct SortCfg<uint32_t> { static constexpr int kItems = 16; };
 template <> struct SortCfg<uint64_t> { static constexpr int kItems = 16; };
 
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
@@ -133,7 +133,7 @@ __global__ void radix_histogram_scan_kernel(unsigned* __restrict__ global_hist) 
 // shared histograms), chain the per-digit tile counts through decoupled look-back, reorder the tile in
 // shared memory and write digit runs back coalesced.  Stable: ranks follow input order.
 template <typename KeyT>
-__global__ void __launch_bounds__(kSortBlock)
+__global__ void __launch_bounds__(kSortBlock, 3)
 onesweep_pass_kernel(int64_t n, const KeyT* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
                      KeyT* __restrict__ keys_out, int32_t* __restrict__ vals_out, int shift, unsigned mask,
                      const unsigned* __restrict__ global_excl, unsigned* __restrict__ status,
@@ -168,12 +168,16 @@ onesweep_pass_kernel(int64_t n, const KeyT* __restrict__ keys_in, const int32_t*
   unsigned rank[ITEMS];
   unsigned* my_hist = s_warp_hist + warp * kRadix;
   const unsigned lanemask_le = 0xffffffffu >> (31 - lane);
+  // The ITEMS match operations do not depend on one another: issue them back to back (their latency is the
+  // longest in the kernel), then run the short dependent chain through the warp's shared histogram.
+  unsigned peers[ITEMS];
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) peers[k] = __match_any_sync(kFull, (unsigned)(key[k] >> shift) & mask);
 #pragma unroll
   for (int k = 0; k < ITEMS; ++k) {
     const unsigned d = (unsigned)(key[k] >> shift) & mask;
-    const unsigned peers = __match_any_sync(kFull, d);
-    const int leader = 31 - __clz(peers);
-    const unsigned cnt_le = __popc(peers & lanemask_le);
+    const int leader = 31 - __clz(peers[k]);
+    const unsigned cnt_le = __popc(peers[k] & lanemask_le);
     unsigned old = 0;
     if (lane == leader) {
       old = my_hist[d];
