@@ -379,7 +379,10 @@ def run_reference(args):
     "impl": "reference", "metric": "gaussians_px_per_s_fwd_bwd", "value": value, "unit": "gaussian*pixel/s",
     "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
     "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-    "config": {"workload": f"oracle restatement fwd+bwd on host cores, {n} gaussians (bounded sample), {w}x{h}"},
+    "config": {"workload": f"render_gaussians fwd+bwd, {W['num_gaussians']} random gaussians, SH degree {W['sh_degree']}, "
+                           f"{w}x{h}, tile {W['tile_size']}, L1 loss",
+               "sample": f"CPU restatement of the reference algorithm (oracle/) on every {CPU_SAMPLE_STRIDE}th gaussian "
+                         f"({n} gaussians), all host threads"},
     "cpu_baseline": {"value": value, "unit": "gaussian*pixel/s", "cores": oracle.num_threads(), "kind": "port",
                      "sample": sample},
     "e2e": {"value": value, "unit": "gaussian*pixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
