@@ -264,12 +264,22 @@ def run_ours(args):
   except Exception:
     pass
   peak_gbs, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json") if "hbm_gbs" in peaks else (6650.0, "fallback")
-  traffic, traffic_src = None, None
+  traffic, traffic_src, warp_inst = None, None, None
   try:   # dram bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of this workload
     t = json.loads((ROOT / "profiles" / "roofline_traffic.json").read_text())["raster_bwd_fast_kernel"]
     traffic, traffic_src = t["dram_bytes_per_launch"], t["source"]
+    warp_inst = t.get("warp_instructions_per_launch")
   except Exception:
     pass
+  # the kernel is issue bound: warp instructions per launch (ncu smsp__inst_executed.sum, same capture) over the live
+  # launch time, against 148 SMs x 4 schedulers x the SM clock sampled during the run
+  issue = None
+  if warp_inst and bwd_avg_ms > 0:
+    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    peak_ips = 148 * 4 * sm_mhz * 1e6
+    ach_ips = warp_inst / (bwd_avg_ms * 1e-3)
+    issue = {"warp_inst_per_launch": warp_inst, "achieved_warp_inst_per_s": ach_ips, "peak_warp_inst_per_s": peak_ips,
+             "frac": ach_ips / peak_ips, "source": traffic_src}
   calls, bwd_ms = stage.get("gs_raster_bwd", (0, 0.0))
   bwd_avg_ms = bwd_ms / max(calls, 1)
   bwd_bytes = K * (32 + 4 * F) + 8 * px * F + V * (28 + 4 * F)   # SURVEY.md §8(d) raster_bwd
@@ -306,7 +316,8 @@ def run_ours(args):
                  "algorithmic_bytes": bwd_bytes, "avg_launch_ms": bwd_avg_ms,
                  "note": "instruction bound kernel (SURVEY.md §8d): HBM fraction is low by construction; "
                          "blend_evals_per_s is the informative figure",
-                 "blend_evals_per_s": K * 256 / (bwd_avg_ms * 1e-3) if bwd_avg_ms > 0 else None},
+                 "blend_evals_per_s": K * 256 / (bwd_avg_ms * 1e-3) if bwd_avg_ms > 0 else None,
+                 "issue_roofline": issue},
     "stage_ms_per_frame": stage_ms,
     "clocks": clocks,
   }
