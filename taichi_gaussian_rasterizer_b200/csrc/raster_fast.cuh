@@ -72,6 +72,48 @@ __device__ __forceinline__ bool block_may_touch(float mx, float my, float a1x, f
   return fminf(qv, qh) < qmax * 1.001f + 1e-3f;
 }
 
+// ------------------------------------------------------------------------------------------------ warp reductions
+// Transposed butterfly over NV per-lane partial sums: every exchange step halves the number of live values
+// (the lane keeps the half selected by its lane bit and adds the partner's copy of it), so NV values cost about
+// NV shuffles instead of 5 NV.  reduce_owner<NV>(lane) tells which value ends up, fully summed, in v[0] of a lane.
+template <int N, int OFF>
+__device__ __forceinline__ void reduce_scatter_step(float* v, int lane) {
+  if constexpr (OFF >= 1) {
+    if constexpr (N > 1) {
+      constexpr int H = (N + 1) / 2;
+      const bool upper = (lane & OFF) != 0;
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const float hi = (i + H < N) ? v[i + H] : 0.f;
+        const float send = upper ? v[i] : hi;
+        const float keep = upper ? hi : v[i];
+        v[i] = keep + __shfl_xor_sync(kFull, send, OFF);
+      }
+      reduce_scatter_step<H, OFF / 2>(v, lane);
+    } else {
+      v[0] += __shfl_xor_sync(kFull, v[0], OFF);
+      reduce_scatter_step<1, OFF / 2>(v, lane);
+    }
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ int reduce_owner(int lane) {
+  int base = 0, cnt = NV, n = NV;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    if (n > 1) {
+      const int half = (n + 1) / 2;
+      if (lane & off) { base += half; cnt = max(cnt - half, 0); }
+      else cnt = min(cnt, half);
+      n = half;
+    } else if (lane & off) {
+      cnt = 0;
+    }
+  }
+  return cnt == 1 ? base : -1;
+}
+
 int raster_fast_pack(const GsRasterParams& p, const RasterArgs& a, bool forward, bool features, cudaStream_t st);
 
 // raster_fast_bwd_wide.cu: backward for 8..64 feature channels (one pixel per lane, image gradient in registers)

@@ -27,47 +27,6 @@ namespace gs {
 
 constexpr int kBwdBatch = 64;
 
-// Transposed butterfly over NV per-lane partial sums: every exchange step halves the number of live values
-// (the lane keeps the half selected by its lane bit and adds the partner's copy of it), so NV values cost about
-// NV shuffles instead of 5 NV.  reduce_owner<NV>(lane) tells which value ends up, fully summed, in v[0] of a lane.
-template <int N, int OFF>
-__device__ __forceinline__ void reduce_scatter_step(float* v, int lane) {
-  if constexpr (OFF >= 1) {
-    if constexpr (N > 1) {
-      constexpr int H = (N + 1) / 2;
-      const bool upper = (lane & OFF) != 0;
-#pragma unroll
-      for (int i = 0; i < H; ++i) {
-        const float hi = (i + H < N) ? v[i + H] : 0.f;
-        const float send = upper ? v[i] : hi;
-        const float keep = upper ? hi : v[i];
-        v[i] = keep + __shfl_xor_sync(kFull, send, OFF);
-      }
-      reduce_scatter_step<H, OFF / 2>(v, lane);
-    } else {
-      v[0] += __shfl_xor_sync(kFull, v[0], OFF);
-      reduce_scatter_step<1, OFF / 2>(v, lane);
-    }
-  }
-}
-
-template <int NV>
-__device__ __forceinline__ int reduce_owner(int lane) {
-  int base = 0, cnt = NV, n = NV;
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    if (n > 1) {
-      const int half = (n + 1) / 2;
-      if (lane & off) { base += half; cnt = max(cnt - half, 0); }
-      else cnt = min(cnt, half);
-      n = half;
-    } else if (lane & off) {
-      cnt = 0;
-    }
-  }
-  return cnt == 1 ? base : -1;
-}
-
 // The ellipse alpha0 p = thr in the form q(d) = d^T A d = qlim (log2 domain), for the block tests.
 struct CullConic {
   float mx, my, A00, A01, A11, r00, r11, qlim;

@@ -20,46 +20,6 @@ namespace gs {
 constexpr int kWideBatch = 32;
 constexpr int kWideThreads = 256;
 
-template <int N, int OFF>
-__device__ __forceinline__ void wide_reduce_step(float* v, int lane) {
-  if constexpr (OFF >= 1) {
-    if constexpr (N > 1) {
-      constexpr int H = (N + 1) / 2;
-      const bool upper = (lane & OFF) != 0;
-#pragma unroll
-      for (int i = 0; i < H; ++i) {
-        const float hi = (i + H < N) ? v[i + H] : 0.f;
-        const float send = upper ? v[i] : hi;
-        const float keep = upper ? hi : v[i];
-        v[i] = keep + __shfl_xor_sync(kFull, send, OFF);
-      }
-      wide_reduce_step<H, OFF / 2>(v, lane);
-    } else {
-      v[0] += __shfl_xor_sync(kFull, v[0], OFF);
-      wide_reduce_step<1, OFF / 2>(v, lane);
-    }
-  }
-}
-
-// value index (0..NV-1) whose warp total ends up in v[0] of this lane after wide_reduce_step<NV, 16>, or -1
-template <int NV>
-__device__ __forceinline__ int wide_reduce_owner(int lane) {
-  static_assert(NV <= 32, "one value per lane at most");
-  int base = 0, cnt = NV, n = NV;
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    if (n > 1) {
-      const int half = (n + 1) / 2;
-      if (lane & off) { base += half; cnt = max(cnt - half, 0); }
-      else cnt = min(cnt, half);
-      n = half;
-    } else if (lane & off) {
-      cnt = 0;
-    }
-  }
-  return cnt == 1 ? base : -1;
-}
-
 template <int FP, bool HEUR>
 __global__ void __launch_bounds__(kWideThreads)
 raster_bwd_wide_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
@@ -88,9 +48,9 @@ raster_bwd_wide_kernel(const __grid_constant__ GsRasterParams p, const float4* _
   const bool pg = p.points_requires_grad && grad_pts != nullptr;
   const bool fg = p.features_requires_grad && grad_feat != nullptr;
 
-  const int own_g = wide_reduce_owner<NG>(lane);
-  const int own_0 = wide_reduce_owner<C0>(lane);
-  const int own_1 = C1 > 0 ? wide_reduce_owner<(C1 > 0 ? C1 : 1)>(lane) : -1;
+  const int own_g = reduce_owner<NG>(lane);
+  const int own_0 = reduce_owner<C0>(lane);
+  const int own_1 = C1 > 0 ? reduce_owner<(C1 > 0 ? C1 : 1)>(lane) : -1;
 
   float G[FP];
   float W = inb ? 0.f : 1.f, RG = 0.f;
@@ -194,7 +154,7 @@ raster_bwd_wide_kernel(const __grid_constant__ GsRasterParams p, const float4* _
           if (HEUR) { vg[7] = aag * aag; vg[8] = fabsf(vg[0]) + fabsf(vg[1]); }
         }
         const int64_t idx = __float_as_int(r1.w);
-        wide_reduce_step<NG, 16>(vg, lane);
+        reduce_scatter_step<NG, 16>(vg, lane);
         if (own_g >= 0) {
           if (own_g < 7) { if (pg) atomicAdd(grad_pts + idx * 7 + own_g, vg[0]); }
           else if (HEUR) atomicAdd(heuristic + idx * 2 + (own_g - 7), vg[0]);
@@ -204,14 +164,14 @@ raster_bwd_wide_kernel(const __grid_constant__ GsRasterParams p, const float4* _
             float v[C0];
 #pragma unroll
             for (int c = 0; c < C0; ++c) v[c] = wl * G[c];
-            wide_reduce_step<C0, 16>(v, lane);
+            reduce_scatter_step<C0, 16>(v, lane);
             if (own_0 >= 0 && own_0 < F) atomicAdd(grad_feat + idx * F + own_0, v[0]);
           }
           if constexpr (C1 > 0) {
             float v[C1];
 #pragma unroll
             for (int c = 0; c < C1; ++c) v[c] = wl * G[C0 + c];
-            wide_reduce_step<C1, 16>(v, lane);
+            reduce_scatter_step<C1, 16>(v, lane);
             if (own_1 >= 0 && C0 + own_1 < F) atomicAdd(grad_feat + idx * F + C0 + own_1, v[0]);
           }
         }

@@ -104,6 +104,7 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
 #pragma unroll
   for (int c = 0; c < FP; ++c) acc[c] = 0.f;
   float W = inb ? 0.f : 1.f;
+  const int vis_owner = reduce_owner<8>(lane);  // which of a group's 8 totals this lane commits (-1: none)
 
   const int start = ranges[2 * tile], end = ranges[2 * tile + 1];
   const int C = end - start;
@@ -176,26 +177,65 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
           hit = block_may_touch(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z - l2thr, bx0, bx1, by0, by1);
         }
         unsigned mask = __ballot_sync(kFull, hit);
-        while (mask) {
-          const int j = c0 + __ffs(mask) - 1;
-          mask &= mask - 1;
-          const float4 r0 = s_r0[buf][j], r1 = s_r1[buf][j];
-          const float dx = pxf - r0.x, dy = pyf - r0.y;
-          const float tx = fmaf(dy, r0.w, dx * r0.z);
-          const float ty = fmaf(dy, r1.y, dx * r1.x);
-          const float ex = fmaf(-ty, ty, fmaf(-tx, tx, r1.z));
-          float alpha = fminf(fast_ex2(ex), cmax);
-          float weight = 0.f;
-          if (alpha > thr) {
-            weight = alpha * (1.f - W);
-            W += weight;
+        if constexpr (!VIS) {
+          while (mask) {
+            const int j = c0 + __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float4 r0 = s_r0[buf][j], r1 = s_r1[buf][j];
+            const float dx = pxf - r0.x, dy = pyf - r0.y;
+            const float tx = fmaf(dy, r0.w, dx * r0.z);
+            const float ty = fmaf(dy, r1.y, dx * r1.x);
+            const float ex = fmaf(-ty, ty, fmaf(-tx, tx, r1.z));
+            const float alpha = fminf(fast_ex2(ex), cmax);
+            if (alpha > thr) {
+              const float weight = alpha * (1.f - W);
+              W += weight;
 #pragma unroll
-            for (int c = 0; c < FP; ++c) acc[c] = fmaf(s_feat[buf][j][c], weight, acc[c]);
+              for (int c = 0; c < FP; ++c) acc[c] = fmaf(s_feat[buf][j][c], weight, acc[c]);
+            }
           }
-          if (VIS) {
-            if (vbase + j < C && __any_sync(kFull, weight > 0.f)) {
-              const float v = warp_sum(weight);
-              if (lane == 0) atomicAdd(&s_vis[buf][j], v);
+        } else {
+          // Visibility = per gaussian sum of the blend weights over all pixels.  Survivors are walked in groups of
+          // kVisGroup: every lane keeps its weight for each of them, one transposed butterfly then leaves each
+          // gaussian's warp total in one lane (about one shuffle per gaussian instead of five), which adds it to the
+          // batch's shared accumulator.
+          constexpr int kVisGroup = 8;
+          while (mask) {
+            float wv[kVisGroup];
+            int jj[kVisGroup];
+#pragma unroll
+            for (int u = 0; u < kVisGroup; ++u) {
+              wv[u] = 0.f;
+              jj[u] = -1;
+              if (mask) {  // warp uniform
+                const int j = c0 + __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float4 r0 = s_r0[buf][j], r1 = s_r1[buf][j];
+                const float dx = pxf - r0.x, dy = pyf - r0.y;
+                const float tx = fmaf(dy, r0.w, dx * r0.z);
+                const float ty = fmaf(dy, r1.y, dx * r1.x);
+                const float ex = fmaf(-ty, ty, fmaf(-tx, tx, r1.z));
+                const float alpha = fminf(fast_ex2(ex), cmax);
+                if (alpha > thr) {
+                  const float weight = alpha * (1.f - W);
+                  W += weight;
+#pragma unroll
+                  for (int c = 0; c < FP; ++c) acc[c] = fmaf(s_feat[buf][j][c], weight, acc[c]);
+                  if (vbase + j < C) wv[u] = weight;  // stale re-reads (Q1) do not count, as in the reference
+                }
+                jj[u] = j;
+              }
+            }
+            bool any_w = false;
+#pragma unroll
+            for (int u = 0; u < kVisGroup; ++u) any_w = any_w || wv[u] > 0.f;
+            if (__any_sync(kFull, any_w)) {
+              reduce_scatter_step<kVisGroup, 16>(wv, lane);
+              const int own = vis_owner;
+              int jo = -1;
+#pragma unroll
+              for (int u = 0; u < kVisGroup; ++u) jo = (own == u) ? jj[u] : jo;
+              if (jo >= 0 && wv[0] != 0.f) atomicAdd(&s_vis[buf][jo], wv[0]);
             }
           }
         }
