@@ -193,6 +193,42 @@ int gs_raster_bwd(const GsRasterParams* p, const void* gaussians2d, const void* 
                   const void* grad_image, void* grad_gaussians, void* grad_features,
                   void* point_heuristic, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ visibility-weighted sparse optimizers
+ * (the consumers of `visibility`): replace the per point step kernels of
+ * optim/fractional_adam.py:7-85 and optim/fractional_laprop.py:7-86 together with the torch glue around them
+ * (optim/fractional.py:108-151,186: local basis, mask_lr, point_lr, saturate, parameter update;
+ * optim/visibility_aware.py:37-48,88-97: running visibility, weights, gradient rescaling).  f32 only, like the
+ * reference's kernels.  `indexes` (M) int64 must be unique. */
+typedef enum GsOptAlgorithm { GS_OPT_ADAM = 0, GS_OPT_LAPROP = 1 } GsOptAlgorithm;
+typedef enum GsOptGroupType { GS_OPT_SCALAR = 0, GS_OPT_VECTOR = 1, GS_OPT_LOCAL_VECTOR = 2 } GsOptGroupType;
+
+typedef struct GsOptParams {
+  int32_t algorithm;       /* GsOptAlgorithm */
+  int32_t group_type;      /* GsOptGroupType */
+  int32_t dims;            /* D: columns of the parameter viewed as (N, D) */
+  int32_t bias_correction;
+  int64_t num_points;      /* N */
+  int64_t num_visible;     /* M */
+  double lr, beta1, beta2, eps;
+  double grad_scale;       /* visibility-aware optimizers: grad * grad_scale / (visibility + vis_smooth) */
+  double vis_smooth;       /* < 0: no visibility rescaling of the gradient (Fractional* / Sparse*) */
+} GsOptParams;
+
+/* running_vis (N), total_weight (N) updated in place; weight_out (M) = visibility / max(updated running vis, eps) */
+int gs_opt_update_visibility(int64_t num_visible, const int64_t* indexes, const float* visibility,
+                             float* running_vis, float* total_weight, float* weight_out, double vis_beta,
+                             double eps, void* stream);
+/* total_weight[indexes] += weight (Fractional* / Sparse*: optim/fractional.py:176) */
+int gs_opt_accumulate_weight(int64_t num_visible, const int64_t* indexes, const float* weight,
+                             float* total_weight, void* stream);
+/* One fused update of a parameter group over the visible points.  grad, param (N, D); m (N, D); v (N, D) for scalar
+ * groups, (N) for vector groups; total_weight (N) ALREADY updated for this step; weight (M); visibility (M) or NULL;
+ * mask_lr (D) or NULL; point_lr (N) or NULL; basis (M, D, D) row major for local_vector groups (D = 2 or 3).
+ * m, v and param are updated in place. */
+int gs_opt_step(const GsOptParams* p, const int64_t* indexes, const float* weight, const float* visibility,
+                const float* grad, float* m, float* v, const float* total_weight, float* param,
+                const float* mask_lr, const float* point_lr, const float* basis, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,7 @@ EXPORTS = [
   "gs_radix_sort_pairs_workspace_bytes", "gs_radix_sort_pairs", "gs_find_ranges",
   "gs_depth_keys", "gs_tile_count_perm", "gs_tile_emit_tiles", "gs_find_ranges_tiles",
   "gs_raster_workspace_bytes", "gs_raster_fwd", "gs_raster_bwd",
+  "gs_opt_update_visibility", "gs_opt_accumulate_weight", "gs_opt_step",
 ]
 
 
@@ -55,6 +56,13 @@ class GsRasterParams(ctypes.Structure):
               ("num_points", ctypes.c_int64), ("num_overlaps", ctypes.c_int64),
               ("clamp_max_alpha", ctypes.c_double), ("alpha_threshold", ctypes.c_double),
               ("saturate_threshold", ctypes.c_double), ("forward_exit_transmittance", ctypes.c_double)]
+
+
+class GsOptParams(ctypes.Structure):
+  _fields_ = [("algorithm", ctypes.c_int32), ("group_type", ctypes.c_int32), ("dims", ctypes.c_int32),
+              ("bias_correction", ctypes.c_int32), ("num_points", ctypes.c_int64), ("num_visible", ctypes.c_int64),
+              ("lr", ctypes.c_double), ("beta1", ctypes.c_double), ("beta2", ctypes.c_double), ("eps", ctypes.c_double),
+              ("grad_scale", ctypes.c_double), ("vis_smooth", ctypes.c_double)]
 
 
 _lib = None

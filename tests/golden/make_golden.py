@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Generates the golden fixtures of tests/golden/*.npz FROM THE REFERENCE ITSELF (needs /root/reference).
 
-  python tests/golden/make_golden.py [--only tile_map,raster,projection,sh] [--quick]
+  python tests/golden/make_golden.py [--only tile_map,raster,projection,sh,optim] [--quick]
 
 Two sources, both the reference's own code, unmodified, imported from /root/reference:
 
@@ -12,7 +12,8 @@ Two sources, both the reference's own code, unmodified, imported from /root/refe
   here): ``map_to_tiles`` (tile_overlaps / generate_sort_keys / find_ranges kernels + the OBB grid query),
   ``rasterize_with_tiles`` forward and backward (rasterizer/forward.py, backward.py, incl. shared-memory
   staging, warp votes and shuffle reductions), ``project_kernel`` and ``evaluate_sh_at_kernel`` forward
-  -> tile_map.npz, raster.npz and the ``ti_*`` entries of projection.npz / sh.npz.
+  -> tile_map.npz, raster.npz and the ``ti_*`` entries of projection.npz / sh.npz; and the reference's optimizer
+  classes (optim/fractional.py, optim/visibility_aware.py with their Taichi step kernels) -> optim.npz.
 
 Inputs are produced by the reference's own generators (taichi_splatting/tests/random_data.py) with the seeds
 listed below and stored in the fixtures, so the tests in tests/test_golden.py need neither /root/reference nor
@@ -48,7 +49,7 @@ from taichi_splatting.tests.random_data import random_2d_gaussians, random_3d_ga
 
 
 def np_(t):
-  return t.detach().cpu().numpy()
+  return t.detach().cpu().numpy().copy()   # a copy: in-place optimizer updates must not alias stored snapshots
 
 
 def grad_(t):
@@ -191,12 +192,79 @@ def make_sh(out):
   out["num_cases"] = np.array(len(SH_CASES))
 
 
-MAKERS = {"tile_map": make_tile_map, "projection": make_projection, "sh": make_sh, "raster": make_raster}
+# ----------------------------------------------------------------------------------------------- optimizers
+OPTIM_CLASSES = ["FractionalAdam", "FractionalLaProp", "SparseAdam", "SparseLaProp", "VisibilityAwareAdam",
+                 "VisibilityAwareLaProp"]
+OPTIM_STEPS, OPTIM_N = 4, 60
+
+
+def optim_problem(seed):
+  """Four parameter groups shaped like the 2D fit of examples/fit_image_gaussians.py:262-273 (position in the local
+  basis, scalar log-scales with a per column mask, vector features with per point rates, an (N, 3, 4) scalar block)."""
+  torch.manual_seed(seed)
+  n = OPTIM_N
+  params = dict(position=torch.randn(n, 2), log_scaling=torch.randn(n, 2), feature=torch.randn(n, 3),
+                sh=torch.randn(n, 3, 4))
+  groups = dict(position=dict(lr=0.1, type="local_vector"),
+                log_scaling=dict(lr=0.05, type="scalar", mask_lr=torch.tensor([1.0, 0.25])),
+                feature=dict(lr=0.02, type="vector", point_lr=torch.rand(n) + 0.5),
+                sh=dict(lr=0.01, type="scalar"))
+  steps = []
+  for _ in range(OPTIM_STEPS):
+    idx = torch.nonzero(torch.rand(n) < 0.6).squeeze(1)
+    m = idx.shape[0]
+    steps.append(dict(indexes=idx, visibility=torch.rand(m) * 3 + 0.01, weight=torch.rand(m) * 1.5 + 0.05,
+                      basis=torch.randn(m, 2, 2) * 0.3 + 1.5 * torch.eye(2),
+                      grads={k: torch.randn_like(v) for k, v in params.items()}))
+  return params, groups, steps
+
+
+def make_optim(out):
+  import taichi_splatting.optim.fractional as ref_frac
+  import taichi_splatting.optim.visibility_aware as ref_vis
+  for ci, cls_name in enumerate(OPTIM_CLASSES):
+    params, groups, steps = optim_problem(100 + ci)
+    tensors = {k: torch.nn.Parameter(v.clone()) for k, v in params.items()}
+    cls = getattr(ref_vis, cls_name, None) or getattr(ref_frac, cls_name)
+    opt = cls([dict(params=[tensors[k]], name=k, **g) for k, g in groups.items()])
+    for k, v in params.items():
+      out[f"{cls_name}_init_{k}"] = np_(v)
+    for k, g in groups.items():
+      for extra in ("mask_lr", "point_lr"):
+        if extra in g:
+          out[f"{cls_name}_{extra}_{k}"] = np_(g[extra])
+    for si, st in enumerate(steps):
+      for k, t in tensors.items():
+        t.grad = st["grads"][k].clone()
+        out[f"{cls_name}_s{si}_grad_{k}"] = np_(st["grads"][k])
+      out[f"{cls_name}_s{si}_indexes"] = np_(st["indexes"])
+      out[f"{cls_name}_s{si}_basis"] = np_(st["basis"])
+      if cls_name.startswith("Visibility"):
+        out[f"{cls_name}_s{si}_visibility"] = np_(st["visibility"])
+        opt.step(indexes=st["indexes"], visibility=st["visibility"], basis=st["basis"])
+      elif cls_name.startswith("Sparse"):
+        opt.step(indexes=st["indexes"], basis=st["basis"])
+      else:
+        out[f"{cls_name}_s{si}_weight"] = np_(st["weight"])
+        opt.step(indexes=st["indexes"], weight=st["weight"], basis=st["basis"])
+      for k, t in tensors.items():
+        out[f"{cls_name}_s{si}_param_{k}"] = np_(t)
+    for k, t in tensors.items():
+      for sk, sv in opt.state[t].items():
+        out[f"{cls_name}_state_{k}_{sk}"] = np_(sv)
+    print(f"optim {cls_name}: {OPTIM_STEPS} steps, state keys "
+          f"{ {k: sorted(opt.state[t].keys()) for k, t in tensors.items()} }")
+  out["classes"] = np.array(OPTIM_CLASSES)
+  out["num_steps"] = np.array(OPTIM_STEPS)
+
+
+MAKERS = {"tile_map": make_tile_map, "projection": make_projection, "sh": make_sh, "raster": make_raster,
+          "optim": make_optim}
 
 
 def main():
   ap = argparse.ArgumentParser()
-  ap.add_argument("--only", default=",".join(MAKERS))
+  ap.add_argument("--only", default="tile_map,projection,sh,raster,optim")
   ap.add_argument("--quick", action="store_true", help="raster: only the two cheapest cases")
   args = ap.parse_args()
   for name in args.only.split(","):

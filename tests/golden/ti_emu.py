@@ -465,6 +465,12 @@ class NdArray:
     self.shape = tuple(self.a.shape[:ann.ndim])
     self.scalar_elem = isinstance(ann.elem, DType)
 
+  def __iter__(self):
+    """``for i in ndarray`` in a Taichi kernel ranges over the array's indices (struct-for)."""
+    if self.ndim == 1:
+      return iter(range(self.shape[0]))
+    return iter(np.ndindex(*self.shape))
+
   def __getitem__(self, idx):
     r = self.a[idx]
     if isinstance(r, np.ndarray):
@@ -809,6 +815,9 @@ def build_taichi_module():
   ti = _module("taichi")
   for d in (f16, f32, f64, i8, i16, i32, i64, u8, u16, u32, u64):
     setattr(ti, d.name, d)
+  ti.int8, ti.int16, ti.int32, ti.int64 = i8, i16, i32, i64   # long spellings used by the optimizer kernels
+  ti.uint8, ti.uint16, ti.uint32, ti.uint64 = u8, u16, u32, u64
+  ti.float16, ti.float32, ti.float64 = f16, f32, f64
   ti.cpu, ti.cuda, ti.gpu = "cpu", "cuda", "gpu"
   ti.init = lambda *a, **k: None
   ti.reset = lambda *a, **k: None
@@ -831,7 +840,7 @@ def build_taichi_module():
 
   ti.Matrix = Matrix
 
-  tmath = _module("taichi.math", pi=math.pi, clamp=clamp, normalize=normalize,
+  tmath = _module("taichi.math", pi=math.pi, clamp=clamp, normalize=normalize, dot=lambda a, b: a.dot(b),
                   isinf=lambda x: bool(np.isinf(x)), isnan=lambda x: bool(np.isnan(x)))
   for n in (1, 2, 3, 4):
     if n > 1:
