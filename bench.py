@@ -271,6 +271,10 @@ def run_ours(args):
     warp_inst = t.get("warp_instructions_per_launch")
   except Exception:
     pass
+  calls, bwd_ms = stage.get("gs_raster_bwd", (0, 0.0))
+  bwd_avg_ms = bwd_ms / max(calls, 1)
+  bwd_bytes = K * (32 + 4 * F) + 8 * px * F + V * (28 + 4 * F)   # SURVEY.md §8(d) raster_bwd
+  achieved = bwd_bytes / (bwd_avg_ms * 1e-3) / 1e9 if bwd_avg_ms > 0 else 0.0
   # the kernel is issue bound: warp instructions per launch (ncu smsp__inst_executed.sum, same capture) over the live
   # launch time, against 148 SMs x 4 schedulers x the SM clock sampled during the run
   issue = None
@@ -280,10 +284,6 @@ def run_ours(args):
     ach_ips = warp_inst / (bwd_avg_ms * 1e-3)
     issue = {"warp_inst_per_launch": warp_inst, "achieved_warp_inst_per_s": ach_ips, "peak_warp_inst_per_s": peak_ips,
              "frac": ach_ips / peak_ips, "source": traffic_src}
-  calls, bwd_ms = stage.get("gs_raster_bwd", (0, 0.0))
-  bwd_avg_ms = bwd_ms / max(calls, 1)
-  bwd_bytes = K * (32 + 4 * F) + 8 * px * F + V * (28 + 4 * F)   # SURVEY.md §8(d) raster_bwd
-  achieved = bwd_bytes / (bwd_avg_ms * 1e-3) / 1e9 if bwd_avg_ms > 0 else 0.0
   fwd_calls, fwd_ms = stage.get("gs_raster_fwd", (0, 0.0))
   stage_ms = {k: round(v[1] / args.steps / views, 4) for k, v in sorted(stage.items())}
   launches = sum(KERNELS_PER_CALL.get(k, 0) * v[0] for k, v in stage.items())
