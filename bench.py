@@ -387,6 +387,10 @@ def run_reference(args):
   import oracle
   from taichi_gaussian_rasterizer_b200 import RasterConfig
   W = dict(WORKLOAD)
+  if args.num_gaussians:
+    W["num_gaussians"] = args.num_gaussians
+  if args.image_size:
+    W["image_size"] = tuple(args.image_size)
   config = RasterConfig(tile_size=W["tile_size"])
   n, gaussians, camera = cpu_sample(W, CPU_SAMPLE_STRIDE)
   w, h = W["image_size"]

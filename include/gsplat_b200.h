@@ -94,6 +94,13 @@ typedef struct GsSHParams {
 int gs_sh_fwd(const GsSHParams* p, const void* params, const void* positions,
               const int64_t* indexes, const void* camera_pos, void* out, void* stream);
 
+/* Same, but the number of valid indexes is still on the device (count_dev, one int32, e.g. num_visible of
+ * gs_project_fwd): p->num_indexes is the CAPACITY of indexes / out, rows >= *count_dev are left untouched.  Lets the
+ * caller enqueue the SH evaluation before it reads the visible count back. */
+int gs_sh_fwd_counted(const GsSHParams* p, const void* params, const void* positions,
+                      const int64_t* indexes, const void* camera_pos, const int32_t* count_dev,
+                      void* out, void* stream);
+
 /* grad_out (V,K) -> grad_params (M,K,D) grad_positions (M,3) grad_camera_pos (3); each fully
  * written (zeroed then accumulated; repeated indexes are summed).  Any may be NULL. */
 int gs_sh_bwd(const GsSHParams* p, const void* params, const void* positions,
@@ -166,7 +173,9 @@ typedef struct GsRasterParams {
   int32_t points_requires_grad, features_requires_grad;
   int32_t emulate_stale_tail;        /* reproduce forward.py:88; 1 for reference parity */
   int32_t pixel_stride_x, pixel_stride_y; /* validated like backward.py:33-34, otherwise a hint */
-  int32_t workspace_holds_packed;    /* bwd: workspace still holds the records packed by fwd */
+  int32_t workspace_holds_packed;    /* bwd: the workspace is untouched since a gs_raster_fwd call made with the same
+                                        gaussians / features AND a requires_grad flag set (fwd then packs the
+                                        backward records too); 0 = repack */
   int32_t reserved_;
   int64_t num_points;                /* V */
   int64_t num_overlaps;              /* K */

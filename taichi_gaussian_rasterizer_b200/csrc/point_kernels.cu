@@ -78,9 +78,12 @@ template <> __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sq
 template <typename T, int D>
 __global__ void __launch_bounds__(256)
 sh_fwd_kernel(const __grid_constant__ GsSHParams p, const T* __restrict__ params, const T* __restrict__ positions,
-              const int64_t* __restrict__ indexes, const T* __restrict__ cam, T* __restrict__ out) {
+              const int64_t* __restrict__ indexes, const T* __restrict__ cam, T* __restrict__ out,
+              const int32_t* __restrict__ count_dev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.num_indexes) return;
+  // count_dev: number of valid indexes still on the device (gs_sh_fwd_counted); p.num_indexes is then the capacity
+  const int64_t nv = count_dev ? (int64_t)*count_dev : p.num_indexes;
+  if (i >= nv) return;
   const int64_t idx = indexes[i];
   const int K = p.num_channels;
   T dx = positions[3 * idx] - cam[0], dy = positions[3 * idx + 1] - cam[1], dz = positions[3 * idx + 2] - cam[2];
@@ -494,13 +497,13 @@ using namespace gs;
 template <typename T>
 static int sh_dispatch(bool backward, const GsSHParams* p, const void* params, const void* positions,
                        const int64_t* indexes, const void* cam, const void* grad_out, void* out_or_gparams,
-                       void* gpos, void* gcam, cudaStream_t st) {
+                       void* gpos, void* gcam, cudaStream_t st, const int32_t* count_dev = nullptr) {
   const int64_t blocks = ceil_div(p->num_indexes, 256);
 #define GS_SH_CASE(DD)                                                                                              \
   case DD:                                                                                                          \
     if (!backward)                                                                                                  \
       sh_fwd_kernel<T, DD><<<(unsigned)blocks, 256, 0, st>>>(*p, (const T*)params, (const T*)positions, indexes,    \
-                                                             (const T*)cam, (T*)out_or_gparams);                    \
+                                                             (const T*)cam, (T*)out_or_gparams, count_dev);         \
     else                                                                                                            \
       sh_bwd_kernel<T, DD><<<(unsigned)blocks, 256, 0, st>>>(*p, (const T*)params, (const T*)positions, indexes,    \
                                                              (const T*)cam, (const T*)grad_out, (T*)out_or_gparams, \
@@ -538,6 +541,19 @@ int gs_sh_fwd(const GsSHParams* p, const void* params, const void* positions, co
   return p->dtype == GS_F32
              ? sh_dispatch<float>(false, p, params, positions, indexes, camera_pos, nullptr, out, nullptr, nullptr, st)
              : sh_dispatch<double>(false, p, params, positions, indexes, camera_pos, nullptr, out, nullptr, nullptr, st);
+}
+
+int gs_sh_fwd_counted(const GsSHParams* p, const void* params, const void* positions, const int64_t* indexes,
+                      const void* camera_pos, const int32_t* count_dev, void* out, void* stream) {
+  int rc = check_sh(p, "gs_sh_fwd_counted");
+  if (rc != GS_OK) return rc;
+  if (p->num_indexes == 0) return GS_OK;
+  GS_CHECK_ARG(params && positions && indexes && camera_pos && out && count_dev, "gs_sh_fwd_counted: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  return p->dtype == GS_F32 ? sh_dispatch<float>(false, p, params, positions, indexes, camera_pos, nullptr, out, nullptr,
+                                                 nullptr, st, count_dev)
+                            : sh_dispatch<double>(false, p, params, positions, indexes, camera_pos, nullptr, out,
+                                                  nullptr, nullptr, st, count_dev);
 }
 
 int gs_sh_bwd(const GsSHParams* p, const void* params, const void* positions, const int64_t* indexes,

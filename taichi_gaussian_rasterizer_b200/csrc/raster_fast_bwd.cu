@@ -262,8 +262,10 @@ static int launch_bwd_fast(const GsRasterParams& p, const RasterArgs& a, const f
 bool raster_bwd_fast_supported(const GsRasterParams& p) { return raster_fast_supported(p) && p.num_features <= 7; }
 
 int raster_bwd_fast(const GsRasterParams& p, const RasterArgs& a, cudaStream_t st) {
-  int rc = raster_fast_pack(p, a, /*forward=*/false, /*features=*/!p.workspace_holds_packed, st);
-  if (rc != GS_OK) return rc;
+  if (!p.workspace_holds_packed) {  // otherwise gs_raster_fwd (called with the requires_grad flags) left both there
+    int rc = raster_fast_pack(p, a, /*forward=*/false, /*features=*/true, st);
+    if (rc != GS_OK) return rc;
+  }
   const FastLayout L = fast_layout(p);
   unsigned char* ws = (unsigned char*)a.workspace;
   const float4* rec = (const float4*)(ws + L.off_recB);

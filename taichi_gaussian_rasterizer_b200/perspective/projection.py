@@ -20,11 +20,23 @@ from ..data_types import Gaussians3D, RasterConfig
 from .params import CameraParams
 
 
+_pinned = {}
+
+
+def _pinned_count(device) -> torch.Tensor:
+  """One pinned int32 per device for the asynchronous read-back of the visible count (reads are serialised by the
+  event wait that follows each copy)."""
+  key = (device.type, device.index)
+  if key not in _pinned:
+    _pinned[key] = torch.zeros((1,), dtype=torch.int32).pin_memory()
+  return _pinned[key]
+
+
 class _ProjectFunction(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, position, log_scaling, rotation, alpha_logit, T_camera_world, projection,
-              image_size, depth_range, blur_cov, clamp_margin, alpha_threshold):
+              image_size, depth_range, blur_cov, clamp_margin, alpha_threshold, after_launch=None):
     dtype, device = position.dtype, position.device
     n = position.shape[0]
     params = N.GsProjectParams(N.dtype_code(dtype), int(image_size[0]), int(image_size[1]), n,
@@ -40,7 +52,19 @@ class _ProjectFunction(torch.autograd.Function):
                                N.ptr(alpha_logit), N.ptr(T_camera_world), N.ptr(projection), N.ptr(points),
                                N.ptr(depth), N.ptr(indexes), N.ptr(count), N.ptr(ws),
                                ctypes.c_size_t(ws.numel()), N.stream_ptr(device))
-    v = int(count.item())  # the one host read-back: the number of gaussians in view
+    if after_launch is None:
+      v = int(count.item())  # the one host read-back: the number of gaussians in view
+    else:
+      # The copy of the count is enqueued FIRST (pinned buffer + event), then the caller's work that only needs the
+      # device-side visible set (render_gaussians: the SH evaluation); the host waits on the event, not on the
+      # stream, so that work runs on the GPU while the host is blocked and while it prepares the next launches.
+      host_count = _pinned_count(device)
+      host_count.copy_(count, non_blocking=True)
+      ready = torch.cuda.Event()
+      ready.record(torch.cuda.current_stream(device))
+      after_launch(indexes, count)
+      ready.synchronize()
+      v = int(host_count.item())
     points, depth, indexes = points[:v], depth[:v], indexes[:v]
 
     ctx.params = params
@@ -59,7 +83,7 @@ class _ProjectFunction(torch.autograd.Function):
       N.ptr(alpha_logit), N.ptr(T_camera_world), N.ptr(projection), N.ptr(indexes),
       N.ptr(dpoints.contiguous()), N.ptr(ddepth.contiguous()), *[N.ptr(g) for g in grads],
       N.stream_ptr(position.device))
-    return (*grads, None, None, None, None, None)
+    return (*grads, None, None, None, None, None, None)
 
 
 @beartype
@@ -73,18 +97,21 @@ def apply(position: torch.Tensor, log_scaling: torch.Tensor,
 
           blur_cov: float = 0.0,
           clamp_margin: float = 0.15,
-          alpha_threshold: float = 1. / 255.
+          alpha_threshold: float = 1. / 255.,
+          after_launch=None
           ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+  """``after_launch(indexes_capacity, count_device)`` (extension): called after the projection kernel is enqueued and
+  before the visible count is read back; see render_gaussians."""
   dtype = position.dtype
   N.require_cuda(position, log_scaling, rotation, alpha_logit, T_camera_world, projection)
   return _ProjectFunction.apply(
     position.contiguous(), log_scaling.contiguous(), rotation.contiguous(), alpha_logit.contiguous(),
     T_camera_world.to(dtype).contiguous(), projection.to(dtype).contiguous(),
-    image_size, depth_range, blur_cov, clamp_margin, alpha_threshold)
+    image_size, depth_range, blur_cov, clamp_margin, alpha_threshold, after_launch)
 
 
 @beartype
-def project_to_image(gaussians: Gaussians3D, camera_params: CameraParams, config: RasterConfig,
+def project_to_image(gaussians: Gaussians3D, camera_params: CameraParams, config: RasterConfig, after_launch=None
                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
   """
   Project 3D gaussians to 2D gaussians in image space using perspective projection
@@ -103,4 +130,5 @@ def project_to_image(gaussians: Gaussians3D, camera_params: CameraParams, config
     camera_params.depth_range,
     config.blur_cov,
     config.clamp_margin,
-    config.alpha_threshold)
+    config.alpha_threshold,
+    after_launch)

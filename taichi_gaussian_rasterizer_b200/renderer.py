@@ -16,7 +16,7 @@ from .perspective import CameraParams
 from .perspective.projection import project_to_image
 from .rasterizer.function import rasterize_with_tiles
 from .rendering import Rendering
-from .spherical_harmonics import evaluate_sh_at
+from .spherical_harmonics import evaluate_sh_at, launch_sh_forward_counted
 from .torch_lib.projection import ndc_depth
 
 
@@ -47,11 +47,24 @@ def render_gaussians(
   # issued before the projection so that these few tiny launches overlap with it instead of sitting behind the
   # host read-back of the visible count
   camera_position = camera_params.camera_position if use_sh else None
-  gaussians2d, depths, indexes = project_to_image(gaussians, camera_params, config)
+  early = {}
+  if use_sh and gaussians.feature.is_contiguous() and gaussians.position.is_contiguous() \
+      and gaussians.position.dtype == gaussians.feature.dtype:
+    # the SH colours only need the device-side visible set: enqueue them right behind the projection kernel, before
+    # the host blocks on the visible count, so the GPU does not idle across that read-back
+    def early_sh(indexes_capacity, count_device):
+      early["sh"] = launch_sh_forward_counted(gaussians.feature.detach(), gaussians.position.detach(),
+                                              indexes_capacity, count_device,
+                                              camera_position.detach().to(gaussians.feature.dtype).contiguous())
+  else:
+    early_sh = None
+  gaussians2d, depths, indexes = project_to_image(gaussians, camera_params, config, after_launch=early_sh)
 
   if use_sh:
+    pre = early["sh"][:indexes.shape[0]] if "sh" in early else None
     features = evaluate_sh_at(gaussians.feature, gaussians.position.detach(), indexes,
-                              camera_position, indexes_sorted_unique=True)  # visible set: ascending
+                              camera_position, indexes_sorted_unique=True,   # visible set: ascending
+                              precomputed=pre)
   else:
     features = gaussians.feature[indexes]
     assert len(features.shape) == 2, f"Features must be (N, C) if use_sh=False, got {features.shape}"

@@ -6,6 +6,7 @@ Taichi autodiff, :118-134 and :154-161).  Layout is channel major: (M, K, (degre
 """
 import ctypes
 import math
+from typing import Optional
 
 import torch
 from beartype import beartype
@@ -39,13 +40,17 @@ def check_sh_degree(sh_features):
 class _SHFunction(torch.autograd.Function):
 
   @staticmethod
-  def forward(ctx, params, points, indexes, camera_pos, sorted_unique=False):
+  def forward(ctx, params, points, indexes, camera_pos, sorted_unique=False, precomputed=None):
     m, k, d = params.shape
     v = indexes.shape[0]
     p = N.GsSHParams(N.dtype_code(params.dtype), k, d, int(bool(sorted_unique)), m, v, 0, 0)
-    out = torch.empty((v, k), dtype=params.dtype, device=params.device)
-    N.call("gs_sh_fwd", ctypes.byref(p), N.ptr(params), N.ptr(points), N.ptr(indexes), N.ptr(camera_pos),
-                              N.ptr(out), N.stream_ptr(params.device))
+    if precomputed is not None:     # evaluated ahead of time on the capacity buffers (launch_sh_forward_counted)
+      assert precomputed.shape == (v, k)
+      out = precomputed
+    else:
+      out = torch.empty((v, k), dtype=params.dtype, device=params.device)
+      N.call("gs_sh_fwd", ctypes.byref(p), N.ptr(params), N.ptr(points), N.ptr(indexes), N.ptr(camera_pos),
+             N.ptr(out), N.stream_ptr(params.device))
     ctx.p = p
     ctx.sorted_unique = bool(sorted_unique)
     ctx.mark_non_differentiable(indexes)
@@ -65,14 +70,28 @@ class _SHFunction(torch.autograd.Function):
       g_cam = torch.empty_like(camera_pos) if need[3] else None
       N.call("gs_sh_bwd", ctypes.byref(p), N.ptr(params), N.ptr(points), N.ptr(indexes), N.ptr(camera_pos),
              N.ptr(doutput.contiguous()), N.ptr(sink), N.ptr(g_points), N.ptr(g_cam), N.stream_ptr(params.device))
-      return None, g_points, None, g_cam, None
+      return None, g_points, None, g_cam, None, None
     g_params = torch.empty_like(params) if need[0] else None
     g_points = torch.empty_like(points) if need[1] else None
     g_cam = torch.empty_like(camera_pos) if need[3] else None
     N.call("gs_sh_bwd", ctypes.byref(ctx.p), N.ptr(params), N.ptr(points), N.ptr(indexes),
                               N.ptr(camera_pos), N.ptr(doutput.contiguous()), N.ptr(g_params), N.ptr(g_points),
                               N.ptr(g_cam), N.stream_ptr(params.device))
-    return g_params, g_points, None, g_cam, None
+    return g_params, g_points, None, g_cam, None, None
+
+
+def launch_sh_forward_counted(sh_params, positions, indexes_capacity, count_device, camera_pos) -> torch.Tensor:
+  """Enqueue the SH evaluation for a visible set whose SIZE is still on the device: ``indexes_capacity`` (N,) holds
+  the valid indexes in its first ``count_device[0]`` rows.  Returns the (N, K) output buffer; rows past the count are
+  uninitialised.  Used by render_gaussians to keep the GPU busy across the host read-back of the visible count."""
+  check_sh_degree(sh_params)
+  m, k, d = sh_params.shape
+  cap = indexes_capacity.shape[0]
+  p = N.GsSHParams(N.dtype_code(sh_params.dtype), k, d, 1, m, cap, 0, 0)
+  out = torch.empty((cap, k), dtype=sh_params.dtype, device=sh_params.device)
+  N.call("gs_sh_fwd_counted", ctypes.byref(p), N.ptr(sh_params), N.ptr(positions), N.ptr(indexes_capacity),
+         N.ptr(camera_pos), N.ptr(count_device), N.ptr(out), N.stream_ptr(sh_params.device))
+  return out
 
 
 @beartype
@@ -80,14 +99,17 @@ def evaluate_sh_at(sh_params: torch.Tensor,   # M, K, (degree + 1)^2  (usually K
                    positions: torch.Tensor,   # M, 3
                    indexes: torch.Tensor,     # V   (int64 indexes into the M gaussians)
                    camera_pos: torch.Tensor,  # 3
-                   indexes_sorted_unique: bool = False
+                   indexes_sorted_unique: bool = False,
+                   precomputed: Optional[torch.Tensor] = None
                    ) -> torch.Tensor:         # V, K
   """``indexes_sorted_unique`` (extension, not in the reference signature): promise that ``indexes`` is strictly
   ascending, as the visible set returned by project_to_image is; the backward then writes dense gradient rows
-  without atomics or a memset (csrc/point_kernels.cu sh_bwd_dense_kernel).  Results are identical."""
+  without atomics or a memset (csrc/point_kernels.cu sh_bwd_dense_kernel).  Results are identical.
+  ``precomputed``: the forward values already evaluated by launch_sh_forward_counted for exactly these inputs; the
+  call then only builds the autograd node."""
   check_sh_degree(sh_params)
   N.require_cuda(sh_params, positions, indexes, camera_pos)
   dtype = sh_params.dtype
   return _SHFunction.apply(sh_params.contiguous(), positions.to(dtype).contiguous(),
                            indexes.to(torch.int64).contiguous(), camera_pos.to(dtype).contiguous(),
-                           indexes_sorted_unique)
+                           indexes_sorted_unique, precomputed)
