@@ -150,7 +150,11 @@ int gs_find_ranges(const GsTileParams* p, int64_t num_overlaps, const void* sort
  * traffic: (1) gs_depth_keys: u32 depth key (f32 bits, or depth16) + index per gaussian; sort them (stable) to get
  * `perm`; (2) gs_tile_count_perm / gs_tile_emit_tiles visit the gaussians in that order and emit bare tile ids;
  * (3) a stable sort on the tile id bits only; (4) gs_find_ranges_tiles.  perm (V) int32, tile_ids (K) u32. */
-int gs_depth_keys(const GsTileParams* p, const float* depth, uint32_t* keys, int32_t* values, void* stream);
+/* near_plane > 0: `depth` is linear camera depth and the key is built from its NDC value
+ * 1 - (1/d - 1/far) / (1/near - 1/far) (torch_lib/projection.py:120-123), evaluated with the same f32 operation
+ * sequence as torch's eager CUDA kernels; near_plane <= 0: `depth` already is the sort depth. */
+int gs_depth_keys(const GsTileParams* p, const float* depth, double near_plane, double far_plane,
+                  uint32_t* keys, int32_t* values, void* stream);
 int gs_tile_count_perm(const GsTileParams* p, const float* gaussians, const int32_t* perm, int32_t* counts,
                        void* stream);
 int gs_tile_emit_tiles(const GsTileParams* p, const float* gaussians, const int32_t* perm, const int32_t* cum,

@@ -223,11 +223,17 @@ __global__ void find_ranges_kernel(int64_t n, const KeyT* __restrict__ keys, int
 
 // u32 sort keys of the depth-first pipeline: the f32 bit pattern of the depth (mapper/tile_mapper.py:34-40) or
 // the 16 bit quantisation (:53-59); values = gaussian index.
-__global__ void depth_keys_kernel(int64_t n, int use_depth16, const float* __restrict__ depth,
-                                  uint32_t* __restrict__ keys, int32_t* __restrict__ values) {
+// to_ndc: the depth is linear camera depth and the sort depth is its NDC value, computed with exactly the four f32
+// operations torch's eager CUDA kernels perform for  1 - (1/d - 1/far) / (1/near - 1/far)  (reciprocal, subtract,
+// multiply by the reciprocal of the scalar divisor, subtract from one), so the keys carry the same bits as
+// ndc_depth() on the device.  This translation unit is compiled with -fmad=false.
+__global__ void depth_keys_kernel(int64_t n, int use_depth16, int to_ndc, float inv_far, float inv_den,
+                                  const float* __restrict__ depth, uint32_t* __restrict__ keys,
+                                  int32_t* __restrict__ values) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float d = depth[i];
+  float d = depth[i];
+  if (to_ndc) d = 1.0f - ((1.0f / d) - inv_far) * inv_den;
   keys[i] = use_depth16 ? (make_key32(d, 0) & 0xffffu) : (uint32_t)(make_key64(d, 0) & 0xffffffffull);
   values[i] = (int32_t)i;
 }
@@ -355,13 +361,22 @@ int gs_find_ranges(const GsTileParams* p, int64_t num_overlaps, const void* sort
 
 // ---- depth-first tile mapping (same outputs as count -> emit_keys -> sort on 32 + tile bits -> find_ranges):
 // sort the V gaussians by depth key once, visit them in that order, then a stable sort on the tile id only.
-int gs_depth_keys(const GsTileParams* p, const float* depth, uint32_t* keys, int32_t* values, void* stream) {
+int gs_depth_keys(const GsTileParams* p, const float* depth, double near_plane, double far_plane, uint32_t* keys,
+                  int32_t* values, void* stream) {
   int rc = check_tile_params(p, "gs_depth_keys");
   if (rc != GS_OK) return rc;
   if (p->num_points == 0) return GS_OK;
   GS_CHECK_ARG(depth && keys && values, "gs_depth_keys: null tensor");
+  const bool to_ndc = near_plane > 0.0;
+  GS_CHECK_ARG(!to_ndc || far_plane > near_plane, "gs_depth_keys: far_plane must exceed near_plane");
+  float inv_far = 0.f, inv_den = 0.f;
+  if (to_ndc) {  // scalars as torch forms them: Python doubles cast to f32, the divisor inverted in f32
+    inv_far = (float)(1.0 / far_plane);
+    const float den = (float)(1.0 / near_plane - 1.0 / far_plane);
+    inv_den = 1.0f / den;
+  }
   depth_keys_kernel<<<(unsigned)ceil_div(p->num_points, 256), 256, 0, (cudaStream_t)stream>>>(
-      p->num_points, p->use_depth16, depth, keys, values);
+      p->num_points, p->use_depth16, to_ndc ? 1 : 0, inv_far, inv_den, depth, keys, values);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }

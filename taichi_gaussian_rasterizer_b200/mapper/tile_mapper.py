@@ -76,7 +76,16 @@ def map_to_tiles(gaussians: torch.Tensor, depth: torch.Tensor,
      overlap_to_point: (K, ) int32, maps overlap index to point index
      tile_ranges: (TH, TW, 2) int32, maps tile index to its [start, end) range of overlap indices
   """
+  return _map_to_tiles(gaussians, depth, image_size, config, use_depth16, ndc_range=None)
+
+
+def _map_to_tiles(gaussians, depth, image_size, config, use_depth16=False, ndc_range=None):
+  """map_to_tiles; with ``ndc_range=(near, far)`` the ``depth`` column is LINEAR camera depth and the sort depth is
+  its NDC value, formed inside the key kernel with torch's own f32 operation sequence (bit-identical keys to
+  ``map_to_tiles(g, ndc_depth(depth, near, far), ...)`` — tests/test_gpu_tile_mapper.py), which saves the
+  render path four elementwise launches per frame (render_projected)."""
   shape = _check_inputs(gaussians, depth, image_size, config)
+  near, far = (float(ndc_range[0]), float(ndc_range[1])) if ndc_range is not None else (0.0, 0.0)
   with torch.no_grad():
     device = gaussians.device
     g = gaussians.detach().to(torch.float32).contiguous()   # the tile mapper is f32 (tile_mapper.py:12)
@@ -90,7 +99,8 @@ def map_to_tiles(gaussians: torch.Tensor, depth: torch.Tensor,
     if n > 0:
       depth_keys = torch.empty((n,), dtype=torch.int32, device=device)   # bit patterns of u32 keys
       iota = torch.empty((n,), dtype=torch.int32, device=device)
-      N.call("gs_depth_keys", ctypes.byref(p), N.ptr(d), N.ptr(depth_keys), N.ptr(iota), stream)
+      N.call("gs_depth_keys", ctypes.byref(p), N.ptr(d), ctypes.c_double(near), ctypes.c_double(far),
+             N.ptr(depth_keys), N.ptr(iota), stream)
       _, perm = radix_sort_pairs(depth_keys, iota, 0, 16 if use_depth16 else 32)
       counts = torch.empty((n,), dtype=torch.int32, device=device)
       N.call("gs_tile_count_perm", ctypes.byref(p), N.ptr(g), N.ptr(perm), N.ptr(counts), stream)

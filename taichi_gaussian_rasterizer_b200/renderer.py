@@ -11,7 +11,7 @@ import torch
 from beartype import beartype
 
 from .data_types import Gaussians3D, RasterConfig
-from .mapper.tile_mapper import map_to_tiles
+from .mapper.tile_mapper import _map_to_tiles, map_to_tiles
 from .perspective import CameraParams
 from .perspective.projection import project_to_image
 from .rasterizer.function import rasterize_with_tiles
@@ -101,14 +101,19 @@ def render_projected(indexes: torch.Tensor, gaussians2d: torch.Tensor,
   """Tile-map and rasterize gaussians that are already projected (renderer.py:183-231 of the reference).
   Gaussians are ordered by NDC depth inside every tile; depth features stay linear unless use_ndc_depth."""
   size = camera_params.image_size
-  sort_depths = ndc_depth(depths, camera_params.near_plane, camera_params.far_plane)
+  ndc_range = (camera_params.near_plane, camera_params.far_plane)
 
   if render_depth:   # two extra leading channels: depth and depth^2, blended like any other feature
-    depths = sort_depths if use_ndc_depth else depths
+    if use_ndc_depth:
+      depths = ndc_depth(depths, *ndc_range)
     features = torch.cat([depths, depths ** 2, features], dim=1)
 
-  overlap_to_point, tile_ranges = map_to_tiles(gaussians2d, sort_depths, image_size=size, config=config,
-                                               use_depth16=use_depth16)
+  # gaussians are ordered by NDC depth inside every tile; the key kernel forms it from the linear depth
+  if render_depth and use_ndc_depth:
+    overlap_to_point, tile_ranges = map_to_tiles(gaussians2d, depths, image_size=size, config=config,
+                                                 use_depth16=use_depth16)
+  else:
+    overlap_to_point, tile_ranges = _map_to_tiles(gaussians2d, depths, size, config, use_depth16, ndc_range=ndc_range)
   ranges = tile_ranges.view(-1, 2)
   raster = rasterize_with_tiles(gaussians2d, features, tile_overlap_ranges=ranges,
                                 overlap_to_point=overlap_to_point, image_size=size, config=config)

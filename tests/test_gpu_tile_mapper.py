@@ -93,3 +93,22 @@ def test_large_scene_properties(cuda_device):
   assert int(counts.sum()) == K
   o2p_s, ranges_s = map_to_tiles_staged(g.to(cuda_device), depth.to(cuda_device), size, cfg)
   assert torch.equal(o2p_s, o2p) and torch.equal(ranges_s, ranges)
+
+
+def test_fused_ndc_sort_depth_is_bit_identical(cuda_device):
+  """render_projected hands LINEAR depth to the key kernel, which forms the NDC sort depth itself; the tile map must
+  equal map_to_tiles on torch's ndc_depth() of the same depths bit for bit (same f32 operation sequence)."""
+  from taichi_gaussian_rasterizer_b200.mapper.tile_mapper import _map_to_tiles
+  from taichi_gaussian_rasterizer_b200.torch_lib.projection import inverse_ndc_depth, ndc_depth
+  cfg = RasterConfig()
+  size = (640, 480)
+  for seed, (near, far) in enumerate([(0.1, 100.0), (0.05, 1000.0), (1.0, 7.5)]):
+    g, unit, _ = scene2d(70 + seed, 200_000, size, scale_factor=1.0)
+    linear = inverse_ndc_depth(unit.clamp(1e-6, 1 - 1e-6), near, far).to(cuda_device)   # depths between near and far
+    gd = g.to(cuda_device)
+    a_o2p, a_ranges = map_to_tiles(gd, ndc_depth(linear, near, far), size, cfg)
+    b_o2p, b_ranges = _map_to_tiles(gd, linear, size, cfg, ndc_range=(near, far))
+    assert torch.equal(a_ranges, b_ranges) and torch.equal(a_o2p, b_o2p)
+    a16, _ = map_to_tiles(gd, ndc_depth(linear, near, far), size, cfg, use_depth16=True)
+    b16, _ = _map_to_tiles(gd, linear, size, cfg, use_depth16=True, ndc_range=(near, far))
+    assert torch.equal(a16, b16)
