@@ -88,7 +88,6 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
   __shared__ __align__(16) float4 s_r0[2][kFwdBatch];
   __shared__ __align__(16) float4 s_r1[2][kFwdBatch];
   __shared__ __align__(16) float s_feat[2][kFwdBatch][FP];
-  __shared__ float s_vis[2][kFwdBatch];
 
   const int tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int tw = (p.image_width + kFastTile - 1) / kFastTile;
@@ -107,7 +106,6 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
 #pragma unroll
   for (int c = 0; c < FP; ++c) acc[c] = 0.f;
   float W = inb ? 0.f : 1.f;
-  const int vis_owner = reduce_owner<8>(lane);  // which of a group's 8 totals this lane commits (-1: none)
 
   const int start = ranges[2 * tile], end = ranges[2 * tile + 1];
   const int C = end - start;
@@ -127,7 +125,6 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
         if (t < kFwdBatch) {
           cp_async16(&s_r0[buf][slot], rec + 2 * (int64_t)idx);
           cp_async16(&s_r1[buf][slot], rec + 2 * (int64_t)idx + 1);
-          if (VIS) s_vis[buf][slot] = 0.f;
         } else {
 #pragma unroll
           for (int c = 0; c < FP; c += 4) cp_async16(&s_feat[buf][slot][c], featP + (int64_t)idx * FP + c);
@@ -140,7 +137,6 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
           const int idx = o2p[start + (v < C ? v : v - kFastTileArea)];
           cp_async16(&s_r0[buf][t], rec + 2 * (int64_t)idx);
           cp_async16(&s_r1[buf][t], rec + 2 * (int64_t)idx + 1);
-          if (VIS) s_vis[buf][t] = 0.f;
         }
       }
       constexpr int CH = FP / 4;
@@ -180,78 +176,37 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
           hit = block_may_touch(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z - l2thr, bx0, bx1, by0, by1);
         }
         unsigned mask = __ballot_sync(kFull, hit);
-        if constexpr (!VIS) {
-          while (mask) {
-            const int j = c0 + __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float4 r0 = s_r0[buf][j], r1 = s_r1[buf][j];
-            const float dx = pxf - r0.x, dy = pyf - r0.y;
-            const float tx = fmaf(dy, r0.w, dx * r0.z);
-            const float ty = fmaf(dy, r1.y, dx * r1.x);
-            const float ex = fmaf(-ty, ty, fmaf(-tx, tx, r1.z));
-            const float alpha = fminf(fast_ex2(ex), cmax);
-            if (alpha > thr) {
-              const float weight = alpha * (1.f - W);
-              W += weight;
+        while (mask) {
+          const int j = c0 + __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float4 r0 = s_r0[buf][j], r1 = s_r1[buf][j];
+          const float dx = pxf - r0.x, dy = pyf - r0.y;
+          const float tx = fmaf(dy, r0.w, dx * r0.z);
+          const float ty = fmaf(dy, r1.y, dx * r1.x);
+          const float ex = fmaf(-ty, ty, fmaf(-tx, tx, r1.z));
+          const float alpha = fminf(fast_ex2(ex), cmax);
+          float weight = 0.f;
+          if (alpha > thr) {
+            weight = alpha * (1.f - W);
+            W += weight;
 #pragma unroll
-              for (int c = 0; c < FP; ++c) acc[c] = fmaf(s_feat[buf][j][c], weight, acc[c]);
-            }
+            for (int c = 0; c < FP; ++c) acc[c] = fmaf(s_feat[buf][j][c], weight, acc[c]);
           }
-        } else {
-          // Visibility = per gaussian sum of the blend weights over all pixels.  Survivors are walked in groups of
-          // kVisGroup: every lane keeps its weight for each of them, one transposed butterfly then leaves each
-          // gaussian's warp total in one lane (about one shuffle per gaussian instead of five), which adds it to the
-          // batch's shared accumulator.
-          constexpr int kVisGroup = 8;
-          while (mask) {
-            float wv[kVisGroup];
-            int jj[kVisGroup];
-#pragma unroll
-            for (int u = 0; u < kVisGroup; ++u) {
-              wv[u] = 0.f;
-              jj[u] = -1;
-              if (mask) {  // warp uniform
-                const int j = c0 + __ffs(mask) - 1;
-                mask &= mask - 1;
-                const float4 r0 = s_r0[buf][j], r1 = s_r1[buf][j];
-                const float dx = pxf - r0.x, dy = pyf - r0.y;
-                const float tx = fmaf(dy, r0.w, dx * r0.z);
-                const float ty = fmaf(dy, r1.y, dx * r1.x);
-                const float ex = fmaf(-ty, ty, fmaf(-tx, tx, r1.z));
-                const float alpha = fminf(fast_ex2(ex), cmax);
-                if (alpha > thr) {
-                  const float weight = alpha * (1.f - W);
-                  W += weight;
-#pragma unroll
-                  for (int c = 0; c < FP; ++c) acc[c] = fmaf(s_feat[buf][j][c], weight, acc[c]);
-                  if (vbase + j < C) wv[u] = weight;  // stale re-reads (Q1) do not count, as in the reference
-                }
-                jj[u] = j;
-              }
-            }
-            bool any_w = false;
-#pragma unroll
-            for (int u = 0; u < kVisGroup; ++u) any_w = any_w || wv[u] > 0.f;
-            if (__any_sync(kFull, any_w)) {
-              reduce_scatter_step<kVisGroup, 16>(wv, lane);
-              const int own = vis_owner;
-              int jo = -1;
-#pragma unroll
-              for (int u = 0; u < kVisGroup; ++u) jo = (own == u) ? jj[u] : jo;
-              if (jo >= 0 && wv[0] != 0.f) atomicAdd(&s_vis[buf][jo], wv[0]);
-            }
+          if constexpr (VIS) {
+            // visibility[g] += sum over the warp's pixels of the blend weight.  The weights are in [0, 1): summed as
+            // 24 bit fixed point with ONE redux.sync (integer warp reduction) instead of five float shuffles; the
+            // quantisation (2^-25 per pixel) is far below the f32 rounding of the running sums.  Stale re-reads (Q1,
+            // vbase + j >= C) do not count, as in the reference, whose write-back skips those slots.
+            const unsigned wq = (vbase + j < C) ? __float2uint_rn(weight * 16777216.f) : 0u;
+            const unsigned total_q = __reduce_add_sync(kFull, wq);
+            if (lane == 0 && total_q != 0u)
+              atomicAdd(visibility + __float_as_int(r1.w), (float)total_q * (1.f / 16777216.f));
           }
         }
       }
       warp_done = __all_sync(kFull, (1.f - W) <= exit_T);
     }
     const bool all_done = __syncthreads_and(warp_done);
-    if (VIS) {
-      if (t < n_in && vbase + t < C) {
-        const float v = s_vis[buf][t];
-        if (v != 0.f) atomicAdd(visibility + __float_as_int(s_r1[buf][t].w), v);
-      }
-    }
     if (all_done) break;
   }
   cp_async_wait<0>();
