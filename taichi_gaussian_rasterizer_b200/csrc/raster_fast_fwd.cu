@@ -78,16 +78,18 @@ int raster_fast_pack(const GsRasterParams& p, const RasterArgs& a, bool forward,
 
 // ------------------------------------------------------------------------------------------------ forward
 // BATCH = staged tile-list entries per buffer: 128 for narrow features, 64 for FP >= 16 (shared memory budget).
-template <int FP, bool VIS, int BATCH>
+// FOURTH: with FP = 4 the fourth accumulator is only needed when F = 4 (it is padding for F <= 3).
+template <int FP, bool VIS, int BATCH, bool FOURTH = true>
 __global__ void __launch_bounds__(kFwdThreads)
 raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
                        const float* __restrict__ featP, const int32_t* __restrict__ ranges,
                        const int32_t* __restrict__ o2p, float* __restrict__ image, float* __restrict__ image_alpha,
                        float* __restrict__ visibility) {
   constexpr int kFwdBatch = BATCH;
-  __shared__ __align__(16) float4 s_r0[2][kFwdBatch];
-  __shared__ __align__(16) float4 s_r1[2][kFwdBatch];
-  __shared__ __align__(16) float s_feat[2][kFwdBatch][FP];
+  // one staged entry = {record (2 x float4), feature row (FP / 4 x float4)} in consecutive 16 B units: one address
+  // per entry in the inner loop.  U is odd so that a lane-per-entry LDS.128 (the cull) is bank-conflict free.
+  constexpr int U = (2 + FP / 4) | 1;
+  __shared__ __align__(16) float4 s_e[2][kFwdBatch][U];
 
   const int tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int tw = (p.image_width + kFastTile - 1) / kFastTile;
@@ -123,11 +125,11 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
         const int k = v < C ? v : v - kFastTileArea;
         const int idx = o2p[start + k];
         if (t < kFwdBatch) {
-          cp_async16(&s_r0[buf][slot], rec + 2 * (int64_t)idx);
-          cp_async16(&s_r1[buf][slot], rec + 2 * (int64_t)idx + 1);
+          cp_async16(&s_e[buf][slot][0], rec + 2 * (int64_t)idx);
+          cp_async16(&s_e[buf][slot][1], rec + 2 * (int64_t)idx + 1);
         } else {
 #pragma unroll
-          for (int c = 0; c < FP; c += 4) cp_async16(&s_feat[buf][slot][c], featP + (int64_t)idx * FP + c);
+          for (int c = 0; c < FP; c += 4) cp_async16(&s_e[buf][slot][2 + c / 4], featP + (int64_t)idx * FP + c);
         }
       }
     } else {  // wide rows: records by the first BATCH threads, the 16 B feature chunks spread over the whole CTA
@@ -135,8 +137,8 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
         const int v = b * kFwdBatch + t;
         if (v < total) {
           const int idx = o2p[start + (v < C ? v : v - kFastTileArea)];
-          cp_async16(&s_r0[buf][t], rec + 2 * (int64_t)idx);
-          cp_async16(&s_r1[buf][t], rec + 2 * (int64_t)idx + 1);
+          cp_async16(&s_e[buf][t][0], rec + 2 * (int64_t)idx);
+          cp_async16(&s_e[buf][t][1], rec + 2 * (int64_t)idx + 1);
         }
       }
       constexpr int CH = FP / 4;
@@ -147,7 +149,7 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
         const int v = b * kFwdBatch + slot;
         if (q < kFwdBatch * CH && v < total) {
           const int idx = o2p[start + (v < C ? v : v - kFastTileArea)];
-          cp_async16(&s_feat[buf][slot][part * 4], featP + (int64_t)idx * FP + part * 4);
+          cp_async16(&s_e[buf][slot][2 + part], featP + (int64_t)idx * FP + part * 4);
         }
       }
     }
@@ -172,25 +174,31 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
         const int e = c0 + lane;
         bool hit = false;
         if (e < n_in) {
-          const float4 r0 = s_r0[buf][e], r1 = s_r1[buf][e];
+          const float4 r0 = s_e[buf][e][0], r1 = s_e[buf][e][1];
           hit = block_may_touch(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z - l2thr, bx0, bx1, by0, by1);
         }
         unsigned mask = __ballot_sync(kFull, hit);
         while (mask) {
           const int j = c0 + __ffs(mask) - 1;
           mask &= mask - 1;
-          const float4 r0 = s_r0[buf][j], r1 = s_r1[buf][j];
+          const float4* ent = s_e[buf][j];
+          const float4 r0 = ent[0], r1 = ent[1];
           const float dx = pxf - r0.x, dy = pyf - r0.y;
           const float tx = fmaf(dy, r0.w, dx * r0.z);
           const float ty = fmaf(dy, r1.y, dx * r1.x);
           const float ex = fmaf(-ty, ty, fmaf(-tx, tx, r1.z));
           const float alpha = fminf(fast_ex2(ex), cmax);
-          float weight = 0.f;
-          if (alpha > thr) {
-            weight = alpha * (1.f - W);
-            W += weight;
+          // branch-free blend: a pixel below the threshold adds weight 0 (exactly nothing), which costs less than
+          // the divergent branch did (the cull leaves few gaussians that miss every pixel of the block)
+          const float weight = alpha > thr ? alpha * (1.f - W) : 0.f;
+          W += weight;
 #pragma unroll
-            for (int c = 0; c < FP; ++c) acc[c] = fmaf(s_feat[buf][j][c], weight, acc[c]);
+          for (int c4 = 0; c4 < FP / 4; ++c4) {
+            const float4 f4 = ent[2 + c4];
+            acc[4 * c4] = fmaf(f4.x, weight, acc[4 * c4]);
+            acc[4 * c4 + 1] = fmaf(f4.y, weight, acc[4 * c4 + 1]);
+            acc[4 * c4 + 2] = fmaf(f4.z, weight, acc[4 * c4 + 2]);
+            if (FP > 4 || FOURTH) acc[4 * c4 + 3] = fmaf(f4.w, weight, acc[4 * c4 + 3]);
           }
           if constexpr (VIS) {
             // visibility[g] += sum over the warp's pixels of the blend weight.  The weights are in [0, 1): summed as
@@ -237,9 +245,16 @@ int raster_fwd_fast(const GsRasterParams& p, const RasterArgs& a, cudaStream_t s
   const int tiles = tiles_wide(p) * tiles_high(p);
   const bool vis = p.compute_visibility && a.visibility != nullptr;
 #define GS_FWD_LAUNCH(FPV, VISV, BATCHV)                                                                           \
-  raster_fwd_fast_kernel<FPV, VISV, BATCHV><<<tiles, kFwdThreads, 0, st>>>(p, rec, featP, a.tile_ranges,            \
-                                                                           a.overlap_to_point, (float*)a.image,     \
-                                                                           (float*)a.image_alpha, (float*)a.visibility)
+  do {                                                                                                             \
+    if (FPV == 4 && p.num_features < 4)                                                                            \
+      raster_fwd_fast_kernel<FPV, VISV, BATCHV, false><<<tiles, kFwdThreads, 0, st>>>(                             \
+          p, rec, featP, a.tile_ranges, a.overlap_to_point, (float*)a.image, (float*)a.image_alpha,                \
+          (float*)a.visibility);                                                                                   \
+    else                                                                                                           \
+      raster_fwd_fast_kernel<FPV, VISV, BATCHV, true><<<tiles, kFwdThreads, 0, st>>>(                              \
+          p, rec, featP, a.tile_ranges, a.overlap_to_point, (float*)a.image, (float*)a.image_alpha,                \
+          (float*)a.visibility);                                                                                   \
+  } while (0)
 #define GS_FWD_CASE(FPV, BATCHV) \
   case FPV: if (vis) GS_FWD_LAUNCH(FPV, true, BATCHV); else GS_FWD_LAUNCH(FPV, false, BATCHV); break
   switch (L.FP) {
