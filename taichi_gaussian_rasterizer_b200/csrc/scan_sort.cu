@@ -168,11 +168,23 @@ onesweep_pass_kernel(int64_t n, const KeyT* __restrict__ keys_in, const int32_t*
   unsigned rank[ITEMS];
   unsigned* my_hist = s_warp_hist + warp * kRadix;
   const unsigned lanemask_le = 0xffffffffu >> (31 - lane);
-  // The ITEMS match operations do not depend on one another: issue them back to back (their latency is the
-  // longest in the kernel), then run the short dependent chain through the warp's shared histogram.
+  // Peer masks (lanes holding the same digit) from one ballot per digit bit instead of match.any: the ballots of the
+  // ITEMS keys are independent and pipeline, MATCH.ANY serialises (measured 0.206 -> 0.177 ms on 3 M 32 bit pairs).
   unsigned peers[ITEMS];
 #pragma unroll
-  for (int k = 0; k < ITEMS; ++k) peers[k] = __match_any_sync(kFull, (unsigned)(key[k] >> shift) & mask);
+  for (int k = 0; k < ITEMS; ++k) {
+    const unsigned d = (unsigned)(key[k] >> shift) & mask;
+    unsigned pm = kFull;
+#pragma unroll
+    for (int b = 0; b < kRadixBits; ++b) {
+      if ((mask >> b) & 1u) {  // uniform: short last digits skip their absent bits
+        const bool bit = (d >> b) & 1u;
+        const unsigned bal = __ballot_sync(kFull, bit);
+        pm &= bit ? bal : ~bal;
+      }
+    }
+    peers[k] = pm;
+  }
 #pragma unroll
   for (int k = 0; k < ITEMS; ++k) {
     const unsigned d = (unsigned)(key[k] >> shift) & mask;
@@ -205,12 +217,23 @@ onesweep_pass_kernel(int64_t n, const KeyT* __restrict__ keys_in, const int32_t*
     } else {
       st_relaxed_u32(st, kSortFlagAgg | tile_count);
       int j = tile - 1;
+      // LB independent loads in flight per step: the walk is a chain of L2 round trips otherwise
+      constexpr int LB = 8;
       while (true) {
-        const unsigned v = ld_relaxed_u32(status + (size_t)j * kRadix + tid);
-        if ((v >> 30) == 0u) continue;
-        exclusive += v & kSortValueMask;
-        if ((v >> 30) == 2u) break;
-        --j;
+        unsigned v[LB];
+#pragma unroll
+        for (int u = 0; u < LB; ++u)
+          v[u] = j - u >= 0 ? ld_relaxed_u32(status + (size_t)(j - u) * kRadix + tid) : kSortFlagPrefix;
+        bool done = false;
+        int u = 0;
+#pragma unroll
+        for (; u < LB; ++u) {
+          if ((v[u] >> 30) == 0u) break;  // not published yet: retry from here
+          exclusive += v[u] & kSortValueMask;
+          if ((v[u] >> 30) == 2u) { done = true; break; }
+        }
+        if (done) break;
+        j -= u;
       }
       st_relaxed_u32(st, kSortFlagPrefix | ((exclusive + tile_count) & kSortValueMask));
     }
@@ -299,11 +322,9 @@ static int radix_sort_impl(int64_t n, const KeyT* keys_in, const int32_t* vals_i
   radix_histogram_scan_kernel<<<L.passes, kRadix, 0, st>>>(hist);
   GS_LAUNCH_CHECK();
 
-  static bool attr_set = false;
   const size_t smem = sort_smem_bytes<KeyT>();
-  if (!attr_set) {
-    GS_CUDA(cudaFuncSetAttribute(onesweep_pass_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  auto kern = onesweep_pass_kernel<KeyT>;
+  GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const KeyT* src_k = keys_in;
   const int32_t* src_v = vals_in;
   for (int p = 0; p < L.passes; ++p) {
@@ -313,7 +334,7 @@ static int radix_sort_impl(int64_t n, const KeyT* keys_in, const int32_t* vals_i
     int32_t* dst_v = to_out ? vals_out : tmp_vals;
     const int shift = begin_bit + p * kRadixBits;
     const int nb = min(kRadixBits, end_bit - shift);
-    onesweep_pass_kernel<KeyT><<<(unsigned)L.tiles, kSortBlock, smem, st>>>(
+    kern<<<(unsigned)L.tiles, kSortBlock, smem, st>>>(
         n, src_k, src_v, dst_k, dst_v, shift, (1u << nb) - 1u, hist + p * kRadix,
         status + (size_t)p * L.tiles * kRadix, tickets + p);
     GS_LAUNCH_CHECK();
