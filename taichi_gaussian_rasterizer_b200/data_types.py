@@ -133,8 +133,9 @@ class _TensorFields:
   def __getitem__(self, index):
     return self.apply(lambda t: t[index], batch_size=None)
 
-  def to_tensordict(self) -> Dict[str, torch.Tensor]:
-    return dict(self._tensor_items())
+  def to_tensordict(self):
+    from .tensor_dict import TensorDict
+    return TensorDict(dict(self._tensor_items()), batch_size=self.batch_size)
 
   def to_dict(self) -> Dict[str, torch.Tensor]:
     return dict(self._tensor_items())
