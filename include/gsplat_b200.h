@@ -200,7 +200,10 @@ int gs_raster_fwd(const GsRasterParams* p, const void* gaussians2d, const void* 
 
 /* image (H,W,F: forward output) grad_image (H,W,F) -> grad_gaussians (V,7) grad_features (V,F)
  * (each zeroed by the callee; NULL if the matching *_requires_grad is 0) and point_heuristic
- * (V,2), ACCUMULATED in place like backward.py:227-228 (the caller zero-fills it in forward). */
+ * (V,2), ACCUMULATED in place like backward.py:227-228 (the caller zero-fills it in forward).
+ * Quantile mode (use_alpha_blending = 0; forward.py:107-114 has no backward in the reference): every pixel's image
+ * gradient is added to the feature gradient of the gaussian the forward selected for it (the walk is replayed, `image`
+ * may be NULL), grad_gaussians is zero (the selection is piecewise constant), point_heuristic is left untouched. */
 int gs_raster_bwd(const GsRasterParams* p, const void* gaussians2d, const void* features,
                   const int32_t* tile_ranges, const int32_t* overlap_to_point, const void* image,
                   const void* grad_image, void* grad_gaussians, void* grad_features,

@@ -63,10 +63,9 @@ int gs_raster_bwd(const GsRasterParams* p, const void* gaussians2d, const void* 
                   void* grad_features, void* point_heuristic, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_raster(p, "gs_raster_bwd");
   if (rc != GS_OK) return rc;
-  GS_CHECK_ARG(tile_ranges && image && grad_image, "gs_raster_bwd: null tensor");
+  GS_CHECK_ARG(tile_ranges && grad_image && (image || !p->use_alpha_blending), "gs_raster_bwd: null tensor");
   GS_CHECK_ARG(p->num_points == 0 || (gaussians2d && features), "gs_raster_bwd: null gaussians / features");
   GS_CHECK_ARG(p->num_overlaps == 0 || overlap_to_point, "gs_raster_bwd: null overlap_to_point");
-  GS_CHECK_ARG(p->use_alpha_blending, "gs_raster_bwd: backward requires use_alpha_blending (reference has none for quantile mode)");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t es = p->dtype == GS_F32 ? 4 : 8;
   if (grad_gaussians && p->num_points > 0) GS_CUDA(cudaMemsetAsync(grad_gaussians, 0, (size_t)p->num_points * 7 * es, st));

@@ -13,11 +13,20 @@
 
 namespace gs {
 
-template <typename T, int MAXF, bool AA, bool BLEND, int NT>
+// MODE kBlend: alpha blending.  kQuantile: the feature of the gaussian at which the accumulated weight first reaches
+// 1 - saturate_threshold (forward.py:107-114).  kQuantileBwd: the same walk, but instead of writing the image each
+// pixel adds its image gradient to the feature gradient of the gaussian it selected — the backward of quantile mode
+// (the reference has none, tests/test_rasterizer.py:92-94).  The selection is piecewise constant in
+// the gaussians' geometry and opacity, so their gradient is zero almost everywhere and is returned as zeros.
+constexpr int kBlend = 1, kQuantile = 0, kQuantileBwd = 2;
+
+template <typename T, int MAXF, bool AA, int MODE, int NT>
 __global__ void __launch_bounds__(NT) raster_fwd_generic_kernel(const __grid_constant__ GsRasterParams p, const T* __restrict__ pts,
                                           const T* __restrict__ feat, const int32_t* __restrict__ ranges,
                                           const int32_t* __restrict__ o2p, T* __restrict__ image,
-                                          T* __restrict__ image_alpha, T* __restrict__ visibility) {
+                                          T* __restrict__ image_alpha, T* __restrict__ visibility,
+                                          const T* __restrict__ grad_image, T* __restrict__ grad_feat) {
+  constexpr bool BLEND = MODE == kBlend;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int ts = p.tile_size, A = ts * ts, F = p.num_features;
   T* s_pts = reinterpret_cast<T*>(smem_raw);
@@ -32,11 +41,16 @@ __global__ void __launch_bounds__(NT) raster_fwd_generic_kernel(const __grid_con
   const T pxf = T(px) + T(0.5), pyf = T(py) + T(0.5);
   const T thr = T(p.alpha_threshold), cmax = T(p.clamp_max_alpha);
   const T sat_w = T(1.0 - p.saturate_threshold), exit_T = T(p.forward_exit_transmittance);
-  const bool want_vis = p.compute_visibility && visibility != nullptr;
+  const bool want_vis = MODE != kQuantileBwd && p.compute_visibility && visibility != nullptr;
 
-  T acc[MAXF];
+  T acc[MAXF];  // kQuantileBwd: the pixel's image gradient
 #pragma unroll
   for (int c = 0; c < MAXF; ++c) acc[c] = T(0);
+  if (MODE == kQuantileBwd && inb) {
+#pragma unroll
+    for (int c = 0; c < MAXF; ++c)
+      if (c < F) acc[c] = grad_image[((int64_t)py * p.image_width + px) * F + c];
+  }
   T W = inb ? T(0) : T(1);
   bool saturated = false;
   bool done = BLEND ? ((T(1) - W) <= exit_T) : false;
@@ -51,7 +65,8 @@ __global__ void __launch_bounds__(NT) raster_fwd_generic_kernel(const __grid_con
       const int idx = o2p[load_index];
 #pragma unroll
       for (int k = 0; k < 7; ++k) s_pts[t * 7 + k] = pts[(int64_t)idx * 7 + k];
-      for (int c = 0; c < F; ++c) s_feat[t * F + c] = feat[(int64_t)idx * F + c];
+      if (MODE != kQuantileBwd)
+        for (int c = 0; c < F; ++c) s_feat[t * F + c] = feat[(int64_t)idx * F + c];
       s_id[t] = idx;
       s_vis[t] = T(0);
     }
@@ -76,8 +91,12 @@ __global__ void __launch_bounds__(NT) raster_fwd_generic_kernel(const __grid_con
           } else {
             if (W >= sat_w && !saturated) {
 #pragma unroll
-              for (int c = 0; c < MAXF; ++c)
-                if (c < F) acc[c] = s_feat[s * F + c];
+              for (int c = 0; c < MAXF; ++c) {
+                if (c < F) {
+                  if (MODE == kQuantileBwd) red_add(grad_feat + (int64_t)s_id[s] * F + c, acc[c]);
+                  else acc[c] = s_feat[s * F + c];
+                }
+              }
             }
             saturated = W >= sat_w;
           }
@@ -96,7 +115,7 @@ __global__ void __launch_bounds__(NT) raster_fwd_generic_kernel(const __grid_con
       if (load_index < end) red_add(visibility + s_id[t], s_vis[t]);
     }
   }
-  if (inb) {
+  if (MODE != kQuantileBwd && inb) {
     const int64_t pix = (int64_t)py * p.image_width + px;
 #pragma unroll
     for (int c = 0; c < MAXF; ++c)
@@ -230,15 +249,16 @@ __global__ void __launch_bounds__(NT) raster_bwd_generic_kernel(const __grid_con
   }
 }
 
-template <typename T, int MAXF, bool AA, bool BLEND, int NT>
+template <typename T, int MAXF, bool AA, int MODE, int NT>
 static int launch_fwd(const GsRasterParams& p, const RasterArgs& a, cudaStream_t st) {
   const int A = p.tile_size * p.tile_size;
   const size_t smem = (size_t)A * (7 + p.num_features + 1) * sizeof(T) + (size_t)A * sizeof(int);
-  auto kern = raster_fwd_generic_kernel<T, MAXF, AA, BLEND, NT>;
+  auto kern = raster_fwd_generic_kernel<T, MAXF, AA, MODE, NT>;
   if (smem > 48 * 1024) GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = tiles_wide(p) * tiles_high(p);
   kern<<<tiles, A, smem, st>>>(p, (const T*)a.gaussians2d, (const T*)a.features, a.tile_ranges, a.overlap_to_point,
-                               (T*)a.image, (T*)a.image_alpha, (T*)a.visibility);
+                               (T*)a.image, (T*)a.image_alpha, (T*)a.visibility, (const T*)a.grad_image,
+                               (T*)a.grad_features);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }
@@ -260,14 +280,19 @@ static int launch_bwd(const GsRasterParams& p, const RasterArgs& a, cudaStream_t
 
 template <typename T, int MAXF, int NT>
 static int fwd_modes(const GsRasterParams& p, const RasterArgs& a, cudaStream_t st) {
-  if (p.antialias) return p.use_alpha_blending ? launch_fwd<T, MAXF, true, true, NT>(p, a, st)
-                                               : launch_fwd<T, MAXF, true, false, NT>(p, a, st);
-  return p.use_alpha_blending ? launch_fwd<T, MAXF, false, true, NT>(p, a, st)
-                              : launch_fwd<T, MAXF, false, false, NT>(p, a, st);
+  if (p.antialias) return p.use_alpha_blending ? launch_fwd<T, MAXF, true, kBlend, NT>(p, a, st)
+                                               : launch_fwd<T, MAXF, true, kQuantile, NT>(p, a, st);
+  return p.use_alpha_blending ? launch_fwd<T, MAXF, false, kBlend, NT>(p, a, st)
+                              : launch_fwd<T, MAXF, false, kQuantile, NT>(p, a, st);
 }
 
 template <typename T, int MAXF, int NT>
 static int bwd_modes(const GsRasterParams& p, const RasterArgs& a, cudaStream_t st) {
+  if (!p.use_alpha_blending) {  // quantile mode: replay the forward's selection, scatter the image gradient
+    if (!p.features_requires_grad || a.grad_features == nullptr) return GS_OK;
+    return p.antialias ? launch_fwd<T, MAXF, true, kQuantileBwd, NT>(p, a, st)
+                       : launch_fwd<T, MAXF, false, kQuantileBwd, NT>(p, a, st);
+  }
   return p.antialias ? launch_bwd<T, MAXF, true, NT>(p, a, st) : launch_bwd<T, MAXF, false, NT>(p, a, st);
 }
 

@@ -84,10 +84,12 @@ def compute_depth_variance(depth_depthsq, weight, eps=1e-6):
 
 def _median_depth(gaussians2d, depths, overlap_to_point, ranges, camera_params, config):
   """Depth of the first gaussian at which the accumulated alpha reaches one half: the quantile mode of the
-  rasterizer (no blending, saturate_threshold 0.5), forward only."""
+  rasterizer (no blending, saturate_threshold 0.5).  Differentiable w.r.t. the point depths (each pixel's gradient
+  goes to the depth of the gaussian it selected; the selection itself is piecewise constant, so the packed 2D
+  gaussians get no gradient and are detached) — the reference's quantile mode is forward only."""
   quantile = replace(config, use_alpha_blending=False, saturate_threshold=0.5,
                      compute_visibility=False, compute_point_heuristic=False)
-  raster = rasterize_with_tiles(gaussians2d.detach(), depths.detach(), tile_overlap_ranges=ranges,
+  raster = rasterize_with_tiles(gaussians2d.detach(), depths, tile_overlap_ranges=ranges,
                                 overlap_to_point=overlap_to_point, image_size=camera_params.image_size,
                                 config=quantile)
   return raster.image.squeeze(-1)

@@ -123,6 +123,65 @@ def test_quantile_mode_forward(cuda_device):
   assert torch.equal(out.image_weight.cpu(), ref_w)
 
 
+@pytest.mark.parametrize("dtype,tile,antialias", [(torch.float32, 16, False), (torch.float64, 8, False),
+                                                  (torch.float32, 16, True)])
+def test_quantile_mode_backward(cuda_device, dtype, tile, antialias):
+  """SURVEY 8f rank 3: each pixel's image gradient goes to the features of the gaussian the forward selected;
+  the packed gaussians get zeros.  Checked against the selection itself (rendered with index features, by the CUDA
+  path and by the oracle) — the reference has no backward for this mode (tests/test_rasterizer.py:92-94)."""
+  cfg = RasterConfig(use_alpha_blending=False, saturate_threshold=0.5, tile_size=tile, pixel_stride=(1, 1),
+                     antialias=antialias, blur_cov=0.0 if antialias else 0.3)
+  size = (150, 100)
+  g, depth, feat = scene2d(43, 2000, size, channels=2, scale_factor=2.0, alpha_range=(0.3, 0.9), dtype=dtype)
+  o2p, ranges = oracle.map_to_tiles(g.float(), depth, size, cfg)
+  o2p_d, ranges_d = o2p.to(cuda_device), ranges.view(-1, 2).to(cuda_device)
+  V = g.shape[0]
+  torch.manual_seed(7)
+  grad_image = (torch.rand(size[1], size[0], 2, dtype=dtype) - 0.3).to(cuda_device)
+
+  gd, fd = g.to(cuda_device).requires_grad_(True), feat.to(cuda_device).requires_grad_(True)
+  out = rasterize_with_tiles(gd, fd, o2p_d, ranges_d, size, cfg)
+  (out.image * grad_image).sum().backward()
+
+  ids = torch.arange(1, V + 1, dtype=dtype).view(-1, 1)
+  sel = rasterize_with_tiles(g.to(cuda_device), ids.to(cuda_device), o2p_d, ranges_d, size, cfg).image[..., 0].long()
+  hit = sel > 0
+  assert hit.float().mean() > 0.5
+  expect = torch.zeros(V, 2, dtype=dtype, device=cuda_device).index_add_(0, sel[hit] - 1, grad_image[hit])
+  assert torch.allclose(fd.grad, expect, rtol=1e-5, atol=1e-6)
+  assert torch.equal(out.image[hit], feat.to(cuda_device)[sel[hit] - 1])
+  assert gd.grad is not None and not gd.grad.any()
+  # the oracle selects the same gaussians (up to a vanishing number of borderline pixels)
+  sel_ref = oracle.raster_forward(g, ids, o2p, ranges.view(-1, 2), size, cfg)[0][..., 0].long()
+  assert (sel.cpu() != sel_ref).float().mean().item() < 1e-3
+
+
+def test_quantile_mode_gradcheck_and_median_depth_gradient(cuda_device):
+  """float64 gradcheck of quantile mode w.r.t. the features (the case the reference leaves commented out), and the
+  median depth of render_gaussians back-propagating to the gaussian positions."""
+  cfg = RasterConfig(tile_size=8, pixel_stride=(1, 1), use_alpha_blending=False, saturate_threshold=0.5)
+  size = (24, 16)
+  g, depth, feat = scene2d(44, 40, size, channels=2, scale_factor=3.0, alpha_range=(0.4, 0.9), dtype=torch.float64)
+  o2p, ranges = oracle.map_to_tiles(g.float(), depth, size, cfg)
+  gd, o2p, ranges = g.to(cuda_device), o2p.to(cuda_device), ranges.view(-1, 2).to(cuda_device)
+  fd = feat.to(cuda_device).requires_grad_(True)
+  assert torch.autograd.gradcheck(lambda f: rasterize_with_tiles(gd, f, o2p, ranges, size, cfg).image, (fd,),
+                                  eps=1e-6, nondet_tol=1e-9)
+
+  from taichi_gaussian_rasterizer_b200 import render_gaussians
+  from taichi_gaussian_rasterizer_b200.synthetic import random_3d_gaussians, random_camera
+  torch.manual_seed(3)
+  cam = random_camera(image_size=(96, 64))
+  g3 = random_3d_gaussians(800, cam, scale_factor=2.0, alpha_range=(0.5, 0.95)).to(device=cuda_device).requires_grad_(True)
+  r = render_gaussians(g3, cam.to(device=cuda_device), RasterConfig(), render_median_depth=True)
+  assert r.median_depth.shape == (64, 96) and r.median_depth.requires_grad
+  r.median_depth.sum().backward()
+  assert g3.position.grad is not None and g3.position.grad.abs().sum() > 0
+  covered = (r.median_depth > 0).sum().item()
+  # d(sum of median depths)/d(depth_i) = number of pixels that selected gaussian i; total = covered pixels
+  assert covered > 0
+
+
 def test_invalid_pixel_stride_is_rejected(cuda_device):
   cfg = RasterConfig(tile_size=8, pixel_stride=(2, 2))   # 64 / 4 = 16 < 32 threads
   g, depth, feat = scene2d(0, 10, (16, 16))
