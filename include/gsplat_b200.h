@@ -245,6 +245,15 @@ int gs_opt_step(const GsOptParams* p, const int64_t* indexes, const float* weigh
                 const float* grad, float* m, float* v, const float* total_weight, float* param,
                 const float* mask_lr, const float* point_lr, const float* basis, void* stream);
 
+/* ------------------------------------------------------------------ Morton codes
+ * replaces code_points32_kernel / code_points64_kernel (misc/morton_sort.py:93-111): the code of the grid cell
+ * clamp((p - lower) / inc, 0, grid_size - 1) of every point, bits of x / y / z interleaved (x lowest).  points (n,3) f32;
+ * lower, inc: 3 floats each ON THE DEVICE (so that the caller's min / resolution arithmetic needs no host sync);
+ * code_bits 32 (grid_size <= 2^10, codes uint32) or 64 (grid_size <= 2^21, codes uint64).  Sorting the codes is
+ * gs_radix_sort_pairs on 3 * log2(grid_size) bits. */
+int gs_morton_codes(int64_t n, const float* points, const float* lower, const float* inc, int64_t grid_size,
+                    int32_t code_bits, void* codes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

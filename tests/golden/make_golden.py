@@ -259,12 +259,40 @@ def make_optim(out):
 
 
 MAKERS = {"tile_map": make_tile_map, "projection": make_projection, "sh": make_sh, "raster": make_raster,
-          "optim": make_optim}
+          "optim": make_optim, "morton": lambda out: make_morton(out)}
+
+
+# ----------------------------------------------------------------------------------------------- Morton codes
+MORTON_CASES = [(0, 300, 0.001, 2.0), (1, 257, 0.01, 50.0), (2, 64, 1e-5, 0.5), (3, 500, 0.05, 1e5)]  # seed, n, resolution, extent
+
+
+def make_morton(out):
+  """code_points64_kernel / code_points32_kernel of misc/morton_sort.py run by the emulator; some points sit far outside
+  the grid (clamped to the last cell) and several are duplicated (equal codes: the argsort must be stable)."""
+  import taichi_splatting.misc.morton_sort as ms
+  for i, (seed, n, resolution, extent) in enumerate(MORTON_CASES):
+    torch.manual_seed(seed)
+    pts = (torch.rand(n, 3) - 0.3) * extent
+    pts[n // 2:n // 2 + 10] = pts[:10]                       # duplicates
+    pts = pts.to(torch.float32).contiguous()
+    grid = ms.grid_at_resolution(pts, resolution, size=2 ** 20)
+    codes64 = torch.empty(n, dtype=torch.uint64)
+    ms.code_points64_kernel(grid, pts, codes64)
+    grid32 = ms.grid_at_resolution(pts, resolution * 1024, size=2 ** 10)
+    codes32 = torch.empty(n, dtype=torch.uint32)
+    ms.code_points32_kernel(grid32, pts, codes32)
+    c64 = codes64.numpy().copy()
+    print(f"morton case {i}: n={n} resolution={resolution} distinct codes {len(np.unique(c64))} "
+          f"clamped {(int((c64 == c64.max()).sum()))}")
+    out.update({f"c{i}_points": np_(pts), f"c{i}_resolution": np.array(resolution),
+                f"c{i}_codes64": c64, f"c{i}_codes32": codes32.numpy().copy(),
+                f"c{i}_argsort": np.argsort(c64, kind="stable").astype(np.int32)})   # = cuda_lib.radix_argsort(codes)
+  out["num_cases"] = np.array(len(MORTON_CASES))
 
 
 def main():
   ap = argparse.ArgumentParser()
-  ap.add_argument("--only", default="tile_map,projection,sh,raster,optim")
+  ap.add_argument("--only", default="tile_map,projection,sh,raster,optim,morton")
   ap.add_argument("--quick", action="store_true", help="raster: only the two cheapest cases")
   args = ap.parse_args()
   for name in args.only.split(","):

@@ -276,6 +276,8 @@ class VectorType:
     return self.dtype.np_type if self.dtype.kind == "f" else np.int64
 
   def __call__(self, *args):
+    if len(args) == 1 and hasattr(args[0], "detach") and hasattr(args[0], "tolist"):   # a torch tensor
+      args = (args[0].detach().cpu().numpy(),)
     if len(args) == 1 and isinstance(args[0], (list, tuple, Vec, np.ndarray)):
       args = list(args[0])
     vals = []
@@ -846,6 +848,7 @@ def build_taichi_module():
     if n > 1:
       setattr(tmath, f"vec{n}", VectorType(n, f32))
       setattr(tmath, f"ivec{n}", VectorType(n, i32))
+      setattr(tmath, f"uvec{n}", VectorType(n, u32))
       setattr(tmath, f"mat{n}", MatrixType(n, n, f32))
   ti.math = tmath
 
