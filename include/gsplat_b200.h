@@ -48,6 +48,8 @@ const char* gs_last_error_string(void);
 typedef struct GsProjectParams {
   int32_t dtype;
   int32_t image_width, image_height;
+  int32_t accumulate_grads; /* gs_project_bwd: ADD the per gaussian gradients of the visible rows into the caller's
+                               buffers (gradient bucket of a multi-view batch) instead of writing them dense */
   int64_t num_points;      /* N */
   double near_plane, far_plane;
   double blur_cov, clamp_margin, alpha_threshold;
@@ -66,7 +68,9 @@ int gs_project_fwd(const GsProjectParams* p, const void* position, const void* l
 
 /* grad_points (V,7) grad_depth (V,1) -> dense grads, fully written (zero for culled points):
  * grad_position (N,3) grad_log_scaling (N,3) grad_rotation (N,4) grad_alpha_logit (N,1)
- * grad_T_camera_world (4,4; last row zero) grad_projection (4).  Any grad pointer may be NULL. */
+ * grad_T_camera_world (4,4; last row zero) grad_projection (4).  Any grad pointer may be NULL.
+ * With p->accumulate_grads the four per gaussian buffers are NOT cleared: the rows of the visible gaussians are
+ * incremented, all other rows are left as they are (`indexes` must be unique, as the visible set is). */
 int gs_project_bwd(const GsProjectParams* p, int64_t num_visible, const void* position,
                    const void* log_scaling, const void* rotation, const void* alpha_logit,
                    const void* T_camera_world, const void* projection, const int64_t* indexes,

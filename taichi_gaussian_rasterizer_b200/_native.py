@@ -29,7 +29,7 @@ EXPORTS = [
 
 class GsProjectParams(ctypes.Structure):
   _fields_ = [("dtype", ctypes.c_int32), ("image_width", ctypes.c_int32), ("image_height", ctypes.c_int32),
-              ("num_points", ctypes.c_int64), ("near_plane", ctypes.c_double), ("far_plane", ctypes.c_double),
+              ("accumulate_grads", ctypes.c_int32), ("num_points", ctypes.c_int64), ("near_plane", ctypes.c_double), ("far_plane", ctypes.c_double),
               ("blur_cov", ctypes.c_double), ("clamp_margin", ctypes.c_double),
               ("alpha_threshold", ctypes.c_double)]
 

@@ -310,7 +310,8 @@ sh_bwd_dense_kernel(const __grid_constant__ GsSHParams p, const float* __restric
 // ------------------------------------------------------------------------------------------------ projection bwd
 constexpr int kPBwdBlock = 128;
 
-template <typename T>
+// ACC: add into the caller's gradient buffers (visible rows only) instead of overwriting them.
+template <typename T, bool ACC>
 __global__ void __launch_bounds__(kPBwdBlock)
 project_bwd_kernel(const __grid_constant__ GsProjectParams p, int64_t num_visible, const T* __restrict__ position,
                    const T* __restrict__ log_scaling, const T* __restrict__ rotation,
@@ -462,13 +463,20 @@ project_bwd_kernel(const __grid_constant__ GsProjectParams p, int64_t num_visibl
     }
     cam_grad[12] = dfx; cam_grad[13] = dfy; cam_grad[14] = dcx; cam_grad[15] = dcy;
 
-    if (g_position) { g_position[3 * idx] = d_pos[0]; g_position[3 * idx + 1] = d_pos[1]; g_position[3 * idx + 2] = d_pos[2]; }
-    if (g_log_scaling) { g_log_scaling[3 * idx] = d_ls[0]; g_log_scaling[3 * idx + 1] = d_ls[1]; g_log_scaling[3 * idx + 2] = d_ls[2]; }
+    auto put = [](T* dst, T v) { *dst = ACC ? *dst + v : v; };  // rows are unique: plain read-modify-write
+    if (g_position) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) put(g_position + 3 * idx + k, d_pos[k]);
+    }
+    if (g_log_scaling) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) put(g_log_scaling + 3 * idx + k, d_ls[k]);
+    }
     if (g_rotation) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) g_rotation[4 * idx + k] = d_rot[k];
+      for (int k = 0; k < 4; ++k) put(g_rotation + 4 * idx + k, d_rot[k]);
     }
-    if (g_alpha_logit) g_alpha_logit[idx] = d_logit;
+    if (g_alpha_logit) put(g_alpha_logit + idx, d_logit);
   }
 
   if (g_Tcw || g_proj) {  // camera gradients are summed over gaussians (expand backward, projection.py:212-213)
@@ -609,28 +617,28 @@ int gs_project_bwd(const GsProjectParams* p, int64_t num_visible, const void* po
   cudaStream_t st = (cudaStream_t)stream;
   const size_t es = p->dtype == GS_F32 ? 4 : 8;
   const size_t n = (size_t)p->num_points;
-  if (grad_position) GS_CUDA(cudaMemsetAsync(grad_position, 0, n * 3 * es, st));
-  if (grad_log_scaling) GS_CUDA(cudaMemsetAsync(grad_log_scaling, 0, n * 3 * es, st));
-  if (grad_rotation) GS_CUDA(cudaMemsetAsync(grad_rotation, 0, n * 4 * es, st));
-  if (grad_alpha_logit) GS_CUDA(cudaMemsetAsync(grad_alpha_logit, 0, n * es, st));
+  const bool acc = p->accumulate_grads != 0;
+  if (!acc) {
+    if (grad_position) GS_CUDA(cudaMemsetAsync(grad_position, 0, n * 3 * es, st));
+    if (grad_log_scaling) GS_CUDA(cudaMemsetAsync(grad_log_scaling, 0, n * 3 * es, st));
+    if (grad_rotation) GS_CUDA(cudaMemsetAsync(grad_rotation, 0, n * 4 * es, st));
+    if (grad_alpha_logit) GS_CUDA(cudaMemsetAsync(grad_alpha_logit, 0, n * es, st));
+  }
   if (grad_T_camera_world) GS_CUDA(cudaMemsetAsync(grad_T_camera_world, 0, 16 * es, st));
   if (grad_projection) GS_CUDA(cudaMemsetAsync(grad_projection, 0, 4 * es, st));
   if (num_visible == 0) return GS_OK;
   GS_CHECK_ARG(position && log_scaling && rotation && alpha_logit && T_camera_world && projection && indexes &&
                    grad_points, "gs_project_bwd: null tensor");
   const int64_t blocks = ceil_div(num_visible, kPBwdBlock);
-  if (p->dtype == GS_F32)
-    project_bwd_kernel<float><<<(unsigned)blocks, kPBwdBlock, 0, st>>>(
-        *p, num_visible, (const float*)position, (const float*)log_scaling, (const float*)rotation,
-        (const float*)alpha_logit, (const float*)T_camera_world, (const float*)projection, indexes,
-        (const float*)grad_points, (const float*)grad_depth, (float*)grad_position, (float*)grad_log_scaling,
-        (float*)grad_rotation, (float*)grad_alpha_logit, (float*)grad_T_camera_world, (float*)grad_projection);
-  else
-    project_bwd_kernel<double><<<(unsigned)blocks, kPBwdBlock, 0, st>>>(
-        *p, num_visible, (const double*)position, (const double*)log_scaling, (const double*)rotation,
-        (const double*)alpha_logit, (const double*)T_camera_world, (const double*)projection, indexes,
-        (const double*)grad_points, (const double*)grad_depth, (double*)grad_position, (double*)grad_log_scaling,
-        (double*)grad_rotation, (double*)grad_alpha_logit, (double*)grad_T_camera_world, (double*)grad_projection);
+#define GS_PBWD_LAUNCH(TT, ACCV)                                                                                    \
+  project_bwd_kernel<TT, ACCV><<<(unsigned)blocks, kPBwdBlock, 0, st>>>(                                            \
+      *p, num_visible, (const TT*)position, (const TT*)log_scaling, (const TT*)rotation, (const TT*)alpha_logit,    \
+      (const TT*)T_camera_world, (const TT*)projection, indexes, (const TT*)grad_points, (const TT*)grad_depth,     \
+      (TT*)grad_position, (TT*)grad_log_scaling, (TT*)grad_rotation, (TT*)grad_alpha_logit,                         \
+      (TT*)grad_T_camera_world, (TT*)grad_projection)
+  if (p->dtype == GS_F32) { if (acc) GS_PBWD_LAUNCH(float, true); else GS_PBWD_LAUNCH(float, false); }
+  else { if (acc) GS_PBWD_LAUNCH(double, true); else GS_PBWD_LAUNCH(double, false); }
+#undef GS_PBWD_LAUNCH
   GS_LAUNCH_CHECK();
   return GS_OK;
 }

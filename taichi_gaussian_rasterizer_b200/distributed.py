@@ -40,19 +40,20 @@ class GradientBucket:
 
   @contextmanager
   def fused_accumulation(self):
-    """Inside this context the spherical-harmonics backward adds its dense (N, 3, D) gradient straight into the
-    bucket (in the kernel) instead of materialising it for autograd to add: with V views per batch that removes
-    V - 1 read-modify-write passes over the largest gradient (576 MB at 3 M gaussians, SH degree 3).  Results are
-    the same sums; parameters the kernels cannot serve this way keep the normal autograd accumulation."""
-    from . import spherical_harmonics as sh
-    served = [p for p in self.params if p.is_cuda and p.dim() == 3 and p.grad is not None]
+    """Inside this context the spherical-harmonics backward and the projection backward add their gradients straight
+    into the bucket (in the kernel) instead of materialising dense tensors for autograd to add: per view that removes
+    a read-modify-write pass over every gradient (576 MB of SH + 132 MB of geometry at 3 M gaussians) and the zero
+    fill of the culled rows.  Results are the same sums; parameters the kernels cannot serve this way (other
+    dtypes, features used without SH) keep the normal autograd accumulation."""
+    from . import grad_sinks
+    served = [p for p in self.params if p.is_cuda and p.grad is not None]
     for p in served:
-      sh.register_grad_sink(p, p.grad)
+      grad_sinks.register_grad_sink(p, p.grad)
     try:
       yield self
     finally:
       for p in served:
-        sh.unregister_grad_sink(p)
+        grad_sinks.unregister_grad_sink(p)
 
   @property
   def nbytes(self) -> int:

@@ -16,6 +16,7 @@ from beartype import beartype
 from beartype.typing import Tuple
 
 from .. import _native as N
+from ..grad_sinks import grad_sink
 from ..data_types import Gaussians3D, RasterConfig
 from .params import CameraParams
 
@@ -39,7 +40,7 @@ class _ProjectFunction(torch.autograd.Function):
               image_size, depth_range, blur_cov, clamp_margin, alpha_threshold, after_launch=None):
     dtype, device = position.dtype, position.device
     n = position.shape[0]
-    params = N.GsProjectParams(N.dtype_code(dtype), int(image_size[0]), int(image_size[1]), n,
+    params = N.GsProjectParams(N.dtype_code(dtype), int(image_size[0]), int(image_size[1]), 0, n,
                                float(depth_range[0]), float(depth_range[1]), float(blur_cov),
                                float(clamp_margin), float(alpha_threshold))
     points = torch.empty((n, 7), dtype=dtype, device=device)
@@ -77,12 +78,23 @@ class _ProjectFunction(torch.autograd.Function):
     position, log_scaling, rotation, alpha_logit, T_camera_world, projection, indexes = ctx.saved_tensors
     need = ctx.needs_input_grad
     v = indexes.shape[0]
-    grads = [torch.empty_like(t) if need[i] else None
-             for i, t in enumerate((position, log_scaling, rotation, alpha_logit, T_camera_world, projection))]
-    N.call("gs_project_bwd", ctypes.byref(ctx.params), ctypes.c_int64(v), N.ptr(position), N.ptr(log_scaling), N.ptr(rotation),
+    inputs = (position, log_scaling, rotation, alpha_logit, T_camera_world, projection)
+    # fused accumulation (grad_sinks.py): when every per gaussian input that needs a gradient has a sink, the kernel
+    # adds the visible rows into the sinks and autograd gets no gradient for them
+    sinks = [grad_sink(t) if need[i] else None for i, t in enumerate(inputs[:4])]
+    fused = any(need[:4]) and all(s is not None for s, nd in zip(sinks, need[:4]) if nd)
+    if fused:
+      targets = sinks + [torch.empty_like(t) if need[4 + i] else None for i, t in enumerate(inputs[4:])]
+    else:
+      targets = [torch.empty_like(t) if need[i] else None for i, t in enumerate(inputs)]
+    params = ctx.params
+    params.accumulate_grads = int(fused)
+    N.call("gs_project_bwd", ctypes.byref(params), ctypes.c_int64(v), N.ptr(position), N.ptr(log_scaling), N.ptr(rotation),
       N.ptr(alpha_logit), N.ptr(T_camera_world), N.ptr(projection), N.ptr(indexes),
-      N.ptr(dpoints.contiguous()), N.ptr(ddepth.contiguous()), *[N.ptr(g) for g in grads],
+      N.ptr(dpoints.contiguous()), N.ptr(ddepth.contiguous()), *[N.ptr(g) for g in targets],
       N.stream_ptr(position.device))
+    params.accumulate_grads = 0
+    grads = ([None] * 4 + targets[4:]) if fused else targets
     return (*grads, None, None, None, None, None, None)
 
 

@@ -12,20 +12,7 @@ import torch
 from beartype import beartype
 
 from . import _native as N
-
-
-# Gradient sinks: parameter storage (data_ptr) -> buffer that the backward accumulates into IN the kernel instead
-# of returning a fresh dense gradient for autograd to add (distributed.GradientBucket.fused_accumulation()).
-_grad_sinks = {}
-
-
-def register_grad_sink(param: torch.Tensor, buffer: torch.Tensor):
-  assert buffer.shape == param.shape and buffer.dtype == param.dtype and buffer.is_contiguous()
-  _grad_sinks[param.data_ptr()] = buffer
-
-
-def unregister_grad_sink(param: torch.Tensor):
-  _grad_sinks.pop(param.data_ptr(), None)
+from .grad_sinks import grad_sink, register_grad_sink, unregister_grad_sink  # noqa: F401  (re-exported)
 
 
 def check_sh_degree(sh_features):
@@ -61,7 +48,7 @@ class _SHFunction(torch.autograd.Function):
   def backward(ctx, doutput):
     params, points, indexes, camera_pos = ctx.saved_tensors
     need = ctx.needs_input_grad
-    sink = _grad_sinks.get(params.data_ptr()) if need[0] else None
+    sink = grad_sink(params) if need[0] else None
     if sink is not None and ctx.sorted_unique and params.dtype == torch.float32 and params.shape[1] == 3 \
         and params.shape[2] in (4, 16):
       # fused accumulation: the kernel adds into the sink, autograd gets no gradient for `params`
