@@ -312,7 +312,7 @@ constexpr int kPBwdBlock = 128;
 
 // ACC: add into the caller's gradient buffers (visible rows only) instead of overwriting them.
 template <typename T, bool ACC>
-__global__ void __launch_bounds__(kPBwdBlock)
+__global__ void __launch_bounds__(kPBwdBlock, sizeof(T) == 4 ? 8 : 1)
 project_bwd_kernel(const __grid_constant__ GsProjectParams p, int64_t num_visible, const T* __restrict__ position,
                    const T* __restrict__ log_scaling, const T* __restrict__ rotation,
                    const T* __restrict__ alpha_logit, const T* __restrict__ Tcw, const T* __restrict__ proj,
