@@ -91,7 +91,10 @@ typedef struct GsSHParams {
   int32_t accumulate_params; /* gs_sh_bwd: grad_params += instead of = (rows outside `indexes` untouched, no zero
                                 fill); needs indexes_sorted_unique, f32, K = 3, D in {4, 16}; fuses the optimizer-side
                                 gradient accumulation of a multi-view batch into the kernel.  0 = overwrite. */
-  int32_t reserved_;
+  int32_t params_is_forward_output; /* gs_sh_bwd: the `params` argument holds the forward OUTPUT (V,K) instead of the
+                                       coefficients — enough for grad_params (the coefficients only enter through the
+                                       clamp mask, and v in (0,1) <=> clamp(v) in (0,1)) and 4KD bytes per gaussian
+                                       less traffic; dense path only, grad_positions / grad_camera_pos must be NULL */
 } GsSHParams;
 
 /* params (M,K,D) positions (M,3) indexes (V) int64 camera_pos (3) -> out (V,K) */

@@ -37,7 +37,7 @@ class GsProjectParams(ctypes.Structure):
 class GsSHParams(ctypes.Structure):
   _fields_ = [("dtype", ctypes.c_int32), ("num_channels", ctypes.c_int32), ("num_coeffs", ctypes.c_int32),
               ("indexes_sorted_unique", ctypes.c_int32), ("num_points", ctypes.c_int64),
-              ("num_indexes", ctypes.c_int64), ("accumulate_params", ctypes.c_int32), ("reserved_", ctypes.c_int32)]
+              ("num_indexes", ctypes.c_int64), ("accumulate_params", ctypes.c_int32), ("params_is_forward_output", ctypes.c_int32)]
 
 
 class GsTileParams(ctypes.Structure):

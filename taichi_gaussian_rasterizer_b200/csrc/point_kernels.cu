@@ -181,7 +181,10 @@ sh_bwd_kernel(const __grid_constant__ GsSHParams p, const T* __restrict__ params
 // grad_positions need no memset and no atomics: 2 x 4 K D bytes per gaussian of traffic in total.
 constexpr int kSHDenseBlock = 128;
 
-template <int K, int D, bool FILL, bool ACC>
+// FROM_OUT: `params` holds the forward OUTPUT (V, K) instead of the coefficients.  The coefficient gradient
+// g_k b_j needs the coefficients only for the clamp mask, and v in (0, 1) <=> clamp(v) in (0, 1): when no position /
+// camera gradient is asked for, the 4 K D byte row gather per gaussian (a third of the kernel's traffic) is skipped.
+template <int K, int D, bool FILL, bool ACC, bool FROM_OUT = false>
 __global__ void __launch_bounds__(kSHDenseBlock, 6)
 sh_bwd_dense_kernel(const __grid_constant__ GsSHParams p, const float* __restrict__ params,
                     const float* __restrict__ positions, const int64_t* __restrict__ indexes,
@@ -201,18 +204,20 @@ sh_bwd_dense_kernel(const __grid_constant__ GsSHParams p, const float* __restric
   if (t == 0) s_idx[0] = i0 > 0 ? indexes[i0 - 1] : -1;
   __syncthreads();
 
+  if (!FROM_OUT) {
 #pragma unroll
-  for (int m = 0; m < R4; ++m) {  // R4 independent 16 B cp.async gathers in flight per thread, no staging registers
-    const int q = t + m * kSHDenseBlock, r = q / R4, part = q - r * R4;
-    if (q < nrows * R4) {
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_row[r * S4 + part]);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
-                   "l"(reinterpret_cast<const float4*>(params + s_idx[r + 1] * RL) + part) : "memory");
+    for (int m = 0; m < R4; ++m) {  // R4 independent 16 B cp.async gathers in flight per thread, no staging registers
+      const int q = t + m * kSHDenseBlock, r = q / R4, part = q - r * R4;
+      if (q < nrows * R4) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_row[r * S4 + part]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
+                     "l"(reinterpret_cast<const float4*>(params + s_idx[r + 1] * RL) + part) : "memory");
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
 
   float gpx = 0.f, gpy = 0.f, gpz = 0.f;
   if (t < nrows) {
@@ -229,24 +234,31 @@ sh_bwd_dense_kernel(const __grid_constant__ GsSHParams p, const float* __restric
     float4* row = s_row + t * S4;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
+      float v;
       float c[D];
+      if (FROM_OUT) {
+        v = params[i * K + k];  // the clamped forward value: inside (0, 1) exactly when the unclamped one is
+      } else {
 #pragma unroll
-      for (int j4 = 0; j4 < D / 4; ++j4) {
-        const float4 v = row[k * (D / 4) + j4];
-        c[4 * j4] = v.x; c[4 * j4 + 1] = v.y; c[4 * j4 + 2] = v.z; c[4 * j4 + 3] = v.w;
+        for (int j4 = 0; j4 < D / 4; ++j4) {
+          const float4 q4 = row[k * (D / 4) + j4];
+          c[4 * j4] = q4.x; c[4 * j4 + 1] = q4.y; c[4 * j4 + 2] = q4.z; c[4 * j4 + 3] = q4.w;
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc += b[j] * c[j];
+        v = acc + 0.5f;
       }
-      float acc = 0.f;
-#pragma unroll
-      for (int j = 0; j < D; ++j) acc += b[j] * c[j];
-      const float v = acc + 0.5f;
       const float g = (v > 0.f && v < 1.f) ? grad_out[i * K + k] : 0.f;  // clamp passes gradient strictly inside
+      if (!FROM_OUT) {
 #pragma unroll
-      for (int j = 0; j < D; ++j) gb[j] += g * c[j];
+        for (int j = 0; j < D; ++j) gb[j] += g * c[j];
+      }
 #pragma unroll
       for (int j4 = 0; j4 < D / 4; ++j4)
         row[k * (D / 4) + j4] = make_float4(g * b[4 * j4], g * b[4 * j4 + 1], g * b[4 * j4 + 2], g * b[4 * j4 + 3]);
     }
-    if (grad_positions || grad_cam) {
+    if (!FROM_OUT && (grad_positions || grad_cam)) {
       float gx[D], gy[D], gz[D];
       sh_basis_grad<float, D>(x, y, z, gx, gy, gz);
       float ddx = 0.f, ddy = 0.f, ddz = 0.f;
@@ -574,6 +586,11 @@ int gs_sh_bwd(const GsSHParams* p, const void* params, const void* positions, co
   const bool dense = p->indexes_sorted_unique && p->dtype == GS_F32 && grad_params != nullptr && p->num_indexes > 0 &&
                      p->num_channels == 3 && (p->num_coeffs == 16 || p->num_coeffs == 4);
   const bool acc = p->accumulate_params != 0;
+  const bool from_out = p->params_is_forward_output != 0;
+  if (from_out && (!dense || grad_positions || grad_camera_pos)) {
+    set_error("gs_sh_bwd: params_is_forward_output needs the dense path and no position / camera gradient");
+    return GS_ERR_UNSUPPORTED;
+  }
   if (acc && !dense) {
     set_error("gs_sh_bwd: accumulate_params needs the dense path (indexes_sorted_unique, f32, K = 3, D = 4 or 16)");
     return GS_ERR_UNSUPPORTED;
@@ -587,16 +604,19 @@ int gs_sh_bwd(const GsSHParams* p, const void* params, const void* positions, co
   GS_CHECK_ARG(params && positions && indexes && camera_pos && grad_out, "gs_sh_bwd: null tensor");
   if (dense) {
     const unsigned blocks = (unsigned)ceil_div(p->num_indexes, kSHDenseBlock);
-#define GS_SH_DENSE(DD, FILLV, ACCV)                                                                             \
-    sh_bwd_dense_kernel<3, DD, FILLV, ACCV><<<blocks, kSHDenseBlock, 0, st>>>(                                   \
+#define GS_SH_DENSE_(DD, FILLV, ACCV, FROMV)                                                                      \
+    sh_bwd_dense_kernel<3, DD, FILLV, ACCV, FROMV><<<blocks, kSHDenseBlock, 0, st>>>(                            \
         *p, (const float*)params, (const float*)positions, indexes, (const float*)camera_pos,                   \
         (const float*)grad_out, (float*)grad_params, (float*)grad_positions, (float*)grad_camera_pos)
+#define GS_SH_DENSE(DD, FILLV, ACCV) \
+    do { if (from_out) GS_SH_DENSE_(DD, FILLV, ACCV, true); else GS_SH_DENSE_(DD, FILLV, ACCV, false); } while (0)
     if (p->num_coeffs == 16) {
       if (acc) GS_SH_DENSE(16, false, true); else if (fill) GS_SH_DENSE(16, true, false); else GS_SH_DENSE(16, false, false);
     } else {
       if (acc) GS_SH_DENSE(4, false, true); else if (fill) GS_SH_DENSE(4, true, false); else GS_SH_DENSE(4, false, false);
     }
 #undef GS_SH_DENSE
+#undef GS_SH_DENSE_
     GS_LAUNCH_CHECK();
     return GS_OK;
   }

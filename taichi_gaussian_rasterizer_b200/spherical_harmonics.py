@@ -41,27 +41,35 @@ class _SHFunction(torch.autograd.Function):
     ctx.p = p
     ctx.sorted_unique = bool(sorted_unique)
     ctx.mark_non_differentiable(indexes)
-    ctx.save_for_backward(params, points, indexes, camera_pos)
+    ctx.save_for_backward(params, points, indexes, camera_pos, out)
     return out
 
   @staticmethod
   def backward(ctx, doutput):
-    params, points, indexes, camera_pos = ctx.saved_tensors
+    params, points, indexes, camera_pos, out = ctx.saved_tensors
     need = ctx.needs_input_grad
     sink = grad_sink(params) if need[0] else None
-    if sink is not None and ctx.sorted_unique and params.dtype == torch.float32 and params.shape[1] == 3 \
-        and params.shape[2] in (4, 16):
+    dense = ctx.sorted_unique and params.dtype == torch.float32 and params.shape[1] == 3 and params.shape[2] in (4, 16) \
+      and indexes.shape[0] > 0
+    # only the coefficient gradient is wanted (render_gaussians detaches the positions): the kernel then takes the clamp
+    # mask from the forward output and never reads the coefficient rows
+    from_out = int(dense and need[0] and not need[1] and not need[3])
+    coeffs = out if from_out else params
+    if sink is not None and dense:
       # fused accumulation: the kernel adds into the sink, autograd gets no gradient for `params`
-      p = N.GsSHParams(ctx.p.dtype, ctx.p.num_channels, ctx.p.num_coeffs, 1, ctx.p.num_points, ctx.p.num_indexes, 1, 0)
+      p = N.GsSHParams(ctx.p.dtype, ctx.p.num_channels, ctx.p.num_coeffs, 1, ctx.p.num_points, ctx.p.num_indexes, 1,
+                       from_out)
       g_points = torch.empty_like(points) if need[1] else None
       g_cam = torch.empty_like(camera_pos) if need[3] else None
-      N.call("gs_sh_bwd", ctypes.byref(p), N.ptr(params), N.ptr(points), N.ptr(indexes), N.ptr(camera_pos),
+      N.call("gs_sh_bwd", ctypes.byref(p), N.ptr(coeffs), N.ptr(points), N.ptr(indexes), N.ptr(camera_pos),
              N.ptr(doutput.contiguous()), N.ptr(sink), N.ptr(g_points), N.ptr(g_cam), N.stream_ptr(params.device))
       return None, g_points, None, g_cam, None, None
     g_params = torch.empty_like(params) if need[0] else None
     g_points = torch.empty_like(points) if need[1] else None
     g_cam = torch.empty_like(camera_pos) if need[3] else None
-    N.call("gs_sh_bwd", ctypes.byref(ctx.p), N.ptr(params), N.ptr(points), N.ptr(indexes),
+    p = N.GsSHParams(ctx.p.dtype, ctx.p.num_channels, ctx.p.num_coeffs, ctx.p.indexes_sorted_unique, ctx.p.num_points,
+                     ctx.p.num_indexes, 0, from_out)
+    N.call("gs_sh_bwd", ctypes.byref(p), N.ptr(coeffs), N.ptr(points), N.ptr(indexes),
                               N.ptr(camera_pos), N.ptr(doutput.contiguous()), N.ptr(g_params), N.ptr(g_points),
                               N.ptr(g_cam), N.stream_ptr(params.device))
     return g_params, g_points, None, g_cam, None, None

@@ -181,3 +181,33 @@ def test_sh_dense_backward_matches_generic(cuda_device, n, keep, deg):
   mask = torch.ones(n, dtype=torch.bool)
   mask[idx] = False
   assert (g_d[0].cpu()[mask] == 0).all() and (g_d[1].cpu()[mask] == 0).all()
+
+
+@pytest.mark.parametrize("n,keep,deg,scale", [(1000, 0.97, 3, 3.0), (1000, 0.3, 3, 0.6), (517, 0.9, 1, 3.0)])
+def test_sh_backward_from_forward_output(cuda_device, n, keep, deg, scale):
+  """Only the coefficients need a gradient (render_gaussians detaches the positions): the dense kernel takes the clamp
+  mask from the forward output instead of re-reading the coefficient rows.  Same gradient, bit for bit, as the path
+  that reads the coefficients; ``scale`` = 3 makes about half of the colours clamp."""
+  torch.manual_seed(n + deg)
+  params = (torch.rand(n, 3, (deg + 1) ** 2) - 0.5) * scale
+  points, cam = torch.randn(n, 3).to(cuda_device), torch.randn(3).to(cuda_device)
+  idx = torch.nonzero(torch.rand(n) < keep).squeeze(1).to(cuda_device)
+  gout = torch.randn(idx.shape[0], 3).to(cuda_device)
+
+  def grad_params(points_need_grad):
+    p = params.clone().to(cuda_device).requires_grad_(True)
+    pts = points.clone().requires_grad_(points_need_grad)
+    junk = torch.full_like(p, float("nan"))
+    del junk
+    out = evaluate_sh_at(p, pts, idx, cam, indexes_sorted_unique=True)
+    (out * gout).sum().backward()
+    return out, p.grad
+
+  out_a, g_from_out = grad_params(False)
+  out_b, g_from_coeffs = grad_params(True)
+  clamped = ((out_a == 0) | (out_a == 1)).float().mean().item()
+  assert (clamped > 0.2) == (scale > 1)
+  assert torch.equal(out_a, out_b) and torch.equal(g_from_out, g_from_coeffs)
+  pr = params.clone().requires_grad_(True)
+  (torch_ref.evaluate_sh_at(pr, points.cpu(), idx.cpu(), cam.cpu()) * gout.cpu()).sum().backward()
+  assert torch.allclose(g_from_out.cpu(), pr.grad, atol=1e-5)
