@@ -37,10 +37,15 @@ def main():
   targets = [torch.rand(h, w, 3, device=dev) for _ in cams]
   cfg = RasterConfig(tile_size=W["tile_size"])
 
+  # as bench.py: gradients of all views accumulate in one flat bucket, inside the kernels
+  from taichi_gaussian_rasterizer_b200.distributed import GradientBucket
+  bucket = GradientBucket([g.position, g.log_scaling, g.rotation, g.alpha_logit, g.feature])
+
   def step():
-    for cam, tgt in zip(cams, targets):
-      r = render_gaussians(g, cam, cfg, use_sh=True)
-      (r.image - tgt).abs().mean().backward()
+    with bucket.fused_accumulation():
+      for cam, tgt in zip(cams, targets):
+        r = render_gaussians(g, cam, cfg, use_sh=True)
+        (r.image - tgt).abs().mean().backward()
 
   for _ in range(3):
     step()
