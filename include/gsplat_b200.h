@@ -162,10 +162,13 @@ int gs_find_ranges(const GsTileParams* p, int64_t num_overlaps, const void* sort
  * sequence as torch's eager CUDA kernels; near_plane <= 0: `depth` already is the sort depth. */
 int gs_depth_keys(const GsTileParams* p, const float* depth, double near_plane, double far_plane,
                   uint32_t* keys, int32_t* values, void* stream);
+/* tile_masks (V) uint64, optional (NULL = none) in both calls: the count pass records per slot which tiles of a span of
+ * at most 32 tiles passed the test, the emit pass then expands those bits instead of repeating the OBB query and the
+ * tile tests (spans above 32 tiles are flagged and recomputed).  Same outputs either way. */
 int gs_tile_count_perm(const GsTileParams* p, const float* gaussians, const int32_t* perm, int32_t* counts,
-                       void* stream);
+                       uint64_t* tile_masks, void* stream);
 int gs_tile_emit_tiles(const GsTileParams* p, const float* gaussians, const int32_t* perm, const int32_t* cum,
-                       uint32_t* tile_ids, int32_t* values, void* stream);
+                       const uint64_t* tile_masks, uint32_t* tile_ids, int32_t* values, void* stream);
 int gs_find_ranges_tiles(const GsTileParams* p, int64_t num_overlaps, const uint32_t* sorted_tile_ids,
                          int32_t* tile_ranges, void* stream);
 

@@ -149,11 +149,17 @@ __device__ __forceinline__ TileQuery shfl_query(const TileQuery& q, int src) {
 // MODE 2: write bare tile ids (u32) / values at cum[i] (depth-first pipeline: the gaussians are visited in depth
 // order through `perm`, so a stable sort on the tile id alone yields the (tile, depth, index) order).
 // perm (optional): slot i works on gaussian perm[i]; values always hold the gaussian index.
+// masks (optional, one uint2 per slot): the count pass records which tiles of a span of at most 32 passed the test
+// (.x: bit tu * span_y + tv; .y: min_x | min_y << 12 | span_y << 24, bit 31 = span too large, recompute), and the emit
+// pass expands the bits instead of evaluating the OBB query and up to 32 tile tests a second time.
+constexpr unsigned kMaskRecompute = 1u << 31;
+
 template <int MODE, typename KeyT>
 __global__ void __launch_bounds__(kTileBlock)
 tile_query_kernel(const __grid_constant__ GsTileParams p, int img_w, int img_h, const float* __restrict__ g,
                   const float* __restrict__ depth, const int32_t* __restrict__ perm, const int32_t* __restrict__ cum,
-                  int32_t* __restrict__ counts, KeyT* __restrict__ keys, int32_t* __restrict__ values) {
+                  int32_t* __restrict__ counts, KeyT* __restrict__ keys, int32_t* __restrict__ values,
+                  uint2* __restrict__ masks) {
   constexpr bool EMIT = MODE != 0;
   const int64_t slot = (int64_t)blockIdx.x * kTileBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -166,17 +172,38 @@ tile_query_kernel(const __grid_constant__ GsTileParams p, int img_w, int img_h, 
   float d = 0.f;
   int64_t base = 0;
   int64_t i = slot;
+  bool from_mask = false;
   if (valid) {
     if (perm) i = perm[slot];
-    const float* gi = g + 7 * i;
-    qy = obb_query(gi[0], gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], img_w, img_h, ts, (float)p.alpha_threshold);
-    if (MODE == 1) d = depth[i];
     if (EMIT) base = cum[slot];
+    if (MODE == 2 && masks != nullptr) {
+      const uint2 m = masks[slot];
+      if (!(m.y & kMaskRecompute)) {  // expand the recorded bits, in bit order = x outer / y inner
+        from_mask = true;
+        const int min_x = m.y & 0xfff, min_y = (m.y >> 12) & 0xfff, span_y = (m.y >> 24) & 0x3f;
+        unsigned bits = m.x;
+        int c = 0;
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int tu = b / span_y, tv = b - tu * span_y;
+          keys[base + c] = (KeyT)((tu + min_x) + (tv + min_y) * tiles_wide);
+          values[base + c] = (int32_t)i;
+          ++c;
+        }
+      }
+    }
+    if (!from_mask) {
+      const float* gi = g + 7 * i;
+      qy = obb_query(gi[0], gi[1], gi[2], gi[3], gi[4], gi[5], gi[6], img_w, img_h, ts, (float)p.alpha_threshold);
+      if (MODE == 1) d = depth[i];
+    }
   }
   const int n = span_count(qy);
   int count = 0;
 
   if (n <= kSerialSpan) {
+    unsigned bits = 0;
     for (int tu = 0; tu < qy.span_x; ++tu)
       for (int tv = 0; tv < qy.span_y; ++tv)
         if (test_tile(qy, tu, tv, ts)) {
@@ -185,9 +212,18 @@ tile_query_kernel(const __grid_constant__ GsTileParams p, int img_w, int img_h, 
             keys[base + count] = MODE == 2 ? (KeyT)tile_id
                                  : sizeof(KeyT) == 8 ? (KeyT)make_key64(d, tile_id) : (KeyT)make_key32(d, tile_id);
             values[base + count] = (int32_t)i;
+          } else {
+            bits |= 1u << (tu * qy.span_y + tv);
           }
           ++count;
         }
+    if (!EMIT && masks != nullptr && valid) {
+      const bool fits = qy.min_x < 4096 && qy.min_y < 4096;
+      masks[slot] = fits ? make_uint2(bits, (unsigned)qy.min_x | ((unsigned)qy.min_y << 12) | ((unsigned)qy.span_y << 24))
+                         : make_uint2(0u, kMaskRecompute);
+    }
+  } else if (!EMIT && masks != nullptr && valid) {
+    masks[slot] = make_uint2(0u, kMaskRecompute);
   }
   unsigned big = __ballot_sync(kFull, n > kSerialSpan);
   while (big) {
@@ -332,7 +368,7 @@ int gs_tile_count(const GsTileParams* p, const float* gaussians, int32_t* counts
   int img_w = (int)ceil_div(p->image_width, ts) * ts, img_h = (int)ceil_div(p->image_height, ts) * ts;
   int64_t blocks = ceil_div(p->num_points, kTileBlock);
   tile_query_kernel<0, uint64_t><<<(unsigned)blocks, kTileBlock, 0, (cudaStream_t)stream>>>(
-      *p, img_w, img_h, gaussians, nullptr, nullptr, nullptr, counts, nullptr, nullptr);
+      *p, img_w, img_h, gaussians, nullptr, nullptr, nullptr, counts, nullptr, nullptr, nullptr);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }
@@ -348,10 +384,10 @@ int gs_tile_emit_keys(const GsTileParams* p, const float* gaussians, const float
   int64_t blocks = ceil_div(p->num_points, kTileBlock);
   if (p->use_depth16)
     tile_query_kernel<1, uint32_t><<<(unsigned)blocks, kTileBlock, 0, (cudaStream_t)stream>>>(
-        *p, img_w, img_h, gaussians, depth, nullptr, cum, nullptr, (uint32_t*)keys, values);
+        *p, img_w, img_h, gaussians, depth, nullptr, cum, nullptr, (uint32_t*)keys, values, nullptr);
   else
     tile_query_kernel<1, uint64_t><<<(unsigned)blocks, kTileBlock, 0, (cudaStream_t)stream>>>(
-        *p, img_w, img_h, gaussians, depth, nullptr, cum, nullptr, (uint64_t*)keys, values);
+        *p, img_w, img_h, gaussians, depth, nullptr, cum, nullptr, (uint64_t*)keys, values, nullptr);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }
@@ -400,7 +436,7 @@ int gs_depth_keys(const GsTileParams* p, const float* depth, double near_plane, 
 }
 
 int gs_tile_count_perm(const GsTileParams* p, const float* gaussians, const int32_t* perm, int32_t* counts,
-                       void* stream) {
+                       uint64_t* tile_masks, void* stream) {
   int rc = check_tile_params(p, "gs_tile_count_perm");
   if (rc != GS_OK) return rc;
   if (p->num_points == 0) return GS_OK;
@@ -408,13 +444,13 @@ int gs_tile_count_perm(const GsTileParams* p, const float* gaussians, const int3
   int ts = p->tile_size;
   int img_w = (int)ceil_div(p->image_width, ts) * ts, img_h = (int)ceil_div(p->image_height, ts) * ts;
   tile_query_kernel<0, uint32_t><<<(unsigned)ceil_div(p->num_points, kTileBlock), kTileBlock, 0, (cudaStream_t)stream>>>(
-      *p, img_w, img_h, gaussians, nullptr, perm, nullptr, counts, nullptr, nullptr);
+      *p, img_w, img_h, gaussians, nullptr, perm, nullptr, counts, nullptr, nullptr, (uint2*)tile_masks);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }
 
 int gs_tile_emit_tiles(const GsTileParams* p, const float* gaussians, const int32_t* perm, const int32_t* cum,
-                       uint32_t* tile_ids, int32_t* values, void* stream) {
+                       const uint64_t* tile_masks, uint32_t* tile_ids, int32_t* values, void* stream) {
   int rc = check_tile_params(p, "gs_tile_emit_tiles");
   if (rc != GS_OK) return rc;
   if (p->num_points == 0) return GS_OK;
@@ -422,7 +458,7 @@ int gs_tile_emit_tiles(const GsTileParams* p, const float* gaussians, const int3
   int ts = p->tile_size;
   int img_w = (int)ceil_div(p->image_width, ts) * ts, img_h = (int)ceil_div(p->image_height, ts) * ts;
   tile_query_kernel<2, uint32_t><<<(unsigned)ceil_div(p->num_points, kTileBlock), kTileBlock, 0, (cudaStream_t)stream>>>(
-      *p, img_w, img_h, gaussians, nullptr, perm, cum, nullptr, tile_ids, values);
+      *p, img_w, img_h, gaussians, nullptr, perm, cum, nullptr, tile_ids, values, (uint2*)tile_masks);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }

@@ -103,15 +103,16 @@ def _map_to_tiles(gaussians, depth, image_size, config, use_depth16=False, ndc_r
              N.ptr(depth_keys), N.ptr(iota), stream)
       _, perm = radix_sort_pairs(depth_keys, iota, 0, 16 if use_depth16 else 32)
       counts = torch.empty((n,), dtype=torch.int32, device=device)
-      N.call("gs_tile_count_perm", ctypes.byref(p), N.ptr(g), N.ptr(perm), N.ptr(counts), stream)
+      masks = torch.empty((n,), dtype=torch.int64, device=device)   # per slot tile bit masks: count pass -> emit pass
+      N.call("gs_tile_count_perm", ctypes.byref(p), N.ptr(g), N.ptr(perm), N.ptr(counts), N.ptr(masks), stream)
       cum = full_cumsum_device(counts)
       total = int(cum[-1].item())   # host read-back of K
 
     if total > 0:
       tile_ids = torch.empty((total,), dtype=torch.int32, device=device)
       values = torch.empty((total,), dtype=torch.int32, device=device)
-      N.call("gs_tile_emit_tiles", ctypes.byref(p), N.ptr(g), N.ptr(perm), N.ptr(cum), N.ptr(tile_ids), N.ptr(values),
-             stream)
+      N.call("gs_tile_emit_tiles", ctypes.byref(p), N.ptr(g), N.ptr(perm), N.ptr(cum), N.ptr(masks), N.ptr(tile_ids),
+             N.ptr(values), stream)
       tile_bits = max(1, (shape[0] * shape[1] - 1).bit_length())
       tile_ids, overlap_to_point = radix_sort_pairs(tile_ids, values, 0, tile_bits)
     else:
