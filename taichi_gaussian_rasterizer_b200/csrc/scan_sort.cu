@@ -132,7 +132,8 @@ __global__ void radix_histogram_scan_kernel(unsigned* __restrict__ global_hist) 
 // One onesweep pass: rank keys of a tile by the current digit (warp match-any multi-split + per-warp
 // shared histograms), chain the per-digit tile counts through decoupled look-back, reorder the tile in
 // shared memory and write digit runs back coalesced.  Stable: ranks follow input order.
-template <typename KeyT>
+// FULL: the digit has all kRadixBits bits (every pass but a short last one): no per bit "is this bit in the mask" test.
+template <typename KeyT, bool FULL>
 __global__ void __launch_bounds__(kSortBlock, 3)
 onesweep_pass_kernel(int64_t n, const KeyT* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
                      KeyT* __restrict__ keys_out, int32_t* __restrict__ vals_out, int shift, unsigned mask,
@@ -177,10 +178,10 @@ onesweep_pass_kernel(int64_t n, const KeyT* __restrict__ keys_in, const int32_t*
     unsigned pm = kFull;
 #pragma unroll
     for (int b = 0; b < kRadixBits; ++b) {
-      if ((mask >> b) & 1u) {  // uniform: short last digits skip their absent bits
-        const bool bit = (d >> b) & 1u;
+      if (FULL || ((mask >> b) & 1u)) {  // uniform: short last digits skip their absent bits
+        const bool bit = (d & (1u << b)) != 0u;
         const unsigned bal = __ballot_sync(kFull, bit);
-        pm &= bit ? bal : ~bal;
+        pm &= bal ^ (bit ? 0u : ~0u);
       }
     }
     peers[k] = pm;
@@ -323,8 +324,8 @@ static int radix_sort_impl(int64_t n, const KeyT* keys_in, const int32_t* vals_i
   GS_LAUNCH_CHECK();
 
   const size_t smem = sort_smem_bytes<KeyT>();
-  auto kern = onesweep_pass_kernel<KeyT>;
-  GS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GS_CUDA(cudaFuncSetAttribute(onesweep_pass_kernel<KeyT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GS_CUDA(cudaFuncSetAttribute(onesweep_pass_kernel<KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const KeyT* src_k = keys_in;
   const int32_t* src_v = vals_in;
   for (int p = 0; p < L.passes; ++p) {
@@ -334,6 +335,7 @@ static int radix_sort_impl(int64_t n, const KeyT* keys_in, const int32_t* vals_i
     int32_t* dst_v = to_out ? vals_out : tmp_vals;
     const int shift = begin_bit + p * kRadixBits;
     const int nb = min(kRadixBits, end_bit - shift);
+    auto kern = nb == kRadixBits ? onesweep_pass_kernel<KeyT, true> : onesweep_pass_kernel<KeyT, false>;
     kern<<<(unsigned)L.tiles, kSortBlock, smem, st>>>(
         n, src_k, src_v, dst_k, dst_v, shift, (1u << nb) - 1u, hist + p * kRadix,
         status + (size_t)p * L.tiles * kRadix, tickets + p);
