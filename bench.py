@@ -300,6 +300,28 @@ def run_ours(args):
   launches += (sort_calls // 2) * ((2 + 4) + (2 + -(-tile_bits // 8)))
   launches = launches // max(args.steps, 1)
 
+  # HBM rooflines of the bandwidth-bound stages: SURVEY.md §8(d) algorithmic bytes per launch over the live CUDA-event
+  # time of the entry point (the sort figure covers both sorts of a frame: V depth keys in 4 passes, K tile ids in 2)
+  T_tiles, CD = int(ranges.shape[0] * ranges.shape[1]), 3 * (W["sh_degree"] + 1) ** 2
+  passes_k = -(-tile_bits // 8)
+  alg_bytes = {
+    "gs_project_fwd": 44 * n + 40 * V,
+    "gs_project_bwd": 84 * V + 44 * n + 44 * V,                 # + the read half of the in-kernel accumulation
+    "gs_sh_fwd_counted": V * (8 + 12 + 4 * CD) + 12 * V,
+    "gs_sh_bwd": V * (32 + 12) + 4 * CD * n + 4 * CD * V,        # coefficient rows not read; bucket rows read + written
+    "gs_full_cumsum": 8 * V,
+    "gs_tile_emit_tiles": 20 * V + 8 * K,
+    "gs_radix_sort_pairs": (4 * V + 16 * V * 4) + (4 * K + 16 * K * passes_k),
+    "gs_find_ranges_tiles": 4 * K + 8 * T_tiles,
+  }
+  hbm_stages = {}
+  for name, nbytes in alg_bytes.items():
+    ms = stage_ms.get(name)
+    if ms:
+      gbs = nbytes / (ms * 1e-3) / 1e9
+      hbm_stages[name] = {"algorithmic_bytes": int(nbytes), "ms": ms, "achieved_gbs": round(gbs, 1),
+                          "frac": round(gbs / peak_gbs, 3) if peak_gbs else None}
+
   out = {
     "metric": "gaussians_px_per_s_fwd_bwd", "value": value, "unit": "gaussian*pixel/s",
     "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -326,6 +348,7 @@ def run_ours(args):
                  "blend_evals_per_s": K * 256 / (bwd_avg_ms * 1e-3) if bwd_avg_ms > 0 else None,
                  "issue_roofline": issue},
     "stage_ms_per_frame": stage_ms,
+    "hbm_stage_rooflines": hbm_stages,
     "clocks": clocks,
   }
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
