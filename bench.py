@@ -389,6 +389,7 @@ def cpu_sample(W, stride):
 def cpu_baseline(W, budget_s=12.0):
   import oracle
   from taichi_gaussian_rasterizer_b200 import RasterConfig
+  use_all_host_threads()
   config = RasterConfig(tile_size=W["tile_size"])
   n, gaussians, camera = cpu_sample(W, CPU_SAMPLE_STRIDE)
   t0 = time.perf_counter()
@@ -407,6 +408,16 @@ def cpu_baseline(W, budget_s=12.0):
                     f"same camera, {w}x{h}, SH3, fwd+bwd): {dt:.2f} s/frame, V={V}, K={K}"}
 
 
+def use_all_host_threads():
+  """torchrun exports OMP_NUM_THREADS=1 for N > 1; the CPU legs are meant to use every host core the process may
+  run on, so the thread counts of the OpenMP oracle and of torch are set explicitly."""
+  import oracle
+  cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+  oracle.set_num_threads(cores)
+  torch.set_num_threads(cores)
+  return cores
+
+
 def run_reference(args):
   """The reference's algorithm on the host cores: the Taichi package cannot be installed here (no wheel, no
   network; its rasterizer has no CPU arch anyway, SURVEY.md header), so this arm times oracle/ — the C++/OpenMP
@@ -416,6 +427,7 @@ def run_reference(args):
     return
   import oracle
   from taichi_gaussian_rasterizer_b200 import RasterConfig
+  use_all_host_threads()
   W = dict(WORKLOAD)
   if args.num_gaussians:
     W["num_gaussians"] = args.num_gaussians
