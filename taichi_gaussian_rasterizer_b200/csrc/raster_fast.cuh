@@ -15,7 +15,8 @@ inline int fast_feature_pad(int F) { return F <= 4 ? 4 : F <= 8 ? 8 : F <= 16 ? 
 // Workspace layout (all 256 B aligned):
 //   recF  V x 2 float4 : {mx, my, a1x, a1y} {a2x, a2y, log2(alpha), idx}       (forward records)
 //   featP V x FP float  : features padded to FP
-//   recB  V x 2 float4 : {mx, my, ax, ay} {1/sx, 1/sy, alpha, idx}             (backward records)
+//   recB  V x 2 float4 : {mx, my, ax, ay} {1/sx, 1/sy, alpha, idx}             (records of the wide backward, F > 7;
+//                                                                               the narrow one walks recF)
 struct FastLayout {
   size_t off_recF, off_feat, off_recB, total;
   int FP;

@@ -38,13 +38,12 @@ struct CullConic {
 };
 
 __device__ __forceinline__ CullConic make_cull_conic(const float4 r0, const float4 r1, float l2thr) {
-  CullConic c;
-  const float cx = kSqrtHalfLog2e * r1.x, cy = kSqrtHalfLog2e * r1.y;
-  const float a1x = r0.z * cx, a1y = r0.w * cx, a2x = -r0.w * cy, a2y = r0.z * cy;
+  CullConic c;   // forward record: {mx, my, a1x, a1y} {a2x, a2y, log2(alpha0), idx}, a1 / a2 = scaled axes
+  const float a1x = r0.z, a1y = r0.w, a2x = r1.x, a2y = r1.y;
   c.mx = r0.x; c.my = r0.y;
   c.A00 = a1x * a1x + a2x * a2x; c.A01 = a1x * a1y + a2x * a2y; c.A11 = a1y * a1y + a2y * a2y;
   c.r00 = fast_rcp(c.A00); c.r11 = fast_rcp(c.A11);
-  c.qlim = (log2f(r1.z) - l2thr) * 1.001f + 1e-3f;
+  c.qlim = (r1.z - l2thr) * 1.001f + 1e-3f;
   return c;
 }
 
@@ -180,7 +179,7 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
           any &= any - 1;
           const int j = c0 + jl;
           const float4 r0 = s_r0[buf][j], r1 = s_r1[buf][j];
-          const float mx = r0.x, my = r0.y, ax = r0.z, ay = r0.w, isx = r1.x, isy = r1.y, a0 = r1.z;
+          const float mx = r0.x, my = r0.y, a1x = r0.z, a1y = r0.w, a2x = r1.x, a2y = r1.y, l2a = r1.z;
           float f[F];
 #pragma unroll
           for (int c = 0; c < F; ++c) f[c] = s_feat[buf][j][c];
@@ -193,14 +192,11 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
 #pragma unroll
           for (int i = 0; i < NSUB; ++i) {
             if ((bm[i] >> jl) & 1u) {  // warp-uniform: this sub-block can be reached at all
-              const float dx = dxb + 8.f * (i & 1), dy = dyb + 4.f * (i >> 1);
-              const float u = fmaf(dy, ay, dx * ax), w_ = fmaf(dy, ax, -dx * ay);   // offset in the gaussian's frame
-              const float tx = u * isx, ty = w_ * isy;
-              const float q = fmaf(ty, ty, tx * tx);
-              const float pgauss = fast_ex2(-kHalfLog2e * q);
-              float alpha = a0 * pgauss;
-              if (alpha > thr && W[i] < sat) {
-                alpha = fminf(alpha, cmax);
+              const float dx = (i & 1) ? dxb + 8.f : dxb, dy = (i >> 1) ? dyb + 4.f * (i >> 1) : dyb;   // no x + 0.f
+              const float tx = fmaf(dy, a1y, dx * a1x), ty = fmaf(dy, a2y, dx * a2x);   // k x offset / sigma, own frame
+              const float araw = fast_ex2(fmaf(-ty, ty, fmaf(-tx, tx, l2a)));   // alpha0 p, as the forward forms it
+              if (araw > thr && W[i] < sat) {
+                const float alpha = fminf(araw, cmax);
                 const float Ti = 1.f - W[i];
                 const float w = alpha * Ti;
                 W[i] += w;
@@ -213,15 +209,14 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
                 }
                 RG[i] = fmaf(-fG, w, RG[i]);
                 const float ag = fmaf(fG, Ti, -RG[i] * rinv);   // dL/dalpha
-                const float gp = ag * pgauss;                   // dL/dalpha0 share of this pixel
-                const float gu = gp * u, gw = gp * w_;
+                const float gp = ag * araw;                     // alpha0 x the dL/dalpha0 share of this pixel
+                const float gu = gp * tx, gw = gp * ty;
                 M0 += gp; Mu += gu; Mw += gw;
-                Muu = fmaf(gu, u, Muu); Mww = fmaf(gw, w_, Mww); Muw = fmaf(gu, w_, Muw);
+                Muu = fmaf(gu, tx, Muu); Mww = fmaf(gw, ty, Mww); Muw = fmaf(gu, ty, Muw);
                 if (HEUR) {
-                  const float aag = a0 * ag;
-                  const float a = a0 * gu * (isx * isx), bq = a0 * gw * (isy * isy);
-                  h0 = fmaf(aag, aag, h0);
-                  h1 += fabsf(fmaf(a, ax, -bq * ay)) + fabsf(fmaf(a, ay, bq * ax));
+                  const float aag = fast_ex2(l2a) * ag;
+                  h0 = fmaf(aag, aag, h0);   // |d/dmean| of this pixel: g (tx a1 + ty a2) / k^2
+                  h1 += (fabsf(fmaf(gu, a1x, gw * a2x)) + fabsf(fmaf(gu, a1y, gw * a2y))) * (1.f / kHalfLog2e);
                 }
               }
             }
@@ -246,30 +241,32 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
   cp_async_wait<0>();
 }
 
-// Moments -> gradient of the packed gaussian, in place in grad_gaussians (rows hold {M0, Mu, Mw, Muu, Mww, Muw, 0}).
-// With c, s the unit axis, u = dx c + dy s, w = dy c - dx s, tx = u / sx, ty = w / sy and g = alpha0 dL/dalpha p:
-//   d/dmean  = R (sum g u / sx^2, sum g w / sy^2),  d/dsigma = (sum g u^2 / sx^3, sum g w^2 / sy^3),
-//   d/daxis  = (-(c P + s Q), c Q - s P) with P = sum g (u^2 / sx^2 + w^2 / sy^2), Q = (1 / sy^2 - 1 / sx^2) sum g u w,
-//   d/dalpha0 = sum g / alpha0 = M0       (the sums of rasterizer/backward.py:170-200, regrouped; the moments are
-//   accumulated without the alpha0 factor, which is applied here).
+// Moments -> gradient of the packed gaussian, in place in grad_gaussians (rows hold {M0, Mt, Ms, Mtt, Mss, Mts, 0}).
+// The pixel loop works in the forward record's frame: t = k u / sx, s = k w / sy with u, w the offset along / across
+// the unit axis (c, s_) and k = sqrt(log2(e) / 2), and sums g = alpha0 dL/dalpha p (what ex2 returns there, times
+// dL/dalpha).  Regrouping the sums of rasterizer/backward.py:170-200:
+//   d/dmean  = R (Mt / (k sx), Ms / (k sy)),   d/dsigma = (Mtt / (k^2 sx), Mss / (k^2 sy)),
+//   d/daxis  = (-(c P + s_ Q), c Q - s_ P) with P = (Mtt + Mss) / k^2, Q = (sx / sy - sy / sx) Mts / k^2,
+//   d/dalpha0 = M0 / alpha0.
 __global__ void __launch_bounds__(256)
-raster_bwd_moments_kernel(int64_t V, const float4* __restrict__ rec, float* __restrict__ grad_pts) {
+raster_bwd_moments_kernel(int64_t V, const float* __restrict__ g2d, float* __restrict__ grad_pts) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= V) return;
   float* m = grad_pts + 7 * i;
-  const float M0 = m[0], Mu = m[1], Mw = m[2], Muu = m[3], Mww = m[4], Muw = m[5];
-  const float4 r0 = rec[2 * i], r1 = rec[2 * i + 1];
-  const float c = r0.z, s = r0.w, isx = r1.x, isy = r1.y, a0 = r1.z;
-  const float ix2 = isx * isx, iy2 = isy * isy;
-  const float U = a0 * ix2 * Mu, Vv = a0 * iy2 * Mw;
-  const float P = a0 * fmaf(ix2, Muu, iy2 * Mww), Q = a0 * (iy2 - ix2) * Muw;
+  const float* g = g2d + 7 * i;
+  const float M0 = m[0], Mt = m[1], Ms = m[2], Mtt = m[3], Mss = m[4], Mts = m[5];
+  const float c = g[2], s = g[3], sx = g[4], sy = g[5], a0 = g[6];
+  const float isx = 1.0f / sx, isy = 1.0f / sy;
+  constexpr float ik = 1.f / kSqrtHalfLog2e, ik2 = 1.f / kHalfLog2e;
+  const float U = ik * isx * Mt, Vv = ik * isy * Ms;
+  const float P = ik2 * (Mtt + Mss), Q = ik2 * (sx * isy - sy * isx) * Mts;
   m[0] = fmaf(c, U, -s * Vv);
   m[1] = fmaf(s, U, c * Vv);
   m[2] = -fmaf(c, P, s * Q);
   m[3] = fmaf(c, Q, -s * P);
-  m[4] = a0 * ix2 * isx * Muu;
-  m[5] = a0 * iy2 * isy * Mww;
-  m[6] = M0;
+  m[4] = ik2 * isx * Mtt;
+  m[5] = ik2 * isy * Mss;
+  m[6] = M0 / a0;
 }
 
 template <int F, int FP>
@@ -286,8 +283,8 @@ static int launch_bwd_fast(const GsRasterParams& p, const RasterArgs& a, const f
 #undef GS_BWD_LAUNCH
   GS_LAUNCH_CHECK();
   if (p.points_requires_grad && a.grad_gaussians != nullptr && p.num_points > 0) {
-    raster_bwd_moments_kernel<<<(unsigned)ceil_div(p.num_points, 256), 256, 0, st>>>(p.num_points, rec,
-                                                                                      (float*)a.grad_gaussians);
+    raster_bwd_moments_kernel<<<(unsigned)ceil_div(p.num_points, 256), 256, 0, st>>>(
+        p.num_points, (const float*)a.gaussians2d, (float*)a.grad_gaussians);
     GS_LAUNCH_CHECK();
   }
   return GS_OK;
@@ -302,9 +299,10 @@ int raster_bwd_fast(const GsRasterParams& p, const RasterArgs& a, cudaStream_t s
   }
   const FastLayout L = fast_layout(p);
   unsigned char* ws = (unsigned char*)a.workspace;
-  const float4* rec = (const float4*)(ws + L.off_recB);
   const float* featP = (const float*)(ws + L.off_feat);
-  if (p.num_features > 7) return raster_bwd_wide(p, a, rec, featP, st);  // 8..64 channels: one pixel per lane
+  if (p.num_features > 7)   // 8..64 channels: one pixel per lane, its own records
+    return raster_bwd_wide(p, a, (const float4*)(ws + L.off_recB), featP, st);
+  const float4* rec = (const float4*)(ws + L.off_recF);   // the forward's records
   switch (p.num_features) {
     case 1: return launch_bwd_fast<1, 4>(p, a, rec, featP, st);
     case 2: return launch_bwd_fast<2, 4>(p, a, rec, featP, st);

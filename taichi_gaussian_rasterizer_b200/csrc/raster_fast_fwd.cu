@@ -56,9 +56,11 @@ int raster_fast_pack(const GsRasterParams& p, const RasterArgs& a, bool forward,
   unsigned char* ws = (unsigned char*)a.workspace;
   // the forward call also packs the backward records when a gradient will be asked for, so that the backward
   // call (workspace_holds_packed) launches no pack kernel at all
+  // The narrow backward (F <= 7, raster_fast_bwd.cu) walks the forward's records; only the wide one has its own.
   const bool want_bwd = !forward || p.points_requires_grad || p.features_requires_grad;
-  float4* recF = forward ? (float4*)(ws + L.off_recF) : nullptr;
-  float4* recB = want_bwd ? (float4*)(ws + L.off_recB) : nullptr;
+  const bool narrow = p.num_features <= 7;
+  float4* recF = (forward || narrow) ? (float4*)(ws + L.off_recF) : nullptr;
+  float4* recB = (want_bwd && !narrow) ? (float4*)(ws + L.off_recB) : nullptr;
   float* featP = features ? (float*)(ws + L.off_feat) : nullptr;
   const int64_t blocks = ceil_div(p.num_points, 256);
 #define GS_PACK(FPV)                                                                                          \
