@@ -66,9 +66,9 @@ __device__ __forceinline__ bool block_may_touch(float mx, float my, float a1x, f
   const float dxc = fminf(fmaxf(0.f, dx0), dx1);
   const float dyc = fminf(fmaxf(0.f, dy0), dy1);
   const float A00 = a1x * a1x + a2x * a2x, A01 = a1x * a1y + a2x * a2y, A11 = a1y * a1y + a2y * a2y;
-  const float dyv = fminf(fmaxf(__fdividef(-A01 * dxc, A11), dy0), dy1);
+  const float dyv = fminf(fmaxf(-A01 * dxc * fast_rcp(A11), dy0), dy1);
   const float qv = A00 * dxc * dxc + 2.f * A01 * dxc * dyv + A11 * dyv * dyv;
-  const float dxh = fminf(fmaxf(__fdividef(-A01 * dyc, A00), dx0), dx1);
+  const float dxh = fminf(fmaxf(-A01 * dyc * fast_rcp(A00), dx0), dx1);
   const float qh = A00 * dxh * dxh + 2.f * A01 * dxh * dyc + A11 * dyc * dyc;
   return fminf(qv, qh) < qmax * 1.001f + 1e-3f;
 }
@@ -85,10 +85,15 @@ __device__ __forceinline__ void reduce_scatter_step(float* v, int lane) {
       const bool upper = (lane & OFF) != 0;
 #pragma unroll
       for (int i = 0; i < H; ++i) {
-        const float hi = (i + H < N) ? v[i + H] : 0.f;
-        const float send = upper ? v[i] : hi;
-        const float keep = upper ? hi : v[i];
-        v[i] = keep + __shfl_xor_sync(kFull, send, OFF);
+        if (i + H < N) {
+          const float send = upper ? v[i] : v[i + H];
+          const float keep = upper ? v[i + H] : v[i];
+          v[i] = keep + __shfl_xor_sync(kFull, send, OFF);
+        } else {
+          // odd N: the unpaired value is summed on both sides (no selects); the upper half's copy is a duplicate
+          // that reduce_owner never hands out
+          v[i] += __shfl_xor_sync(kFull, v[i], OFF);
+        }
       }
       reduce_scatter_step<H, OFF / 2>(v, lane);
     } else {

@@ -26,6 +26,8 @@
 // them, no shuffles) was built and measured in round 1: same instruction count, lower issue rate (1.74 vs 1.58 ms
 // on the bench workload), so it was dropped (kernel table).
 // F is a template parameter (1..7 here, wider F takes raster_generic.cu).
+#include <cstdlib>
+
 #include "raster_fast.cuh"
 
 namespace gs {
@@ -279,7 +281,9 @@ static int launch_bwd_fast(const GsRasterParams& p, const RasterArgs& a, const f
       p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,   \
       (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr)
   // NSUB = 4 (two warps per tile) measured faster than NSUB = 8 (one warp per tile, 96 registers): 1.58 vs 1.70 ms
-  if (heur) GS_BWD_LAUNCH(true, 4); else GS_BWD_LAUNCH(false, 4);
+  static const int nsub = getenv("GS_BWD_NSUB") ? atoi(getenv("GS_BWD_NSUB")) : 4;   // experiment switch
+  if (nsub == 8) { if (heur) GS_BWD_LAUNCH(true, 8); else GS_BWD_LAUNCH(false, 8); }
+  else if (heur) GS_BWD_LAUNCH(true, 4); else GS_BWD_LAUNCH(false, 4);
 #undef GS_BWD_LAUNCH
   GS_LAUNCH_CHECK();
   if (p.points_requires_grad && a.grad_gaussians != nullptr && p.num_points > 0) {
