@@ -116,6 +116,7 @@ KERNELS_PER_CALL = {  # kernels launched by each entry point (memsets not counte
   "gs_project_fwd": 1, "gs_project_bwd": 1, "gs_sh_fwd": 1, "gs_sh_bwd": 1, "gs_tile_count": 1, "gs_full_cumsum": 1,
   "gs_tile_emit_keys": 1, "gs_find_ranges": 1, "gs_raster_fwd": 2, "gs_raster_bwd": 2,
   "gs_depth_keys": 1, "gs_tile_count_perm": 1, "gs_tile_emit_tiles": 1, "gs_find_ranges_tiles": 1,
+  "gs_camera_position": 1, "gs_sh_fwd_counted": 1,
 }
 
 

@@ -264,6 +264,13 @@ int gs_opt_step(const GsOptParams* p, const int64_t* indexes, const float* weigh
 int gs_morton_codes(int64_t n, const float* points, const float* lower, const float* inc, int64_t grid_size,
                     int32_t code_bits, void* codes, void* stream);
 
+/* ------------------------------------------------------------------ camera centre
+ * replaces CameraParams.camera_position (perspective/params.py:75-78: torch.inverse(T_camera_world)[:3, 3], an LU
+ * factorisation whose info check synchronises the host): position = -A^-1 t of the affine view matrix [A | t] held
+ * row-major in T_camera_world (4x4, only the first three rows are read), A^-1 from cross products.  One thread, no
+ * workspace, nothing read back.  dtype GS_F32 / GS_F64. */
+int gs_camera_position(int32_t dtype, const void* T_camera_world, void* position, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

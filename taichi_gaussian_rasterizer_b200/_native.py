@@ -23,7 +23,7 @@ EXPORTS = [
   "gs_depth_keys", "gs_tile_count_perm", "gs_tile_emit_tiles", "gs_find_ranges_tiles",
   "gs_raster_workspace_bytes", "gs_raster_fwd", "gs_raster_bwd",
   "gs_opt_update_visibility", "gs_opt_accumulate_weight", "gs_opt_step",
-  "gs_morton_codes",
+  "gs_morton_codes", "gs_camera_position",
 ]
 
 

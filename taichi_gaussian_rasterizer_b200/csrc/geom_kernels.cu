@@ -292,6 +292,22 @@ __global__ void depth_keys_kernel(int64_t n, int use_depth16, int to_ndc, float 
   values[i] = (int32_t)i;
 }
 
+// ---- camera centre: -A^-1 t of the affine view matrix [A | t], A^-1 from cross products (one thread; replaces the
+// ten ATen launches of the same closed form, or torch.inverse + its host sync, perspective/params.py:75-78)
+template <typename T>
+__global__ void camera_position_kernel(const T* __restrict__ M, T* __restrict__ out) {
+  const T a0x = M[0], a0y = M[1], a0z = M[2], tx = M[3];
+  const T a1x = M[4], a1y = M[5], a1z = M[6], ty = M[7];
+  const T a2x = M[8], a2y = M[9], a2z = M[10], tz = M[11];
+  const T c0x = a1y * a2z - a1z * a2y, c0y = a1z * a2x - a1x * a2z, c0z = a1x * a2y - a1y * a2x;   // a1 x a2
+  const T c1x = a2y * a0z - a2z * a0y, c1y = a2z * a0x - a2x * a0z, c1z = a2x * a0y - a2y * a0x;   // a2 x a0
+  const T c2x = a0y * a1z - a0z * a1y, c2y = a0z * a1x - a0x * a1z, c2z = a0x * a1y - a0y * a1x;   // a0 x a1
+  const T det = a0x * c0x + a0y * c0y + a0z * c0z;
+  out[0] = -(c0x * tx + c1x * ty + c2x * tz) / det;
+  out[1] = -(c0y * tx + c1y * ty + c2y * tz) / det;
+  out[2] = -(c0z * tx + c1z * ty + c2z * tz) / det;
+}
+
 }  // namespace gs
 
 using namespace gs;
@@ -409,6 +425,17 @@ int gs_find_ranges(const GsTileParams* p, int64_t num_overlaps, const void* sort
   else
     find_ranges_kernel<uint64_t, 32><<<(unsigned)blocks, 256, 0, st>>>(num_overlaps, (const uint64_t*)sorted_keys,
                                                                       tile_ranges);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+int gs_camera_position(int32_t dtype, const void* T_camera_world, void* position, void* stream) {
+  GS_CHECK_ARG(T_camera_world && position, "gs_camera_position: null tensor");
+  GS_CHECK_ARG(dtype == GS_F32 || dtype == GS_F64, "gs_camera_position: dtype must be GS_F32 or GS_F64");
+  if (dtype == GS_F32)
+    camera_position_kernel<float><<<1, 1, 0, (cudaStream_t)stream>>>((const float*)T_camera_world, (float*)position);
+  else
+    camera_position_kernel<double><<<1, 1, 0, (cudaStream_t)stream>>>((const double*)T_camera_world, (double*)position);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }

@@ -66,6 +66,15 @@ class CameraParams:
     perspective/projection.py:212), so the position is -A^-1 t; A^-1 is formed from cross products.  Unlike
     ``torch.inverse`` on a CUDA tensor this launches no LU factorisation and does not synchronise the host
     (the info check of linalg.inv costs a device round trip per frame), and it stays differentiable."""
+    T = self.T_camera_world
+    if T.is_cuda and T.dtype in (torch.float32, torch.float64) and not (T.requires_grad and torch.is_grad_enabled()):
+      # one single-thread kernel (gs_camera_position) instead of ten ATen launches of the same closed form
+      import ctypes
+      from .. import _native as N
+      Tc = T.detach().contiguous()
+      out = torch.empty((3,), dtype=T.dtype, device=T.device)
+      N.call("gs_camera_position", ctypes.c_int32(N.dtype_code(T.dtype)), N.ptr(Tc), N.ptr(out), N.stream_ptr(T.device))
+      return out
     A, t = self.T_camera_world[0:3, 0:3], self.T_camera_world[0:3, 3]
     c0 = torch.linalg.cross(A[1], A[2])
     c1 = torch.linalg.cross(A[2], A[0])

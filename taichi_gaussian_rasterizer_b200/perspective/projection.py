@@ -70,6 +70,7 @@ class _ProjectFunction(torch.autograd.Function):
 
     ctx.params = params
     ctx.mark_non_differentiable(indexes)
+    ctx.set_materialize_grads(False)   # no zero fills for outputs nobody differentiated (depth, indexes)
     ctx.save_for_backward(position, log_scaling, rotation, alpha_logit, T_camera_world, projection, indexes)
     return points, depth, indexes
 
@@ -78,6 +79,8 @@ class _ProjectFunction(torch.autograd.Function):
     position, log_scaling, rotation, alpha_logit, T_camera_world, projection, indexes = ctx.saved_tensors
     need = ctx.needs_input_grad
     v = indexes.shape[0]
+    if dpoints is None:   # only the depth was differentiated
+      dpoints = torch.zeros((v, 7), dtype=position.dtype, device=position.device)
     inputs = (position, log_scaling, rotation, alpha_logit, T_camera_world, projection)
     # fused accumulation (grad_sinks.py): when every per gaussian input that needs a gradient has a sink, the kernel
     # adds the visible rows into the sinks and autograd gets no gradient for them
@@ -91,7 +94,7 @@ class _ProjectFunction(torch.autograd.Function):
     params.accumulate_grads = int(fused)
     N.call("gs_project_bwd", ctypes.byref(params), ctypes.c_int64(v), N.ptr(position), N.ptr(log_scaling), N.ptr(rotation),
       N.ptr(alpha_logit), N.ptr(T_camera_world), N.ptr(projection), N.ptr(indexes),
-      N.ptr(dpoints.contiguous()), N.ptr(ddepth.contiguous()), *[N.ptr(g) for g in targets],
+      N.ptr(dpoints.contiguous()), N.ptr(None if ddepth is None else ddepth.contiguous()), *[N.ptr(g) for g in targets],
       N.stream_ptr(position.device))
     params.accumulate_grads = 0
     grads = ([None] * 4 + targets[4:]) if fused else targets

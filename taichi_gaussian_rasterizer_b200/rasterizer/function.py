@@ -89,6 +89,7 @@ class _RasterFunction(torch.autograd.Function):
     ctx.point_heuristic = point_heuristic
     ctx.config = config
     ctx.mark_non_differentiable(image_alpha, visibility, point_heuristic)
+    ctx.set_materialize_grads(False)   # no zero fills for the non-differentiable outputs' gradients
     ctx.save_for_backward(gaussians, features, image_feature)
     return image_feature, image_alpha, point_heuristic, visibility
 
@@ -96,6 +97,8 @@ class _RasterFunction(torch.autograd.Function):
   def backward(ctx, grad_image_feature, grad_alpha, grad_point_heuristic, grad_visibility):
     gaussians, features, image_feature = ctx.saved_tensors
     need_g, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    if grad_image_feature is None:
+      grad_image_feature = torch.zeros_like(image_feature)
     grad_gaussians = torch.empty_like(gaussians) if need_g else None   # zeroed by the callee
     grad_features = torch.empty_like(features) if need_f else None
     params = ctx.params

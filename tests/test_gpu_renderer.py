@@ -127,3 +127,28 @@ def test_fused_gradient_accumulation_matches_autograd(cuda_device, n, margin):
   assert feat_a.abs().sum() > 0
   assert rel_l2(feat_b, feat_a) < 1e-6
   assert rel_l2(flat_b, flat_a) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_camera_position_kernel(cuda_device, dtype):
+  """gs_camera_position == inverse(T_camera_world)[:3, 3] (perspective/params.py:75-78 of the reference), for rigid
+  and for general affine view matrices; the differentiable torch path is kept when the pose needs a gradient."""
+  from taichi_gaussian_rasterizer_b200.synthetic import random_camera
+  torch.manual_seed(3)
+  for k in range(4):
+    cam = random_camera(image_size=(160, 120)).to(dtype=dtype)
+    T = cam.T_camera_world.clone()
+    if k % 2:   # not a rotation: sheared / scaled
+      T[:3, :3] = T[:3, :3] @ (torch.eye(3, dtype=dtype) + 0.3 * torch.rand(3, 3, dtype=dtype))
+    ref = torch.linalg.inv(T.double())[:3, 3]
+    camd = cam.to(device=cuda_device)
+    camd.T_camera_world = T.to(cuda_device)
+    got = camd.camera_position
+    assert got.dtype == dtype and got.shape == (3,)
+    tol = 2e-5 if dtype == torch.float32 else 1e-12
+    assert rel_l2(got.cpu(), ref) < tol
+    Tg = T.to(cuda_device).requires_grad_(True)
+    camd.T_camera_world = Tg
+    pos = camd.camera_position
+    assert pos.requires_grad
+    assert rel_l2(pos.detach().cpu(), ref) < tol
