@@ -116,7 +116,7 @@ KERNELS_PER_CALL = {  # kernels launched by each entry point (memsets not counte
   "gs_project_fwd": 1, "gs_project_bwd": 1, "gs_sh_fwd": 1, "gs_sh_bwd": 1, "gs_tile_count": 1, "gs_full_cumsum": 1,
   "gs_tile_emit_keys": 1, "gs_find_ranges": 1, "gs_raster_fwd": 2, "gs_raster_bwd": 2,
   "gs_depth_keys": 1, "gs_tile_count_perm": 1, "gs_tile_emit_tiles": 1, "gs_find_ranges_tiles": 1,
-  "gs_camera_position": 1, "gs_sh_fwd_counted": 1,
+  "gs_camera_position": 1, "gs_sh_fwd_counted": 1, "gs_sh_bwd_stage": 1, "gs_sh_bwd_flush": 1,
 }
 
 
@@ -204,7 +204,7 @@ def run_ours(args):
       else:
         cam, target = dev_cams[i], dev_targets[i]
       rendering = render_gaussians(gaussians, cam, config, use_sh=True)
-      loss = (rendering.image - target).abs().mean()
+      loss = torch.nn.functional.l1_loss(rendering.image, target)   # mean |image - target|, one fused ATen op each way
       loss.backward()
       total += loss.detach()
       if from_host:
@@ -310,6 +310,10 @@ def run_ours(args):
     "gs_project_bwd": 84 * V + 44 * n + 44 * V,                 # + the read half of the in-kernel accumulation
     "gs_sh_fwd_counted": V * (8 + 12 + 4 * CD) + 12 * V,
     "gs_sh_bwd": V * (32 + 12) + 4 * CD * n + 4 * CD * V,        # coefficient rows not read; bucket rows read + written
+    # deferred SH gradient: per view the masked colour gradient is staged (V x (out, grad, index) in, (N,3) out) ...
+    "gs_sh_bwd_stage": V * (12 + 12 + 8) + 12 * n,
+    # ... and one flush per step reads the staged views + positions and adds to the coefficient rows (per frame share)
+    "gs_sh_bwd_flush": (n * (12 * views + 12 + 2 * 4 * CD)) // views,
     "gs_full_cumsum": 8 * V,
     "gs_tile_emit_tiles": 20 * V + 8 * K,
     "gs_radix_sort_pairs": (4 * V + 16 * V * 4) + (4 * K + 16 * K * passes_k),

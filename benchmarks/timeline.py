@@ -45,7 +45,7 @@ def main():
     with bucket.fused_accumulation():
       for cam, tgt in zip(cams, targets):
         r = render_gaussians(g, cam, cfg, use_sh=True)
-        (r.image - tgt).abs().mean().backward()
+        torch.nn.functional.l1_loss(r.image, tgt).backward()
 
   for _ in range(3):
     step()

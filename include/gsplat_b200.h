@@ -114,6 +114,22 @@ int gs_sh_bwd(const GsSHParams* p, const void* params, const void* positions,
               const int64_t* indexes, const void* camera_pos, const void* grad_out,
               void* grad_params, void* grad_positions, void* grad_camera_pos, void* stream);
 
+/* Deferred coefficient gradient for a multi-view batch (f32, K = 3, D in {4, 16}).  evaluate_sh_at_kernel.grad
+ * (spherical_harmonics.py:154-161) followed by autograd's accumulation rewrites the whole (M,K,D) gradient once per
+ * view; the coefficient gradient of a view is the outer product of the masked colour gradient with the basis of the
+ * viewing direction, so a view only has to keep K floats per gaussian:
+ *   gs_sh_bwd_stage: staged (M,K) <- grad_out (V,K) scattered by `indexes`, zero where the forward value
+ *                    (forward_out (V,K), the clamped output of gs_sh_fwd) sits on the clamp and where culled;
+ *   gs_sh_bwd_flush: grad_params (M,K,D) += sum over the num_views staged views of staged_v (x) basis(positions -
+ *                    camera_positions[v]); `staged` / `camera_positions` are HOST arrays of num_views device pointers
+ *                    ((M,K) and (3,) floats), num_views <= GS_SH_MAX_DEFERRED_VIEWS.
+ * p->num_points = M, p->num_indexes = V (stage only). */
+#define GS_SH_MAX_DEFERRED_VIEWS 16
+int gs_sh_bwd_stage(const GsSHParams* p, const void* forward_out, const int64_t* indexes, const void* grad_out,
+                    void* staged, void* stream);
+int gs_sh_bwd_flush(const GsSHParams* p, int32_t num_views, const void* const* staged,
+                    const void* const* camera_positions, const void* positions, void* grad_params, void* stream);
+
 /* ------------------------------------------------------------------ tile mapper (f32)
  * replaces tile_overlaps_kernel / generate_sort_keys_kernel / find_ranges_kernel
  * (mapper/tile_mapper.py:73-84, :112-144, :90-110) with the OBB query of

@@ -319,6 +319,83 @@ sh_bwd_dense_kernel(const __grid_constant__ GsSHParams p, const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------ deferred SH bwd
+// A multi-view batch accumulates grad_params (M, K, D) over its views; done per view that is a read-modify-write of
+// the whole 4 K D byte row per gaussian and view.  The coefficient gradient of one view is the outer product of the
+// masked colour gradient g (K floats) with the basis b(direction) (D floats), and b is a cheap function of the
+// gaussian's position and the camera centre: so a view only STAGES g (K floats per gaussian, dense over M, zero
+// where culled or clamped) and ONE flush per batch forms sum_v g_v (x) b_v in registers and adds it to the row.
+// Per view 4 K (2 V + M) + 8 V bytes instead of 8 K D M; per flush 4 K M (views + 2 D) + 12 M.
+template <int K>
+__global__ void __launch_bounds__(256)
+sh_bwd_stage_kernel(int64_t nv, const float* __restrict__ out_fwd, const int64_t* __restrict__ indexes,
+                    const float* __restrict__ grad_out, float* __restrict__ staged) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nv) return;
+  const int64_t idx = indexes[j];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float v = out_fwd[j * K + k];   // clamped forward value: strictly inside (0, 1) iff the unclamped one is
+    staged[idx * K + k] = (v > 0.f && v < 1.f) ? grad_out[j * K + k] : 0.f;
+  }
+}
+
+constexpr int kSHMaxDeferred = 16;   // GS_SH_MAX_DEFERRED_VIEWS
+struct SHFlushViews {
+  const float* staged[kSHMaxDeferred];
+  const float* cam[kSHMaxDeferred];
+};
+
+template <int K, int D>
+__global__ void __launch_bounds__(kSHDenseBlock, 4)
+sh_bwd_flush_kernel(int64_t n, int num_views, const __grid_constant__ SHFlushViews views,
+                    const float* __restrict__ positions, float* __restrict__ grad_params) {
+  constexpr int RL = K * D, R4 = RL / 4, S4 = (R4 + 1) | 1;   // odd float4 stride: conflict-free LDS.128 / STS.128
+  static_assert(RL % 4 == 0, "row length must be a multiple of 4 floats");
+  __shared__ float4 s_row[kSHDenseBlock * S4];
+  const int t = threadIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.x * kSHDenseBlock, i = i0 + t;
+  const int nrows = (int)min((int64_t)kSHDenseBlock, n - i0);
+
+  float acc[RL];
+#pragma unroll
+  for (int q = 0; q < RL; ++q) acc[q] = 0.f;
+  if (t < nrows) {
+    const float px = positions[3 * i], py = positions[3 * i + 1], pz = positions[3 * i + 2];
+    for (int v = 0; v < num_views; ++v) {
+      float g[K];
+      bool any = false;
+#pragma unroll
+      for (int k = 0; k < K; ++k) { g[k] = views.staged[v][i * K + k]; any = any || g[k] != 0.f; }
+      if (!any) continue;
+      const float* cam = views.cam[v];
+      const float dx = px - cam[0], dy = py - cam[1], dz = pz - cam[2];
+      const float inv = rsqrt_<float>(dx * dx + dy * dy + dz * dz);
+      float b[D];
+      sh_basis<float, D>(dx * inv, dy * inv, dz * inv, b);
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc[k * D + j] = fmaf(g[k], b[j], acc[k * D + j]);
+    }
+  }
+#pragma unroll
+  for (int q4 = 0; q4 < R4; ++q4)
+    s_row[t * S4 + q4] = make_float4(acc[4 * q4], acc[4 * q4 + 1], acc[4 * q4 + 2], acc[4 * q4 + 3]);
+  __syncthreads();
+  float4* dst = reinterpret_cast<float4*>(grad_params + i0 * RL);   // the block's rows are contiguous
+#pragma unroll
+  for (int m = 0; m < R4; ++m) {
+    const int q = t + m * kSHDenseBlock, r = q / R4, part = q - r * R4;
+    if (q < nrows * R4) {
+      const float4 a = s_row[r * S4 + part];
+      float4 o = dst[q];
+      o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      dst[q] = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ projection bwd
 constexpr int kPBwdBlock = 128;
 
@@ -624,6 +701,54 @@ int gs_sh_bwd(const GsSHParams* p, const void* params, const void* positions, co
                                                  grad_params, grad_positions, grad_camera_pos, st)
                             : sh_dispatch<double>(true, p, params, positions, indexes, camera_pos, grad_out,
                                                   grad_params, grad_positions, grad_camera_pos, st);
+}
+
+int gs_sh_bwd_stage(const GsSHParams* p, const void* forward_out, const int64_t* indexes, const void* grad_out,
+                    void* staged, void* stream) {
+  int rc = check_sh(p, "gs_sh_bwd_stage");
+  if (rc != GS_OK) return rc;
+  if (p->dtype != GS_F32 || p->num_channels != 3) {
+    set_error("gs_sh_bwd_stage: f32 and K = 3 only");
+    return GS_ERR_UNSUPPORTED;
+  }
+  GS_CHECK_ARG(staged != nullptr, "gs_sh_bwd_stage: null staging buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->num_indexes < p->num_points)   // culled gaussians stage zeros
+    GS_CUDA(cudaMemsetAsync(staged, 0, (size_t)p->num_points * 3 * sizeof(float), st));
+  if (p->num_indexes == 0) return GS_OK;
+  GS_CHECK_ARG(forward_out && indexes && grad_out, "gs_sh_bwd_stage: null tensor");
+  sh_bwd_stage_kernel<3><<<(unsigned)ceil_div(p->num_indexes, 256), 256, 0, st>>>(
+      p->num_indexes, (const float*)forward_out, indexes, (const float*)grad_out, (float*)staged);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+int gs_sh_bwd_flush(const GsSHParams* p, int32_t num_views, const void* const* staged,
+                    const void* const* camera_positions, const void* positions, void* grad_params, void* stream) {
+  GS_CHECK_ARG(p != nullptr, "gs_sh_bwd_flush: null params");
+  if (p->dtype != GS_F32 || p->num_channels != 3 || (p->num_coeffs != 16 && p->num_coeffs != 4)) {
+    set_error("gs_sh_bwd_flush: f32, K = 3 and D in {4, 16} only");
+    return GS_ERR_UNSUPPORTED;
+  }
+  GS_CHECK_ARG(num_views >= 0 && num_views <= kSHMaxDeferred, "gs_sh_bwd_flush: at most 16 views per flush");
+  if (num_views == 0 || p->num_points == 0) return GS_OK;
+  GS_CHECK_ARG(staged && camera_positions && positions && grad_params, "gs_sh_bwd_flush: null tensor");
+  SHFlushViews views;
+  for (int v = 0; v < kSHMaxDeferred; ++v) {
+    views.staged[v] = v < num_views ? (const float*)staged[v] : nullptr;
+    views.cam[v] = v < num_views ? (const float*)camera_positions[v] : nullptr;
+    GS_CHECK_ARG(v >= num_views || (views.staged[v] && views.cam[v]), "gs_sh_bwd_flush: null view");
+  }
+  const unsigned blocks = (unsigned)ceil_div(p->num_points, kSHDenseBlock);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->num_coeffs == 16)
+    sh_bwd_flush_kernel<3, 16><<<blocks, kSHDenseBlock, 0, st>>>(p->num_points, num_views, views,
+                                                                  (const float*)positions, (float*)grad_params);
+  else
+    sh_bwd_flush_kernel<3, 4><<<blocks, kSHDenseBlock, 0, st>>>(p->num_points, num_views, views,
+                                                                 (const float*)positions, (float*)grad_params);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
 }
 
 int gs_project_bwd(const GsProjectParams* p, int64_t num_visible, const void* position, const void* log_scaling,

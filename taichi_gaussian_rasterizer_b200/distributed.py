@@ -39,21 +39,41 @@ class GradientBucket:
     self.flat.zero_()
 
   @contextmanager
-  def fused_accumulation(self):
+  def fused_accumulation(self, defer_sh: bool = True):
     """Inside this context the spherical-harmonics backward and the projection backward add their gradients straight
     into the bucket (in the kernel) instead of materialising dense tensors for autograd to add: per view that removes
     a read-modify-write pass over every gradient (576 MB of SH + 132 MB of geometry at 3 M gaussians) and the zero
     fill of the culled rows.  Results are the same sums; parameters the kernels cannot serve this way (other
-    dtypes, features used without SH) keep the normal autograd accumulation."""
+    dtypes, features used without SH) keep the normal autograd accumulation.
+
+    ``defer_sh``: the SH coefficient gradient (N, 3, D) of the batch is formed ONCE, by ``flush()`` (called on exit and
+    by ``all_reduce``): each view only stages its masked colour gradient (N, 3) and the flush adds
+    sum_v staged_v (x) basis(position - camera_v) — one pass over the coefficient rows per batch (or per 16 views)
+    instead of one read-modify-write pass per view (grad_sinks.DeferredSH).  Anything that reads the SH gradient
+    inside the context (an optimizer step, say) must call ``flush()`` first."""
     from . import grad_sinks
     served = [p for p in self.params if p.is_cuda and p.grad is not None]
+    deferred = [p for p in served if defer_sh and p.dtype == torch.float32 and p.ndim == 3 and p.shape[1] == 3
+                and p.shape[2] in (4, 16)]
     for p in served:
       grad_sinks.register_grad_sink(p, p.grad)
+    for p in deferred:
+      grad_sinks.register_deferred_sh(p, p.grad)
     try:
       yield self
     finally:
+      for p in deferred:
+        grad_sinks.unregister_deferred_sh(p)   # flushes
       for p in served:
         grad_sinks.unregister_grad_sink(p)
+
+  def flush(self):
+    """Add the pending deferred SH gradients (fused_accumulation(defer_sh=True)) to the bucket."""
+    from . import grad_sinks
+    for p in self.params:
+      d = grad_sinks.deferred_sh(p)
+      if d is not None:
+        d.flush()
 
   @property
   def nbytes(self) -> int:
@@ -61,6 +81,7 @@ class GradientBucket:
 
   def all_reduce(self, group=None, async_op: bool = False):
     """Sum the bucket over ranks (no-op without an initialised process group / single rank)."""
+    self.flush()
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
       return None
     return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)

@@ -21,3 +21,66 @@ def unregister_grad_sink(param: torch.Tensor):
 
 def grad_sink(param: torch.Tensor) -> Optional[torch.Tensor]:
   return _sinks.get(param.data_ptr())
+
+
+# ---------------------------------------------------------------------------------------------- deferred SH gradient
+class DeferredSH:
+  """Pending spherical-harmonics coefficient gradients of a multi-view batch (csrc/point_kernels.cu, "deferred SH
+  bwd"): every view stages its masked colour gradient (N, 3) with gs_sh_bwd_stage; ``flush`` adds
+  sum_v staged_v (x) basis(position - camera_v) to the sink with ONE pass over the (N, 3, D) rows instead of one
+  read-modify-write pass per view.  Flushes by itself after GS_SH_MAX_DEFERRED_VIEWS views."""
+  MAX_VIEWS = 16
+
+  def __init__(self, sink: torch.Tensor):
+    self.sink = sink
+    self.pending = []      # (staged (N,3), camera_pos (3,))
+    self.points = None     # (N,3) positions shared by the pending views
+
+  def add(self, staged: torch.Tensor, camera_pos: torch.Tensor, points: torch.Tensor):
+    if self.points is not None and (self.points.data_ptr() != points.data_ptr() or self.points.shape != points.shape):
+      self.flush()
+    self.points = points
+    self.pending.append((staged, camera_pos))
+    if len(self.pending) >= self.MAX_VIEWS:
+      self.flush()
+
+  def flush(self):
+    if not self.pending:
+      self.points = None
+      return
+    import ctypes
+    from . import _native as N
+    n, k, d = self.sink.shape
+    nv = len(self.pending)
+    p = N.GsSHParams(N.dtype_code(self.sink.dtype), k, d, 1, n, 0, 1, 1)
+    arr = ctypes.c_void_p * nv
+    staged = arr(*[t.data_ptr() for t, _ in self.pending])
+    cams = arr(*[c.data_ptr() for _, c in self.pending])
+    N.call("gs_sh_bwd_flush", ctypes.byref(p), ctypes.c_int32(nv), staged, cams, N.ptr(self.points), N.ptr(self.sink),
+           N.stream_ptr(self.sink.device))
+    self.pending = []
+    self.points = None
+
+
+_deferred = {}
+
+
+def register_deferred_sh(param: torch.Tensor, sink: torch.Tensor) -> DeferredSH:
+  d = DeferredSH(sink)
+  _deferred[param.data_ptr()] = d
+  return d
+
+
+def unregister_deferred_sh(param: torch.Tensor):
+  d = _deferred.pop(param.data_ptr(), None)
+  if d is not None:
+    d.flush()
+
+
+def deferred_sh(param: torch.Tensor) -> Optional[DeferredSH]:
+  return _deferred.get(param.data_ptr())
+
+
+def flush_deferred():
+  for d in list(_deferred.values()):
+    d.flush()

@@ -12,7 +12,7 @@ import torch
 from beartype import beartype
 
 from . import _native as N
-from .grad_sinks import grad_sink, register_grad_sink, unregister_grad_sink  # noqa: F401  (re-exported)
+from .grad_sinks import deferred_sh, grad_sink, register_grad_sink, unregister_grad_sink  # noqa: F401  (re-exported)
 
 
 def check_sh_degree(sh_features):
@@ -55,6 +55,16 @@ class _SHFunction(torch.autograd.Function):
     # mask from the forward output and never reads the coefficient rows
     from_out = int(dense and need[0] and not need[1] and not need[3])
     coeffs = out if from_out else params
+    deferred = deferred_sh(params) if (sink is not None and dense and from_out) else None
+    if deferred is not None:
+      # deferred accumulation (grad_sinks.DeferredSH): this view only stages its masked colour gradient, the batch's
+      # flush forms the coefficient rows once
+      staged = torch.empty((params.shape[0], params.shape[1]), dtype=params.dtype, device=params.device)
+      p = N.GsSHParams(ctx.p.dtype, ctx.p.num_channels, ctx.p.num_coeffs, 1, ctx.p.num_points, ctx.p.num_indexes, 1, 1)
+      N.call("gs_sh_bwd_stage", ctypes.byref(p), N.ptr(out), N.ptr(indexes), N.ptr(doutput.contiguous()), N.ptr(staged),
+             N.stream_ptr(params.device))
+      deferred.add(staged, camera_pos.detach().contiguous(), points.detach())
+      return None, None, None, None, None, None
     if sink is not None and dense:
       # fused accumulation: the kernel adds into the sink, autograd gets no gradient for `params`
       p = N.GsSHParams(ctx.p.dtype, ctx.p.num_channels, ctx.p.num_coeffs, 1, ctx.p.num_points, ctx.p.num_indexes, 1,

@@ -96,37 +96,42 @@ def test_median_depth_and_depth16(cuda_device):
   assert out.ndc_median_depth.shape == (192, 256)
 
 
-@pytest.mark.parametrize("n,margin", [(5000, 0.0), (5000, 2.0)])   # nearly all visible / most gaussians culled
-def test_fused_gradient_accumulation_matches_autograd(cuda_device, n, margin):
-  """GradientBucket.fused_accumulation(): the SH backward adds into the bucket inside the kernel; after several
-  views the bucket must equal plain autograd accumulation (same sums, different rounding order)."""
+@pytest.mark.parametrize("defer_sh", [True, False])
+@pytest.mark.parametrize("n,margin,views,sh_degree", [(5000, 0.0, 3, 3), (5000, 2.0, 3, 3), (3000, 0.5, 19, 1)])
+def test_fused_gradient_accumulation_matches_autograd(cuda_device, n, margin, views, sh_degree, defer_sh):
+  """GradientBucket.fused_accumulation(): the SH / projection backward add into the bucket inside the kernel, and
+  with defer_sh the SH coefficient gradient of the batch is formed once by the flush (per view only the masked colour
+  gradient is staged; 19 views cross the 16 view auto-flush).  After the batch the bucket must equal plain autograd
+  accumulation (same sums, different rounding order).  Nearly all visible / most gaussians culled / SH degree 1."""
   from taichi_gaussian_rasterizer_b200.distributed import GradientBucket
   from taichi_gaussian_rasterizer_b200.torch_lib.projection import join_rt, quat_to_mat
   cfg = RasterConfig()
-  g, cam = scene3d(11, n, image_size=(256, 192), scale_factor=0.7, sh_degree=3, margin=margin)
+  g, cam = scene3d(11, n, image_size=(256, 192), scale_factor=0.7, sh_degree=sh_degree, margin=margin)
   cams = [cam.to(device=cuda_device)]
-  for k in range(2):
-    q = torch.tensor([0.01 * (k + 1), -0.02, 0.005, 1.0])
-    cams.append(cam.transformed(join_rt(quat_to_mat(q / q.norm()), torch.tensor([0.02, 0.0, -0.01]))).to(device=cuda_device))
+  for k in range(views - 1):
+    q = torch.tensor([0.01 * (k % 5 + 1), -0.02 + 0.003 * k, 0.005, 1.0])
+    cams.append(cam.transformed(join_rt(quat_to_mat(q / q.norm()), torch.tensor([0.02, 0.001 * k, -0.01]))).to(device=cuda_device))
 
   def run(fused):
     gd = g.to(device=cuda_device)
     gd.requires_grad_(True)
     params = [gd.position, gd.log_scaling, gd.rotation, gd.alpha_logit, gd.feature]
     bucket = GradientBucket(params)
-    ctx = bucket.fused_accumulation() if fused else __import__("contextlib").nullcontext()
+    ctx = bucket.fused_accumulation(defer_sh=defer_sh) if fused else __import__("contextlib").nullcontext()
     with ctx:
-      for c in cams:
+      for i, c in enumerate(cams):
         out = render_gaussians(gd, c, cfg, use_sh=True)
         out.image.square().mean().backward()
+        if fused and i == 1:
+          bucket.flush()   # an early flush (e.g. before an optimizer step) must not lose or double anything
     assert gd.feature.grad.data_ptr() >= bucket.flat.data_ptr()   # still views of the bucket
     return bucket.flat.clone(), gd.feature.grad.clone()
 
   flat_a, feat_a = run(False)
   flat_b, feat_b = run(True)
   assert feat_a.abs().sum() > 0
-  assert rel_l2(feat_b, feat_a) < 1e-6
-  assert rel_l2(flat_b, flat_a) < 1e-6
+  assert rel_l2(feat_b, feat_a) < 2e-6
+  assert rel_l2(flat_b, flat_a) < 2e-6
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
