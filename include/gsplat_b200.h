@@ -122,7 +122,9 @@ int gs_sh_bwd(const GsSHParams* p, const void* params, const void* positions,
  *                    (forward_out (V,K), the clamped output of gs_sh_fwd) sits on the clamp and where culled;
  *   gs_sh_bwd_flush: grad_params (M,K,D) += sum over the num_views staged views of staged_v (x) basis(positions -
  *                    camera_positions[v]); `staged` / `camera_positions` are HOST arrays of num_views device pointers
- *                    ((M,K) and (3,) floats), num_views <= GS_SH_MAX_DEFERRED_VIEWS.
+ *                    ((M,K) and (3,) floats), num_views <= GS_SH_MAX_DEFERRED_VIEWS.  With p->accumulate_params = 0
+ *                    the rows are OVERWRITTEN with the sum (zeroed when num_views = 0): the first flush of a batch
+ *                    then needs neither a zero fill of grad_params before nor a read of it.
  * p->num_points = M, p->num_indexes = V (stage only). */
 #define GS_SH_MAX_DEFERRED_VIEWS 16
 int gs_sh_bwd_stage(const GsSHParams* p, const void* forward_out, const int64_t* indexes, const void* grad_out,

@@ -346,7 +346,8 @@ struct SHFlushViews {
   const float* cam[kSHMaxDeferred];
 };
 
-template <int K, int D>
+// OVERWRITE: grad_params = the batch's sum (the caller knows the rows hold nothing yet: no zero fill before, no read here)
+template <int K, int D, bool OVERWRITE>
 __global__ void __launch_bounds__(kSHDenseBlock, 4)
 sh_bwd_flush_kernel(int64_t n, int num_views, const __grid_constant__ SHFlushViews views,
                     const float* __restrict__ positions, float* __restrict__ grad_params) {
@@ -388,10 +389,12 @@ sh_bwd_flush_kernel(int64_t n, int num_views, const __grid_constant__ SHFlushVie
   for (int m = 0; m < R4; ++m) {
     const int q = t + m * kSHDenseBlock, r = q / R4, part = q - r * R4;
     if (q < nrows * R4) {
-      const float4 a = s_row[r * S4 + part];
-      float4 o = dst[q];
-      o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-      dst[q] = o;
+      float4 a = s_row[r * S4 + part];
+      if (!OVERWRITE) {
+        const float4 o = dst[q];
+        a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+      }
+      dst[q] = a;
     }
   }
 }
@@ -731,7 +734,16 @@ int gs_sh_bwd_flush(const GsSHParams* p, int32_t num_views, const void* const* s
     return GS_ERR_UNSUPPORTED;
   }
   GS_CHECK_ARG(num_views >= 0 && num_views <= kSHMaxDeferred, "gs_sh_bwd_flush: at most 16 views per flush");
-  if (num_views == 0 || p->num_points == 0) return GS_OK;
+  const bool overwrite = p->accumulate_params == 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->num_points == 0) return GS_OK;
+  if (num_views == 0) {
+    if (overwrite) {
+      GS_CHECK_ARG(grad_params != nullptr, "gs_sh_bwd_flush: null tensor");
+      GS_CUDA(cudaMemsetAsync(grad_params, 0, (size_t)p->num_points * 3 * p->num_coeffs * sizeof(float), st));
+    }
+    return GS_OK;
+  }
   GS_CHECK_ARG(staged && camera_positions && positions && grad_params, "gs_sh_bwd_flush: null tensor");
   SHFlushViews views;
   for (int v = 0; v < kSHMaxDeferred; ++v) {
@@ -740,13 +752,12 @@ int gs_sh_bwd_flush(const GsSHParams* p, int32_t num_views, const void* const* s
     GS_CHECK_ARG(v >= num_views || (views.staged[v] && views.cam[v]), "gs_sh_bwd_flush: null view");
   }
   const unsigned blocks = (unsigned)ceil_div(p->num_points, kSHDenseBlock);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (p->num_coeffs == 16)
-    sh_bwd_flush_kernel<3, 16><<<blocks, kSHDenseBlock, 0, st>>>(p->num_points, num_views, views,
-                                                                  (const float*)positions, (float*)grad_params);
-  else
-    sh_bwd_flush_kernel<3, 4><<<blocks, kSHDenseBlock, 0, st>>>(p->num_points, num_views, views,
-                                                                 (const float*)positions, (float*)grad_params);
+#define GS_SH_FLUSH(DD, OW)                                                                                        \
+  sh_bwd_flush_kernel<3, DD, OW><<<blocks, kSHDenseBlock, 0, st>>>(p->num_points, num_views, views,               \
+                                                                    (const float*)positions, (float*)grad_params)
+  if (p->num_coeffs == 16) { if (overwrite) GS_SH_FLUSH(16, true); else GS_SH_FLUSH(16, false); }
+  else { if (overwrite) GS_SH_FLUSH(4, true); else GS_SH_FLUSH(4, false); }
+#undef GS_SH_FLUSH
   GS_LAUNCH_CHECK();
   return GS_OK;
 }

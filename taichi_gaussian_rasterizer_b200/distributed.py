@@ -36,7 +36,21 @@ class GradientBucket:
       off += n
 
   def zero_(self):
-    self.flat.zero_()
+    """Zero the gradients.  Inside ``fused_accumulation(defer_sh=True)`` the SH coefficient slices are not touched:
+    their deferred state is marked clean and the batch's first flush overwrites them (no 4 K D bytes per gaussian of
+    zero fill, no read of the rows by that flush)."""
+    from . import grad_sinks
+    clean = [(p, grad_sinks.deferred_sh(p)) for p in self.params]
+    clean = [(p, d) for p, d in clean if d is not None]
+    if not clean:
+      self.flat.zero_()
+      return
+    skip = {p.grad.data_ptr() for p, _ in clean}
+    for p in self.params:
+      if p.grad.data_ptr() not in skip:
+        p.grad.zero_()
+    for _, d in clean:
+      d.mark_clean()
 
   @contextmanager
   def fused_accumulation(self, defer_sh: bool = True):

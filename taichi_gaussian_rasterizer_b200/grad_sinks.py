@@ -35,6 +35,14 @@ class DeferredSH:
     self.sink = sink
     self.pending = []      # (staged (N,3), camera_pos (3,))
     self.points = None     # (N,3) positions shared by the pending views
+    self.overwrite_next = False   # the sink holds nothing yet (mark_clean): the next flush writes instead of adding
+
+  def mark_clean(self):
+    """The caller declares the sink's content void (start of a batch): pending views are dropped and the next flush
+    overwrites the rows, so nobody has to zero them (GradientBucket.zero_)."""
+    self.pending = []
+    self.points = None
+    self.overwrite_next = True
 
   def add(self, staged: torch.Tensor, camera_pos: torch.Tensor, points: torch.Tensor):
     if self.points is not None and (self.points.data_ptr() != points.data_ptr() or self.points.shape != points.shape):
@@ -45,14 +53,19 @@ class DeferredSH:
       self.flush()
 
   def flush(self):
-    if not self.pending:
+    if not self.pending and not self.overwrite_next:
       self.points = None
       return
     import ctypes
     from . import _native as N
     n, k, d = self.sink.shape
     nv = len(self.pending)
-    p = N.GsSHParams(N.dtype_code(self.sink.dtype), k, d, 1, n, 0, 1, 1)
+    if nv == 0:   # clean sink, nothing staged: the rows become zeros
+      self.sink.zero_()
+      self.overwrite_next = False
+      return
+    p = N.GsSHParams(N.dtype_code(self.sink.dtype), k, d, 1, n, 0, 0 if self.overwrite_next else 1, 1)
+    self.overwrite_next = False
     arr = ctypes.c_void_p * nv
     staged = arr(*[t.data_ptr() for t, _ in self.pending])
     cams = arr(*[c.data_ptr() for _, c in self.pending])

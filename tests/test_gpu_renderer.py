@@ -119,6 +119,8 @@ def test_fused_gradient_accumulation_matches_autograd(cuda_device, n, margin, vi
     bucket = GradientBucket(params)
     ctx = bucket.fused_accumulation(defer_sh=defer_sh) if fused else __import__("contextlib").nullcontext()
     with ctx:
+      bucket.flat.fill_(7.0)   # stale content: zero_() inside the context must void it (deferred slices: overwritten
+      bucket.zero_()           # by the first flush instead of zero-filled)
       for i, c in enumerate(cams):
         out = render_gaussians(gd, c, cfg, use_sh=True)
         out.image.square().mean().backward()
@@ -157,3 +159,17 @@ def test_camera_position_kernel(cuda_device, dtype):
     pos = camd.camera_position
     assert pos.requires_grad
     assert rel_l2(pos.detach().cpu(), ref) < tol
+
+
+def test_deferred_sh_clean_bucket_without_views(cuda_device):
+  """zero_() inside fused_accumulation(defer_sh=True) only marks the SH slice clean; leaving the context without a
+  single staged view must still leave zeros there."""
+  from taichi_gaussian_rasterizer_b200.distributed import GradientBucket
+  g, _ = scene3d(5, 500, image_size=(64, 48), sh_degree=3)
+  gd = g.to(device=cuda_device)
+  gd.requires_grad_(True)
+  bucket = GradientBucket([gd.position, gd.feature])
+  with bucket.fused_accumulation():
+    bucket.flat.fill_(3.0)
+    bucket.zero_()
+  assert float(bucket.flat.abs().max()) == 0.0
