@@ -117,12 +117,13 @@ KERNELS_PER_CALL = {  # kernels launched by each entry point (memsets not counte
   "gs_tile_emit_keys": 1, "gs_find_ranges": 1, "gs_raster_fwd": 2, "gs_raster_bwd": 2,
   "gs_depth_keys": 1, "gs_tile_count_perm": 1, "gs_tile_emit_tiles": 1, "gs_find_ranges_tiles": 1,
   "gs_camera_position": 1, "gs_sh_fwd_counted": 1, "gs_sh_bwd_stage": 1, "gs_sh_bwd_flush": 1,
+  "gs_sh_fwd_views": 1, "gs_gather_rows_counted": 1, "gs_depth_keys_counted": 1,
 }
 
 
 def run_ours(args):
   import torch.distributed as dist
-  from taichi_gaussian_rasterizer_b200 import RasterConfig, _native, render_gaussians
+  from taichi_gaussian_rasterizer_b200 import RasterConfig, _native, evaluate_sh_views, render_gaussians
   from taichi_gaussian_rasterizer_b200.distributed import GradientBucket
   from taichi_gaussian_rasterizer_b200.perspective import CameraParams
 
@@ -178,32 +179,45 @@ def run_ours(args):
                  pose=torch.empty(4, 4, device=device), ready=torch.cuda.Event(), free=torch.cuda.Event())
             for _ in range(views)]
 
+  poses_ready = torch.cuda.Event()
+
   def _step(from_host: bool):
     compute = torch.cuda.current_stream(device)
     if from_host:
-      # this step's inputs (camera + target image of every view) go host -> device on a side stream, so the copy of
-      # view i+1 overlaps the rendering of view i; the compute stream waits on each view's event before using it
+      # this step's inputs (camera + target image of every view) go host -> device on a side stream: the (tiny) camera
+      # blocks of all views first, then the target images, so the copy of view i+1's image overlaps the rendering of
+      # view i; the compute stream waits on each event before using what it guards
       with torch.cuda.stream(copy_stream):
         for i in range(views):
           st = staged[i]
           copy_stream.wait_event(st["free"])      # the previous step has finished reading this slot
           st["proj"].copy_(host_proj[i], non_blocking=True)
           st["pose"].copy_(host_pose[i], non_blocking=True)
+        poses_ready.record(copy_stream)
+        for i in range(views):
+          st = staged[i]
           st["target"].copy_(host_targets[i], non_blocking=True)
           st["ready"].record(copy_stream)
+      compute.wait_event(poses_ready)
+      cams = [CameraParams(projection=st["proj"], T_camera_world=st["pose"], near_plane=my_cameras[i].near_plane,
+                           far_plane=my_cameras[i].far_plane, image_size=my_cameras[i].image_size)
+              for i, st in enumerate(staged)]
+    else:
+      cams = dev_cams
     bucket.zero_()
     total = torch.zeros((), device=device)
+    # the batch's cameras are known up front: the SH coefficients are read once for all views of the step
+    colors = (evaluate_sh_views(gaussians.feature, gaussians.position, [c.camera_position for c in cams])
+              if args.batched_sh else [None] * views)
     for i in range(views):
+      cam = cams[i]
       if from_host:
         st = staged[i]
         compute.wait_event(st["ready"])
-        cam = CameraParams(projection=st["proj"], T_camera_world=st["pose"],
-                           near_plane=my_cameras[i].near_plane, far_plane=my_cameras[i].far_plane,
-                           image_size=my_cameras[i].image_size)
         target = st["target"]
       else:
-        cam, target = dev_cams[i], dev_targets[i]
-      rendering = render_gaussians(gaussians, cam, config, use_sh=True)
+        target = dev_targets[i]
+      rendering = render_gaussians(gaussians, cam, config, use_sh=True, sh_colors=colors[i])
       loss = torch.nn.functional.l1_loss(rendering.image, target)   # mean |image - target|, one fused ATen op each way
       loss.backward()
       total += loss.detach()
@@ -295,10 +309,11 @@ def run_ours(args):
   fwd_calls, fwd_ms = stage.get("gs_raster_fwd", (0, 0.0))
   stage_ms = {k: round(v[1] / args.steps / views, 4) for k, v in sorted(stage.items())}
   launches = sum(KERNELS_PER_CALL.get(k, 0) * v[0] for k, v in stage.items())
-  # two sorts per frame (depth keys: 32 bits; tile ids: tile_bits), each = histogram + scan + one kernel per 8 bit pass
-  sort_calls = stage.get("gs_radix_sort_pairs", (0, 0.0))[0]
+  # two sorts per frame, each = histogram + scan + one kernel per 8 bit pass: the depth keys (32 bits, enqueued with
+  # the count still on the device: gs_radix_sort_pairs_counted) and the tile ids (tile_bits)
   tile_bits = max(1, (int(ranges.shape[0] * ranges.shape[1]) - 1).bit_length())
-  launches += (sort_calls // 2) * ((2 + 4) + (2 + -(-tile_bits // 8)))
+  launches += stage.get("gs_radix_sort_pairs_counted", (0, 0.0))[0] * (2 + 4)
+  launches += stage.get("gs_radix_sort_pairs", (0, 0.0))[0] * (2 + -(-tile_bits // 8))
   launches = launches // max(args.steps, 1)
 
   # HBM rooflines of the bandwidth-bound stages: SURVEY.md §8(d) algorithmic bytes per launch over the live CUDA-event
@@ -312,11 +327,16 @@ def run_ours(args):
     "gs_sh_bwd": V * (32 + 12) + 4 * CD * n + 4 * CD * V,        # coefficient rows not read; bucket rows read + written
     # deferred SH gradient: per view the masked colour gradient is staged (V x (out, grad, index) in, (N,3) out) ...
     "gs_sh_bwd_stage": V * (12 + 12 + 8) + 12 * n,
+    # batched SH colours: coefficient rows + positions read once per step, (N,3) written per view (per frame share);
+    # a view gathers its visible rows
+    "gs_sh_fwd_views": (n * (4 * CD + 12 + 12 * views)) // views,
+    "gs_gather_rows_counted": V * (8 + 12 + 12),
     # ... and one flush per step reads the staged views + positions and adds to the coefficient rows (per frame share)
     "gs_sh_bwd_flush": (n * (12 * views + 12 + 2 * 4 * CD)) // views,
     "gs_full_cumsum": 8 * V,
     "gs_tile_emit_tiles": 20 * V + 8 * K,
-    "gs_radix_sort_pairs": (4 * V + 16 * V * 4) + (4 * K + 16 * K * passes_k),
+    "gs_radix_sort_pairs_counted": 4 * V + 16 * V * 4,          # depth keys: histogram read + 4 passes over 8 B pairs
+    "gs_radix_sort_pairs": 4 * K + 16 * K * passes_k,            # tile ids
     "gs_find_ranges_tiles": 4 * K + 8 * T_tiles,
   }
   hbm_stages = {}
@@ -339,7 +359,9 @@ def run_ours(args):
                "V_in_view": V, "K_overlaps": K, "K_per_tile_mean": float(counts.mean()),
                "K_per_tile_max": int(counts.max()), "scale_factor": W["scale_factor"],
                "l2_policy": "inputs larger than L2 (708 MB of gaussians per view)", "gaussian_order": "morton" if args.morton else "as generated (random)",
-               "emulate_stale_tail": True, "forward_exit_transmittance": 0.0},
+               "emulate_stale_tail": True, "forward_exit_transmittance": 0.0,
+               "sh": "colours of all views of a step evaluated in one pass over the coefficients, coefficient gradient "
+                     "formed once per step" if args.batched_sh else "evaluated per view, coefficient gradient formed once per step"},
     "e2e": {"value": e2e, "unit": "gaussian*pixel/s", "ms_per_step": ms_e2e / args.steps,
             "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
     "gpu_launches": launches,
@@ -482,6 +504,8 @@ def main():
   ap.add_argument("--num-gaussians", type=int, default=0)
   ap.add_argument("--image-size", type=int, nargs=2, default=None)
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--per-view-sh", dest="batched_sh", action="store_false",
+                  help="evaluate the SH colours per view (evaluate_sh_at) instead of once per step for all views")
   ap.add_argument("--morton", action="store_true", help="store the gaussians in Morton order of their positions")
   ap.add_argument("--cpu-budget", type=float, default=12.0)
   args = ap.parse_args()

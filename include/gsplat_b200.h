@@ -132,6 +132,18 @@ int gs_sh_bwd_stage(const GsSHParams* p, const void* forward_out, const int64_t*
 int gs_sh_bwd_flush(const GsSHParams* p, int32_t num_views, const void* const* staged,
                     const void* const* camera_positions, const void* positions, void* grad_params, void* stream);
 
+/* Batched evaluation for the views of a multi-view batch (f32, K = 3, D in {4, 16}): evaluate_sh_at_kernel
+ * (spherical_harmonics.py:118-134) reads the 4 K D byte coefficient row of every visible gaussian once per VIEW;
+ * gs_sh_fwd_views reads every row once per BATCH and writes one dense colour tensor (M,K) per view (outs /
+ * camera_positions: HOST arrays of num_views device pointers, num_views <= GS_SH_MAX_DEFERRED_VIEWS; same arithmetic
+ * and clamp as gs_sh_fwd).  A view then takes its visible rows with gs_gather_rows_counted: out[j] = src[indexes[j]]
+ * for j < *count_dev (count_dev NULL: j < capacity), rows of row_floats = 3 floats — the count may still be on the
+ * device, as for gs_sh_fwd_counted. */
+int gs_sh_fwd_views(const GsSHParams* p, int32_t num_views, const void* params, const void* positions,
+                    const void* const* camera_positions, void* const* outs, void* stream);
+int gs_gather_rows_counted(int64_t capacity, int32_t row_floats, const void* src, const int64_t* indexes,
+                           const int32_t* count_dev, void* out, void* stream);
+
 /* ------------------------------------------------------------------ tile mapper (f32)
  * replaces tile_overlaps_kernel / generate_sort_keys_kernel / find_ranges_kernel
  * (mapper/tile_mapper.py:73-84, :112-144, :90-110) with the OBB query of
@@ -165,6 +177,11 @@ size_t gs_radix_sort_pairs_workspace_bytes(int64_t n, int32_t key_bytes, int32_t
 int gs_radix_sort_pairs(int64_t n, int32_t key_bytes, const void* keys_in, const int32_t* values_in,
                         void* keys_out, int32_t* values_out, int32_t begin_bit, int32_t end_bit,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* Same for the first *count_dev of `capacity` pairs (count on the device; workspace sized for `capacity`; output rows
+ * >= *count_dev are left untouched). */
+int gs_radix_sort_pairs_counted(int64_t capacity, const int32_t* count_dev, int32_t key_bytes, const void* keys_in,
+                                const int32_t* values_in, void* keys_out, int32_t* values_out, int32_t begin_bit,
+                                int32_t end_bit, void* workspace, size_t workspace_bytes, void* stream);
 
 /* sorted keys (K) -> tile_ranges (T,2) int32, fully written ([0,0] for empty tiles) */
 int gs_find_ranges(const GsTileParams* p, int64_t num_overlaps, const void* sorted_keys,
@@ -180,6 +197,11 @@ int gs_find_ranges(const GsTileParams* p, int64_t num_overlaps, const void* sort
  * sequence as torch's eager CUDA kernels; near_plane <= 0: `depth` already is the sort depth. */
 int gs_depth_keys(const GsTileParams* p, const float* depth, double near_plane, double far_plane,
                   uint32_t* keys, int32_t* values, void* stream);
+/* Same with the number of gaussians still on the device (count_dev, e.g. num_visible of gs_project_fwd):
+ * p->num_points is the CAPACITY of depth / keys / values, rows >= *count_dev are left untouched.  Together with
+ * gs_radix_sort_pairs_counted the depth ordering of a frame can be enqueued before the host reads the visible count. */
+int gs_depth_keys_counted(const GsTileParams* p, const float* depth, double near_plane, double far_plane,
+                          const int32_t* count_dev, uint32_t* keys, int32_t* values, void* stream);
 /* tile_masks (V) uint64, optional (NULL = none) in both calls: the count pass records per slot which tiles of a span of
  * at most 32 tiles passed the test, the emit pass then expands those bits instead of repeating the OBB query and the
  * tile tests (spans above 32 tiles are flagged and recomputed).  Same outputs either way. */

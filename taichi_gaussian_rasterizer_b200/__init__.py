@@ -14,7 +14,7 @@ from .data_types import Gaussians2D, Gaussians3D, RasterConfig
 from .perspective import CameraParams
 from . import perspective
 # operators, in pipeline order
-from .spherical_harmonics import evaluate_sh_at
+from .spherical_harmonics import evaluate_sh_at, evaluate_sh_views
 from .mapper.tile_mapper import map_to_tiles, pad_to_tile
 from . import cuda_lib
 from .rasterizer import rasterize, rasterize_with_tiles, set_raster_options
@@ -26,7 +26,7 @@ from .taichi_queue import TaichiQueue, taichi_queue
 
 __all__ = [
   "Gaussians2D", "Gaussians3D", "RasterConfig", "CameraParams", "perspective",
-  "evaluate_sh_at", "map_to_tiles", "pad_to_tile", "cuda_lib", "rasterize", "rasterize_with_tiles",
+  "evaluate_sh_at", "evaluate_sh_views", "map_to_tiles", "pad_to_tile", "cuda_lib", "rasterize", "rasterize_with_tiles",
   "set_raster_options", "Rendering", "render_gaussians", "render_projected", "viewspace_gradient",
   "TaichiQueue", "taichi_queue",
 ]

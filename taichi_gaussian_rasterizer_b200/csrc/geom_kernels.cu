@@ -283,8 +283,9 @@ __global__ void find_ranges_kernel(int64_t n, const KeyT* __restrict__ keys, int
 // ndc_depth() on the device.  This translation unit is compiled with -fmad=false.
 __global__ void depth_keys_kernel(int64_t n, int use_depth16, int to_ndc, float inv_far, float inv_den,
                                   const float* __restrict__ depth, uint32_t* __restrict__ keys,
-                                  int32_t* __restrict__ values) {
+                                  int32_t* __restrict__ values, const int32_t* __restrict__ n_dev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, (int64_t)*n_dev);   // counted variant: n is the capacity
   if (i >= n) return;
   float d = depth[i];
   if (to_ndc) d = 1.0f - ((1.0f / d) - inv_far) * inv_den;
@@ -442,8 +443,8 @@ int gs_camera_position(int32_t dtype, const void* T_camera_world, void* position
 
 // ---- depth-first tile mapping (same outputs as count -> emit_keys -> sort on 32 + tile bits -> find_ranges):
 // sort the V gaussians by depth key once, visit them in that order, then a stable sort on the tile id only.
-int gs_depth_keys(const GsTileParams* p, const float* depth, double near_plane, double far_plane, uint32_t* keys,
-                  int32_t* values, void* stream) {
+static int depth_keys_entry(const GsTileParams* p, const float* depth, double near_plane, double far_plane,
+                            const int32_t* count_dev, uint32_t* keys, int32_t* values, void* stream) {
   int rc = check_tile_params(p, "gs_depth_keys");
   if (rc != GS_OK) return rc;
   if (p->num_points == 0) return GS_OK;
@@ -457,9 +458,20 @@ int gs_depth_keys(const GsTileParams* p, const float* depth, double near_plane, 
     inv_den = 1.0f / den;
   }
   depth_keys_kernel<<<(unsigned)ceil_div(p->num_points, 256), 256, 0, (cudaStream_t)stream>>>(
-      p->num_points, p->use_depth16, to_ndc ? 1 : 0, inv_far, inv_den, depth, keys, values);
+      p->num_points, p->use_depth16, to_ndc ? 1 : 0, inv_far, inv_den, depth, keys, values, count_dev);
   GS_LAUNCH_CHECK();
   return GS_OK;
+}
+
+int gs_depth_keys(const GsTileParams* p, const float* depth, double near_plane, double far_plane, uint32_t* keys,
+                  int32_t* values, void* stream) {
+  return depth_keys_entry(p, depth, near_plane, far_plane, nullptr, keys, values, stream);
+}
+
+int gs_depth_keys_counted(const GsTileParams* p, const float* depth, double near_plane, double far_plane,
+                          const int32_t* count_dev, uint32_t* keys, int32_t* values, void* stream) {
+  GS_CHECK_ARG(count_dev != nullptr, "gs_depth_keys_counted: null count");
+  return depth_keys_entry(p, depth, near_plane, far_plane, count_dev, keys, values, stream);
 }
 
 int gs_tile_count_perm(const GsTileParams* p, const float* gaussians, const int32_t* perm, int32_t* counts,

@@ -399,6 +399,61 @@ sh_bwd_flush_kernel(int64_t n, int num_views, const __grid_constant__ SHFlushVie
   }
 }
 
+// ------------------------------------------------------------------------------------------------ batched SH fwd
+// The forward counterpart of the deferred gradient: the views of a batch all read the same (M, K, D) coefficients,
+// 4 K D bytes per gaussian and view.  One pass holds a gaussian's row in registers and evaluates it for every view
+// of the batch (dense (M, K) colours per view, 4 K bytes each); a view then only gathers its visible rows.
+struct SHViewsOut {
+  float* out[kSHMaxDeferred];
+  const float* cam[kSHMaxDeferred];
+};
+
+template <int K, int D>
+__global__ void __launch_bounds__(128)
+sh_fwd_views_kernel(int64_t n, int num_views, const __grid_constant__ SHViewsOut views,
+                    const float* __restrict__ params, const float* __restrict__ positions) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float c[K * D];
+  const float4* r4 = reinterpret_cast<const float4*>(params + i * K * D);
+#pragma unroll
+  for (int q = 0; q < K * D / 4; ++q) {
+    const float4 v = __ldg(r4 + q);
+    c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+  }
+  const float px = positions[3 * i], py = positions[3 * i + 1], pz = positions[3 * i + 2];
+  for (int v = 0; v < num_views; ++v) {
+    const float* cam = views.cam[v];
+    const float dx = px - cam[0], dy = py - cam[1], dz = pz - cam[2];
+    const float inv = rsqrt_<float>(dx * dx + dy * dy + dz * dz);
+    float b[D];
+    sh_basis<float, D>(dx * inv, dy * inv, dz * inv, b);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float acc = 0.f;   // same summation order as sh_fwd_kernel (groups of four)
+#pragma unroll
+      for (int j = 0; j < D / 4; ++j)
+        acc += b[4 * j] * c[k * D + 4 * j] + b[4 * j + 1] * c[k * D + 4 * j + 1] + b[4 * j + 2] * c[k * D + 4 * j + 2] +
+               b[4 * j + 3] * c[k * D + 4 * j + 3];
+      const float val = acc + 0.5f;
+      views.out[v][i * K + k] = val < 0.f ? 0.f : (val > 1.f ? 1.f : val);
+    }
+  }
+}
+
+// out[j] = src[indexes[j]] for j < *count_dev (rows of K floats; the count is still on the device)
+template <int K>
+__global__ void __launch_bounds__(256)
+gather_rows_counted_kernel(int64_t capacity, const float* __restrict__ src, const int64_t* __restrict__ indexes,
+                           const int32_t* __restrict__ count_dev, float* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nv = count_dev ? (int64_t)*count_dev : capacity;
+  if (j >= nv || j >= capacity) return;
+  const int64_t idx = indexes[j];
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[j * K + k] = src[idx * K + k];
+}
+
 // ------------------------------------------------------------------------------------------------ projection bwd
 constexpr int kPBwdBlock = 128;
 
@@ -758,6 +813,49 @@ int gs_sh_bwd_flush(const GsSHParams* p, int32_t num_views, const void* const* s
   if (p->num_coeffs == 16) { if (overwrite) GS_SH_FLUSH(16, true); else GS_SH_FLUSH(16, false); }
   else { if (overwrite) GS_SH_FLUSH(4, true); else GS_SH_FLUSH(4, false); }
 #undef GS_SH_FLUSH
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+int gs_sh_fwd_views(const GsSHParams* p, int32_t num_views, const void* params, const void* positions,
+                    const void* const* camera_positions, void* const* outs, void* stream) {
+  GS_CHECK_ARG(p != nullptr, "gs_sh_fwd_views: null params");
+  if (p->dtype != GS_F32 || p->num_channels != 3 || (p->num_coeffs != 16 && p->num_coeffs != 4)) {
+    set_error("gs_sh_fwd_views: f32, K = 3 and D in {4, 16} only");
+    return GS_ERR_UNSUPPORTED;
+  }
+  GS_CHECK_ARG(num_views >= 0 && num_views <= kSHMaxDeferred, "gs_sh_fwd_views: at most 16 views per call");
+  if (num_views == 0 || p->num_points == 0) return GS_OK;
+  GS_CHECK_ARG(params && positions && camera_positions && outs, "gs_sh_fwd_views: null tensor");
+  SHViewsOut views;
+  for (int v = 0; v < kSHMaxDeferred; ++v) {
+    views.out[v] = v < num_views ? (float*)outs[v] : nullptr;
+    views.cam[v] = v < num_views ? (const float*)camera_positions[v] : nullptr;
+    GS_CHECK_ARG(v >= num_views || (views.out[v] && views.cam[v]), "gs_sh_fwd_views: null view");
+  }
+  const unsigned blocks = (unsigned)ceil_div(p->num_points, 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->num_coeffs == 16)
+    sh_fwd_views_kernel<3, 16><<<blocks, 128, 0, st>>>(p->num_points, num_views, views, (const float*)params,
+                                                       (const float*)positions);
+  else
+    sh_fwd_views_kernel<3, 4><<<blocks, 128, 0, st>>>(p->num_points, num_views, views, (const float*)params,
+                                                      (const float*)positions);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+int gs_gather_rows_counted(int64_t capacity, int32_t row_floats, const void* src, const int64_t* indexes,
+                           const int32_t* count_dev, void* out, void* stream) {
+  GS_CHECK_ARG(capacity >= 0, "gs_gather_rows_counted: bad capacity");
+  if (row_floats != 3) {
+    set_error("gs_gather_rows_counted: rows of 3 floats only");
+    return GS_ERR_UNSUPPORTED;
+  }
+  if (capacity == 0) return GS_OK;
+  GS_CHECK_ARG(src && indexes && out, "gs_gather_rows_counted: null tensor");
+  gather_rows_counted_kernel<3><<<(unsigned)ceil_div(capacity, 256), 256, 0, (cudaStream_t)stream>>>(
+      capacity, (const float*)src, indexes, count_dev, (float*)out);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }

@@ -92,8 +92,9 @@ __device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
 radix_histogram_kernel(int64_t n, const KeyT* __restrict__ keys, int begin_bit, int end_bit, int passes,
-                       unsigned* __restrict__ global_hist) {
+                       unsigned* __restrict__ global_hist, const int32_t* __restrict__ n_dev) {
   __shared__ unsigned h[kMaxPasses * kRadix];
+  if (n_dev) n = min(n, (int64_t)*n_dev);   // counted variant: n is the capacity, the count is on the device
   for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) h[i] = 0;
   __syncthreads();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -138,8 +139,9 @@ __global__ void __launch_bounds__(kSortBlock, 3)
 onesweep_pass_kernel(int64_t n, const KeyT* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
                      KeyT* __restrict__ keys_out, int32_t* __restrict__ vals_out, int shift, unsigned mask,
                      const unsigned* __restrict__ global_excl, unsigned* __restrict__ status,
-                     unsigned* __restrict__ ticket) {
+                     unsigned* __restrict__ ticket, const int32_t* __restrict__ n_dev) {
   constexpr int ITEMS = SortCfg<KeyT>::kItems;
+  if (n_dev) n = min(n, (int64_t)*n_dev);   // counted variant: the grid covers the capacity
   constexpr int TILE = kSortBlock * ITEMS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
@@ -156,6 +158,7 @@ onesweep_pass_kernel(int64_t n, const KeyT* __restrict__ keys_in, const int32_t*
   __syncthreads();
   const int tile = s_tile;
   const int64_t tile_base = (int64_t)tile * TILE;
+  if (tile_base >= n) return;   // (counted) tiles past the end: no items, and no later tile looks back at them
   const int valid = (int)min((int64_t)TILE, n - tile_base);
   const int64_t warp_base = tile_base + (int64_t)warp * (32 * ITEMS);
 
@@ -308,7 +311,8 @@ static SortLayout sort_layout(int64_t n, int key_bytes, int begin_bit, int end_b
 
 template <typename KeyT>
 static int radix_sort_impl(int64_t n, const KeyT* keys_in, const int32_t* vals_in, KeyT* keys_out, int32_t* vals_out,
-                           int begin_bit, int end_bit, unsigned char* ws, cudaStream_t st) {
+                           int begin_bit, int end_bit, unsigned char* ws, cudaStream_t st,
+                           const int32_t* n_dev = nullptr) {
   const SortLayout L = sort_layout(n, sizeof(KeyT), begin_bit, end_bit);
   unsigned* hist = (unsigned*)(ws + L.off_hist);
   unsigned* tickets = (unsigned*)(ws + L.off_ticket);
@@ -318,7 +322,7 @@ static int radix_sort_impl(int64_t n, const KeyT* keys_in, const int32_t* vals_i
 
   GS_CUDA(cudaMemsetAsync(ws, 0, L.zero_bytes, st));
   int hist_blocks = (int)min((int64_t)148 * 8, ceil_div(n, 256));
-  radix_histogram_kernel<KeyT><<<hist_blocks, 256, 0, st>>>(n, keys_in, begin_bit, end_bit, L.passes, hist);
+  radix_histogram_kernel<KeyT><<<hist_blocks, 256, 0, st>>>(n, keys_in, begin_bit, end_bit, L.passes, hist, n_dev);
   GS_LAUNCH_CHECK();
   radix_histogram_scan_kernel<<<L.passes, kRadix, 0, st>>>(hist);
   GS_LAUNCH_CHECK();
@@ -338,7 +342,7 @@ static int radix_sort_impl(int64_t n, const KeyT* keys_in, const int32_t* vals_i
     auto kern = nb == kRadixBits ? onesweep_pass_kernel<KeyT, true> : onesweep_pass_kernel<KeyT, false>;
     kern<<<(unsigned)L.tiles, kSortBlock, smem, st>>>(
         n, src_k, src_v, dst_k, dst_v, shift, (1u << nb) - 1u, hist + p * kRadix,
-        status + (size_t)p * L.tiles * kRadix, tickets + p);
+        status + (size_t)p * L.tiles * kRadix, tickets + p, n_dev);
     GS_LAUNCH_CHECK();
     src_k = dst_k;
     src_v = dst_v;
@@ -391,9 +395,9 @@ size_t gs_radix_sort_pairs_workspace_bytes(int64_t n, int32_t key_bytes, int32_t
   return sort_layout(n, key_bytes, begin_bit, end_bit).total;
 }
 
-int gs_radix_sort_pairs(int64_t n, int32_t key_bytes, const void* keys_in, const int32_t* values_in, void* keys_out,
-                        int32_t* values_out, int32_t begin_bit, int32_t end_bit, void* workspace,
-                        size_t workspace_bytes, void* stream) {
+static int radix_sort_entry(int64_t n, const int32_t* count_dev, int32_t key_bytes, const void* keys_in,
+                            const int32_t* values_in, void* keys_out, int32_t* values_out, int32_t begin_bit,
+                            int32_t end_bit, void* workspace, size_t workspace_bytes, void* stream) {
   GS_CHECK_ARG(key_bytes == 4 || key_bytes == 8, "gs_radix_sort_pairs: key_bytes must be 4 or 8");
   GS_CHECK_ARG(begin_bit >= 0 && end_bit > begin_bit && end_bit <= key_bytes * 8,
                "gs_radix_sort_pairs: bad bit range [%d, %d)", begin_bit, end_bit);
@@ -409,9 +413,24 @@ int gs_radix_sort_pairs(int64_t n, int32_t key_bytes, const void* keys_in, const
   cudaStream_t st = (cudaStream_t)stream;
   if (key_bytes == 8)
     return radix_sort_impl<uint64_t>(n, (const uint64_t*)keys_in, values_in, (uint64_t*)keys_out, values_out,
-                                     begin_bit, end_bit, (unsigned char*)workspace, st);
+                                     begin_bit, end_bit, (unsigned char*)workspace, st, count_dev);
   return radix_sort_impl<uint32_t>(n, (const uint32_t*)keys_in, values_in, (uint32_t*)keys_out, values_out, begin_bit,
-                                   end_bit, (unsigned char*)workspace, st);
+                                   end_bit, (unsigned char*)workspace, st, count_dev);
+}
+
+int gs_radix_sort_pairs(int64_t n, int32_t key_bytes, const void* keys_in, const int32_t* values_in, void* keys_out,
+                        int32_t* values_out, int32_t begin_bit, int32_t end_bit, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  return radix_sort_entry(n, nullptr, key_bytes, keys_in, values_in, keys_out, values_out, begin_bit, end_bit,
+                          workspace, workspace_bytes, stream);
+}
+
+int gs_radix_sort_pairs_counted(int64_t capacity, const int32_t* count_dev, int32_t key_bytes, const void* keys_in,
+                                const int32_t* values_in, void* keys_out, int32_t* values_out, int32_t begin_bit,
+                                int32_t end_bit, void* workspace, size_t workspace_bytes, void* stream) {
+  GS_CHECK_ARG(count_dev != nullptr, "gs_radix_sort_pairs_counted: null count");
+  return radix_sort_entry(capacity, count_dev, key_bytes, keys_in, values_in, keys_out, values_out, begin_bit, end_bit,
+                          workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

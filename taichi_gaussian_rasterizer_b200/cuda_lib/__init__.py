@@ -64,6 +64,31 @@ def radix_sort_pairs(keys: torch.Tensor, values: torch.Tensor, start_bit=0, end_
   return keys_out, values_out
 
 
+def radix_sort_pairs_counted(keys: torch.Tensor, values: torch.Tensor, count_device: torch.Tensor, start_bit=0,
+                             end_bit=None):
+  """radix_sort_pairs of the first ``count_device[0]`` pairs of capacity-sized buffers, the count (int32) still on
+  the device: nothing is read back; output rows past the count are uninitialised (extension, not in the reference)."""
+  check_cuda("keys", keys)
+  check_cuda("values", values)
+  check_cuda("count", count_device)
+  assert keys.dtype in _KEY_BYTES and values.dtype == torch.int32 and count_device.dtype == torch.int32
+  assert keys.shape == values.shape and keys.dim() == 1
+  kb = _KEY_BYTES[keys.dtype]
+  if end_bit is None or end_bit < 0:
+    end_bit = kb * 8
+  n = keys.shape[0]
+  keys_out, values_out = torch.empty_like(keys), torch.empty_like(values)
+  if n == 0:
+    return keys_out, values_out
+  lib = N.lib()
+  ws = N.workspace(lib.gs_radix_sort_pairs_workspace_bytes(n, kb, start_bit, end_bit), keys.device)
+  N.call("gs_radix_sort_pairs_counted", ctypes.c_int64(n), N.ptr(count_device), ctypes.c_int32(kb),
+         N.ptr(keys.contiguous()), N.ptr(values.contiguous()), N.ptr(keys_out), N.ptr(values_out),
+         ctypes.c_int32(start_bit), ctypes.c_int32(end_bit), N.ptr(ws), ctypes.c_size_t(ws.numel()),
+         N.stream_ptr(keys.device))
+  return keys_out, values_out
+
+
 def radix_argsort(keys: torch.Tensor):
   idx = torch.arange(keys.shape[0], dtype=torch.int32, device=keys.device)
   _, idx = radix_sort_pairs(keys, idx)
@@ -75,4 +100,5 @@ def segmented_sort_pairs(*args, **kwargs):
                             "render path (SURVEY.md K12); it is out of scope here")
 
 
-__all__ = ["full_cumsum", "full_cumsum_device", "radix_sort_pairs", "radix_argsort", "segmented_sort_pairs"]
+__all__ = ["full_cumsum", "full_cumsum_device", "radix_sort_pairs", "radix_sort_pairs_counted", "radix_argsort",
+           "segmented_sort_pairs"]

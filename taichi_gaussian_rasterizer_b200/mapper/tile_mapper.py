@@ -26,7 +26,7 @@ from beartype import beartype
 from beartype.typing import Tuple
 
 from .. import _native as N
-from ..cuda_lib import full_cumsum_device, radix_sort_pairs
+from ..cuda_lib import full_cumsum_device, radix_sort_pairs, radix_sort_pairs_counted
 from ..data_types import RasterConfig
 
 MAX_TILE = 65535  # 16 bit tile id inside the sorted key bits (tile_mapper.py:29)
@@ -79,11 +79,32 @@ def map_to_tiles(gaussians: torch.Tensor, depth: torch.Tensor,
   return _map_to_tiles(gaussians, depth, image_size, config, use_depth16, ndc_range=None)
 
 
-def _map_to_tiles(gaussians, depth, image_size, config, use_depth16=False, ndc_range=None):
+def launch_depth_order_counted(depth_capacity, count_device, image_size, config, use_depth16=False, ndc_range=None):
+  """Stage 1 of the depth-first mapping (depth keys + their stable sort) for a visible set whose SIZE is still on the
+  device: ``depth_capacity`` (N, 1) f32 holds the depths in its first ``count_device[0]`` rows.  Returns the (N,)
+  int32 permutation buffer, valid in its first count rows; hand ``perm[:V]`` to ``_map_to_tiles(depth_order=...)``.
+  render_gaussians enqueues this before the host reads the visible count, so that the GPU has work across that
+  read-back and the host's launch latency after it."""
+  cap = depth_capacity.shape[0]
+  near, far = (float(ndc_range[0]), float(ndc_range[1])) if ndc_range is not None else (0.0, 0.0)
+  device = depth_capacity.device
+  p = _tile_params(cap, image_size, config, use_depth16)
+  depth_keys = torch.empty((cap,), dtype=torch.int32, device=device)
+  iota = torch.empty((cap,), dtype=torch.int32, device=device)
+  if cap == 0:
+    return iota
+  N.call("gs_depth_keys_counted", ctypes.byref(p), N.ptr(depth_capacity), ctypes.c_double(near), ctypes.c_double(far),
+         N.ptr(count_device), N.ptr(depth_keys), N.ptr(iota), N.stream_ptr(device))
+  _, perm = radix_sort_pairs_counted(depth_keys, iota, count_device, 0, 16 if use_depth16 else 32)
+  return perm
+
+
+def _map_to_tiles(gaussians, depth, image_size, config, use_depth16=False, ndc_range=None, depth_order=None):
   """map_to_tiles; with ``ndc_range=(near, far)`` the ``depth`` column is LINEAR camera depth and the sort depth is
   its NDC value, formed inside the key kernel with torch's own f32 operation sequence (bit-identical keys to
   ``map_to_tiles(g, ndc_depth(depth, near, far), ...)`` — tests/test_gpu_tile_mapper.py), which saves the
-  render path four elementwise launches per frame (render_projected)."""
+  render path four elementwise launches per frame (render_projected).  ``depth_order``: the (n,) permutation already
+  produced by launch_depth_order_counted for exactly these depths."""
   shape = _check_inputs(gaussians, depth, image_size, config)
   near, far = (float(ndc_range[0]), float(ndc_range[1])) if ndc_range is not None else (0.0, 0.0)
   with torch.no_grad():
@@ -97,11 +118,15 @@ def _map_to_tiles(gaussians, depth, image_size, config, use_depth16=False, ndc_r
 
     total = 0
     if n > 0:
-      depth_keys = torch.empty((n,), dtype=torch.int32, device=device)   # bit patterns of u32 keys
-      iota = torch.empty((n,), dtype=torch.int32, device=device)
-      N.call("gs_depth_keys", ctypes.byref(p), N.ptr(d), ctypes.c_double(near), ctypes.c_double(far),
-             N.ptr(depth_keys), N.ptr(iota), stream)
-      _, perm = radix_sort_pairs(depth_keys, iota, 0, 16 if use_depth16 else 32)
+      if depth_order is not None:
+        assert depth_order.shape == (n,) and depth_order.dtype == torch.int32 and depth_order.is_contiguous()
+        perm = depth_order
+      else:
+        depth_keys = torch.empty((n,), dtype=torch.int32, device=device)   # bit patterns of u32 keys
+        iota = torch.empty((n,), dtype=torch.int32, device=device)
+        N.call("gs_depth_keys", ctypes.byref(p), N.ptr(d), ctypes.c_double(near), ctypes.c_double(far),
+               N.ptr(depth_keys), N.ptr(iota), stream)
+        _, perm = radix_sort_pairs(depth_keys, iota, 0, 16 if use_depth16 else 32)
       counts = torch.empty((n,), dtype=torch.int32, device=device)
       masks = torch.empty((n,), dtype=torch.int64, device=device)   # per slot tile bit masks: count pass -> emit pass
       N.call("gs_tile_count_perm", ctypes.byref(p), N.ptr(g), N.ptr(perm), N.ptr(counts), N.ptr(masks), stream)

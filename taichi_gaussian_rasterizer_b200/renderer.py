@@ -6,17 +6,18 @@ rendering.py.  The two ``torch.compile`` helpers of the reference (ndc_depth, de
 torch here.
 """
 from dataclasses import replace
+from typing import Optional
 
 import torch
 from beartype import beartype
 
 from .data_types import Gaussians3D, RasterConfig
-from .mapper.tile_mapper import _map_to_tiles, map_to_tiles
+from .mapper.tile_mapper import _map_to_tiles, launch_depth_order_counted, map_to_tiles
 from .perspective import CameraParams
 from .perspective.projection import project_to_image
 from .rasterizer.function import rasterize_with_tiles
 from .rendering import Rendering
-from .spherical_harmonics import evaluate_sh_at, launch_sh_forward_counted
+from .spherical_harmonics import evaluate_sh_at, launch_gather_counted, launch_sh_forward_counted
 from .torch_lib.projection import ndc_depth
 
 
@@ -28,7 +29,8 @@ def render_gaussians(
   use_sh: bool = False,
   render_depth: bool = False,
   use_depth16: bool = False,
-  render_median_depth: bool = False
+  render_median_depth: bool = False,
+  sh_colors: Optional[torch.Tensor] = None
 ) -> Rendering:
   """
   A complete renderer for 3D gaussians.
@@ -40,6 +42,9 @@ def render_gaussians(
     render_depth: bool - whether to render depth and depth variance
     use_depth16: bool - whether to use 16 bit depth encoding for sorting (otherwise 32 bit)
     render_median_depth: bool - whether to render the median depth map
+    sh_colors: (extension) with use_sh, this view's dense (N, 3) colours from ``evaluate_sh_views`` (one pass over the
+      SH coefficients for the whole batch of views): the visible rows are gathered instead of evaluated; autograd
+      still reaches ``gaussians.feature``
 
   Returns:
     Rendering - rendered image, with optional depth / depth variance and per point statistics
@@ -48,17 +53,27 @@ def render_gaussians(
   # host read-back of the visible count
   camera_position = camera_params.camera_position if use_sh else None
   early = {}
-  if use_sh and gaussians.feature.is_contiguous() and gaussians.position.is_contiguous() \
-      and gaussians.position.dtype == gaussians.feature.dtype:
-    # the SH colours only need the device-side visible set: enqueue them right behind the projection kernel, before
-    # the host blocks on the visible count, so the GPU does not idle across that read-back
-    def early_sh(indexes_capacity, count_device):
+  sh_early = use_sh and gaussians.feature.is_contiguous() and gaussians.position.is_contiguous() \
+    and gaussians.position.dtype == gaussians.feature.dtype
+  order_early = gaussians.position.dtype == torch.float32
+  assert sh_colors is None or sh_early, "sh_colors needs use_sh and contiguous features / positions of one dtype"
+
+  # Work that only needs the device-side visible set is enqueued right behind the projection kernel, BEFORE the host
+  # blocks on the visible count, so that the GPU does not idle across that read-back and the host's launches after it:
+  # the SH colours (or the gather of this view's rows of a batch evaluation) and the depth ordering of the tile mapper.
+  def early_work(indexes_capacity, count_device, depth_capacity):
+    if sh_early and sh_colors is not None:
+      assert sh_colors.shape == (gaussians.feature.shape[0], gaussians.feature.shape[1]) and sh_colors.is_contiguous()
+      early["sh"] = launch_gather_counted(sh_colors, indexes_capacity, count_device)
+    elif sh_early:
       early["sh"] = launch_sh_forward_counted(gaussians.feature.detach(), gaussians.position.detach(),
                                               indexes_capacity, count_device,
                                               camera_position.detach().to(gaussians.feature.dtype).contiguous())
-  else:
-    early_sh = None
-  gaussians2d, depths, indexes = project_to_image(gaussians, camera_params, config, after_launch=early_sh)
+    if order_early:
+      early["order"] = launch_depth_order_counted(depth_capacity, count_device, camera_params.image_size, config,
+                                                  use_depth16, (camera_params.near_plane, camera_params.far_plane))
+  gaussians2d, depths, indexes = project_to_image(gaussians, camera_params, config,
+                                                  after_launch=early_work if (sh_early or order_early) else None)
 
   if use_sh:
     pre = early["sh"][:indexes.shape[0]] if "sh" in early else None
@@ -69,9 +84,10 @@ def render_gaussians(
     features = gaussians.feature[indexes]
     assert len(features.shape) == 2, f"Features must be (N, C) if use_sh=False, got {features.shape}"
 
+  order = early["order"][:indexes.shape[0]] if "order" in early else None
   return render_projected(indexes, gaussians2d, features, depths, camera_params, config,
                           render_depth=render_depth, use_depth16=use_depth16,
-                          render_median_depth=render_median_depth)
+                          render_median_depth=render_median_depth, depth_order=order)
 
 
 def compute_depth_variance(depth_depthsq, weight, eps=1e-6):
@@ -99,9 +115,12 @@ def render_projected(indexes: torch.Tensor, gaussians2d: torch.Tensor,
                      features: torch.Tensor, depths: torch.Tensor,
                      camera_params: CameraParams, config: RasterConfig,
                      render_depth: bool = False, use_depth16: bool = False,
-                     render_median_depth: bool = False, use_ndc_depth: bool = False):
+                     render_median_depth: bool = False, use_ndc_depth: bool = False,
+                     depth_order: Optional[torch.Tensor] = None):
   """Tile-map and rasterize gaussians that are already projected (renderer.py:183-231 of the reference).
-  Gaussians are ordered by NDC depth inside every tile; depth features stay linear unless use_ndc_depth."""
+  Gaussians are ordered by NDC depth inside every tile; depth features stay linear unless use_ndc_depth.
+  ``depth_order`` (extension): the NDC depth ordering of exactly these gaussians when render_gaussians has already
+  enqueued it (mapper.tile_mapper.launch_depth_order_counted)."""
   size = camera_params.image_size
   ndc_range = (camera_params.near_plane, camera_params.far_plane)
 
@@ -115,7 +134,8 @@ def render_projected(indexes: torch.Tensor, gaussians2d: torch.Tensor,
     overlap_to_point, tile_ranges = map_to_tiles(gaussians2d, depths, image_size=size, config=config,
                                                  use_depth16=use_depth16)
   else:
-    overlap_to_point, tile_ranges = _map_to_tiles(gaussians2d, depths, size, config, use_depth16, ndc_range=ndc_range)
+    overlap_to_point, tile_ranges = _map_to_tiles(gaussians2d, depths, size, config, use_depth16, ndc_range=ndc_range,
+                                                  depth_order=depth_order)
   ranges = tile_ranges.view(-1, 2)
   raster = rasterize_with_tiles(gaussians2d, features, tile_overlap_ranges=ranges,
                                 overlap_to_point=overlap_to_point, image_size=size, config=config)

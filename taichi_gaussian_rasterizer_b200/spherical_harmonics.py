@@ -99,6 +99,41 @@ def launch_sh_forward_counted(sh_params, positions, indexes_capacity, count_devi
   return out
 
 
+def evaluate_sh_views(sh_params: torch.Tensor, positions: torch.Tensor, camera_positions) -> list:
+  """Colours of ALL gaussians for every view of a batch, one dense (M, K) tensor per camera position (extension, not
+  in the reference): the coefficient rows are read once per batch instead of once per view (gs_sh_fwd_views; f32,
+  K = 3, degree 1 or 3).  Pass a view's tensor to ``render_gaussians(..., sh_colors=...)``, which gathers the visible
+  rows and builds the same autograd node as ``evaluate_sh_at`` (gradients reach ``sh_params``).  Worth it when most
+  gaussians are in view in most views; values are those of ``evaluate_sh_at``."""
+  check_sh_degree(sh_params)
+  N.require_cuda(sh_params, positions)
+  m, k, d = sh_params.shape
+  assert sh_params.dtype == torch.float32 and k == 3 and d in (4, 16), \
+    f"evaluate_sh_views: float32, 3 channels, degree 1 or 3 (got {sh_params.dtype}, {tuple(sh_params.shape)})"
+  params = sh_params.detach().contiguous()
+  pos = positions.detach().to(torch.float32).contiguous()
+  cams = [c.detach().to(torch.float32).contiguous() for c in camera_positions]
+  outs = [torch.empty((m, k), dtype=torch.float32, device=sh_params.device) for _ in cams]
+  p = N.GsSHParams(N.GS_F32, k, d, 1, m, 0, 0, 0)
+  for s in range(0, len(cams), 16):
+    nv = len(cams[s:s + 16])
+    arr = ctypes.c_void_p * nv
+    N.call("gs_sh_fwd_views", ctypes.byref(p), ctypes.c_int32(nv), N.ptr(params), N.ptr(pos),
+           arr(*[c.data_ptr() for c in cams[s:s + 16]]), arr(*[o.data_ptr() for o in outs[s:s + 16]]),
+           N.stream_ptr(sh_params.device))
+  return outs
+
+
+def launch_gather_counted(dense: torch.Tensor, indexes_capacity: torch.Tensor, count_device: torch.Tensor) -> torch.Tensor:
+  """``dense[indexes]`` for a visible set whose SIZE is still on the device (see launch_sh_forward_counted): returns
+  the (capacity, K) buffer, rows past the count uninitialised."""
+  cap, k = indexes_capacity.shape[0], dense.shape[1]
+  out = torch.empty((cap, k), dtype=dense.dtype, device=dense.device)
+  N.call("gs_gather_rows_counted", ctypes.c_int64(cap), ctypes.c_int32(k), N.ptr(dense), N.ptr(indexes_capacity),
+         N.ptr(count_device), N.ptr(out), N.stream_ptr(dense.device))
+  return out
+
+
 @beartype
 def evaluate_sh_at(sh_params: torch.Tensor,   # M, K, (degree + 1)^2  (usually K=3, for RGB)
                    positions: torch.Tensor,   # M, 3

@@ -173,3 +173,77 @@ def test_deferred_sh_clean_bucket_without_views(cuda_device):
     bucket.flat.fill_(3.0)
     bucket.zero_()
   assert float(bucket.flat.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("sh_degree,margin", [(3, 0.0), (1, 1.5)])
+def test_batched_sh_views_match_per_view(cuda_device, sh_degree, margin):
+  """evaluate_sh_views (one pass over the coefficients for all views of a batch) gives evaluate_sh_at's colours, and
+  render_gaussians(..., sh_colors=) the same image and the same gradients as the per-view evaluation (18 cameras:
+  more than one gs_sh_fwd_views call)."""
+  from taichi_gaussian_rasterizer_b200 import evaluate_sh_at, evaluate_sh_views
+  from taichi_gaussian_rasterizer_b200.torch_lib.projection import join_rt, quat_to_mat
+  cfg = RasterConfig()
+  g, cam = scene3d(21, 4000, image_size=(256, 192), scale_factor=0.7, sh_degree=sh_degree, margin=margin)
+  cams = [cam]
+  for k in range(17):
+    q = torch.tensor([0.01 * (k % 4 + 1), -0.02 + 0.004 * k, 0.005, 1.0])
+    cams.append(cam.transformed(join_rt(quat_to_mat(q / q.norm()), torch.tensor([0.02, 0.002 * k, -0.01]))))
+  cams = [c.to(device=cuda_device) for c in cams]
+
+  gd = g.to(device=cuda_device)
+  every = torch.arange(gd.feature.shape[0], device=cuda_device)
+  colors = evaluate_sh_views(gd.feature, gd.position, [c.camera_position for c in cams])
+  assert len(colors) == 18
+  for c, col in zip(cams, colors):
+    ref = evaluate_sh_at(gd.feature, gd.position, every, c.camera_position)
+    assert col.shape == ref.shape
+    assert (col - ref).abs().max().item() < 1e-6
+
+  def run(batched):
+    gg = g.to(device=cuda_device)
+    gg.requires_grad_(True)
+    images = []
+    for i in (0, 5, 17):
+      out = render_gaussians(gg, cams[i], cfg, use_sh=True, sh_colors=colors[i] if batched else None)
+      out.image.square().mean().backward()
+      images.append(out.image.detach())
+    return images, [gg.feature.grad, gg.position.grad, gg.log_scaling.grad, gg.rotation.grad, gg.alpha_logit.grad]
+
+  img_a, grads_a = run(False)
+  img_b, grads_b = run(True)
+  for a, b in zip(img_a, img_b):
+    assert rel_l2(b, a) < 1e-6
+  for a, b in zip(grads_a, grads_b):
+    assert rel_l2(b, a) < 1e-5
+
+
+@pytest.mark.parametrize("count", [0, 1, 4095, 4096, 4097, 20000])
+def test_counted_sort_and_depth_order(cuda_device, count):
+  """gs_radix_sort_pairs_counted / gs_depth_keys_counted (the count stays on the device; the grid covers the
+  capacity): same result as the host-sized calls on the prefix, nothing written past the count, and
+  _map_to_tiles(depth_order=...) gives the bit-identical tile map."""
+  from taichi_gaussian_rasterizer_b200.cuda_lib import radix_sort_pairs, radix_sort_pairs_counted
+  from taichi_gaussian_rasterizer_b200.mapper.tile_mapper import _map_to_tiles, launch_depth_order_counted
+  cap = 20000
+  gen = torch.Generator().manual_seed(count)
+  keys = torch.randint(0, 2 ** 31 - 1, (cap,), dtype=torch.int32, generator=gen).to(cuda_device)
+  vals = torch.arange(cap, dtype=torch.int32, device=cuda_device)
+  cnt = torch.tensor([count], dtype=torch.int32, device=cuda_device)
+  k_ref, v_ref = radix_sort_pairs(keys[:count].contiguous(), vals[:count].contiguous())
+  k_out, v_out = radix_sort_pairs_counted(keys, vals, cnt)
+  assert torch.equal(k_out[:count], k_ref) and torch.equal(v_out[:count], v_ref)
+
+  cfg = RasterConfig()
+  g, cam = scene3d(31, cap, image_size=(320, 240), scale_factor=0.7, sh_degree=None)
+  from taichi_gaussian_rasterizer_b200.perspective.projection import project_to_image
+  g2d, depths, idx = project_to_image(g.to(device=cuda_device), cam.to(device=cuda_device), cfg)
+  v = min(count, g2d.shape[0])
+  depth_cap = torch.full((cap, 1), float("nan"), device=cuda_device)
+  depth_cap[:v] = depths[:v]
+  cntv = torch.tensor([v], dtype=torch.int32, device=cuda_device)
+  rng = (cam.near_plane, cam.far_plane)
+  order = launch_depth_order_counted(depth_cap, cntv, cam.image_size, cfg, False, rng)
+  a = _map_to_tiles(g2d[:v].contiguous(), depths[:v].contiguous(), cam.image_size, cfg, False, ndc_range=rng)
+  b = _map_to_tiles(g2d[:v].contiguous(), depths[:v].contiguous(), cam.image_size, cfg, False, ndc_range=rng,
+                    depth_order=order[:v])
+  assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
