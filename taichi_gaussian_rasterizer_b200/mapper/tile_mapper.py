@@ -32,6 +32,18 @@ from ..data_types import RasterConfig
 MAX_TILE = 65535  # 16 bit tile id inside the sorted key bits (tile_mapper.py:29)
 
 
+_pinned = {}
+
+
+def _pinned_total(device) -> torch.Tensor:
+  """One pinned int32 per device for the asynchronous read-back of the overlap total (reads are serialised by the
+  event wait that follows each copy)."""
+  key = (device.type, device.index)
+  if key not in _pinned:
+    _pinned[key] = torch.zeros((1,), dtype=torch.int32).pin_memory()
+  return _pinned[key]
+
+
 def pad_to_tile(image_size: Tuple[Integral, Integral], tile_size: int):
   def pad(x):
     return int(math.ceil(x / tile_size) * tile_size)
@@ -99,12 +111,15 @@ def launch_depth_order_counted(depth_capacity, count_device, image_size, config,
   return perm
 
 
-def _map_to_tiles(gaussians, depth, image_size, config, use_depth16=False, ndc_range=None, depth_order=None):
+def _map_to_tiles(gaussians, depth, image_size, config, use_depth16=False, ndc_range=None, depth_order=None,
+                  before_total_sync=None):
   """map_to_tiles; with ``ndc_range=(near, far)`` the ``depth`` column is LINEAR camera depth and the sort depth is
   its NDC value, formed inside the key kernel with torch's own f32 operation sequence (bit-identical keys to
   ``map_to_tiles(g, ndc_depth(depth, near, far), ...)`` — tests/test_gpu_tile_mapper.py), which saves the
   render path four elementwise launches per frame (render_projected).  ``depth_order``: the (n,) permutation already
-  produced by launch_depth_order_counted for exactly these depths."""
+  produced by launch_depth_order_counted for exactly these depths.  ``before_total_sync()``: called once, after the
+  overlap scan is enqueued and before the host waits for the overlap total — the caller's chance to enqueue work that
+  does not depend on the tile map, so that the GPU is busy across that read-back."""
   shape = _check_inputs(gaussians, depth, image_size, config)
   near, far = (float(ndc_range[0]), float(ndc_range[1])) if ndc_range is not None else (0.0, 0.0)
   with torch.no_grad():
@@ -131,20 +146,32 @@ def _map_to_tiles(gaussians, depth, image_size, config, use_depth16=False, ndc_r
       masks = torch.empty((n,), dtype=torch.int64, device=device)   # per slot tile bit masks: count pass -> emit pass
       N.call("gs_tile_count_perm", ctypes.byref(p), N.ptr(g), N.ptr(perm), N.ptr(counts), N.ptr(masks), stream)
       cum = full_cumsum_device(counts)
-      total = int(cum[-1].item())   # host read-back of K
+      # host read-back of K: asynchronous copy into a pinned word + event wait (no stream-wide synchronisation, no
+      # pageable staging as `.item()` on a device tensor does)
+      host_total = _pinned_total(device)
+      host_total.copy_(cum[n:], non_blocking=True)
+      ready = torch.cuda.Event()
+      ready.record(torch.cuda.current_stream(device))
+      tile_bits = max(1, (shape[0] * shape[1] - 1).bit_length())
+      if before_total_sync is not None:
+        before_total_sync()
+        before_total_sync = None
+      ready.synchronize()
+      total = int(host_total.item())
 
     if total > 0:
       tile_ids = torch.empty((total,), dtype=torch.int32, device=device)
       values = torch.empty((total,), dtype=torch.int32, device=device)
       N.call("gs_tile_emit_tiles", ctypes.byref(p), N.ptr(g), N.ptr(perm), N.ptr(cum), N.ptr(masks), N.ptr(tile_ids),
              N.ptr(values), stream)
-      tile_bits = max(1, (shape[0] * shape[1] - 1).bit_length())
       tile_ids, overlap_to_point = radix_sort_pairs(tile_ids, values, 0, tile_bits)
     else:
       tile_ids = None
       overlap_to_point = torch.empty((0,), dtype=torch.int32, device=device)
 
     N.call("gs_find_ranges_tiles", ctypes.byref(p), ctypes.c_int64(total), N.ptr(tile_ids), N.ptr(tile_ranges), stream)
+    if before_total_sync is not None:   # nothing in view: the callback still runs exactly once
+      before_total_sync()
     return overlap_to_point, tile_ranges
 
 
@@ -189,7 +216,14 @@ def map_to_tiles_staged(gaussians: torch.Tensor, depth: torch.Tensor,
       counts = torch.empty((n,), dtype=torch.int32, device=device)
       N.call("gs_tile_count", ctypes.byref(p), N.ptr(g), N.ptr(counts), stream)
       cum = full_cumsum_device(counts)
-      total = int(cum[-1].item())   # host read-back of K
+      # host read-back of K: asynchronous copy into a pinned word + event wait (no stream-wide synchronisation, no
+      # pageable staging as `.item()` on a device tensor does)
+      host_total = _pinned_total(device)
+      host_total.copy_(cum[n:], non_blocking=True)
+      ready = torch.cuda.Event()
+      ready.record(torch.cuda.current_stream(device))
+      ready.synchronize()
+      total = int(host_total.item())
 
     if total > 0:
       key_dtype = torch.int32 if use_depth16 else torch.int64   # bit patterns of u32 / u64 keys

@@ -17,7 +17,7 @@ from .perspective import CameraParams
 from .perspective.projection import project_to_image
 from .rasterizer.function import rasterize_with_tiles
 from .rendering import Rendering
-from .spherical_harmonics import evaluate_sh_at, launch_gather_counted, launch_sh_forward_counted
+from .spherical_harmonics import evaluate_sh_at, launch_gather_into, launch_sh_forward_into
 from .torch_lib.projection import ndc_depth
 
 
@@ -60,26 +60,33 @@ def render_gaussians(
 
   # Work that only needs the device-side visible set is enqueued right behind the projection kernel, BEFORE the host
   # blocks on the visible count, so that the GPU does not idle across that read-back and the host's launches after it:
-  # the SH colours (or the gather of this view's rows of a batch evaluation) and the depth ordering of the tile mapper.
+  # the depth ordering of the tile mapper (0.18 ms at 3 M gaussians).
   def early_work(indexes_capacity, count_device, depth_capacity):
-    if sh_early and sh_colors is not None:
-      assert sh_colors.shape == (gaussians.feature.shape[0], gaussians.feature.shape[1]) and sh_colors.is_contiguous()
-      early["sh"] = launch_gather_counted(sh_colors, indexes_capacity, count_device)
-    elif sh_early:
-      early["sh"] = launch_sh_forward_counted(gaussians.feature.detach(), gaussians.position.detach(),
-                                              indexes_capacity, count_device,
-                                              camera_position.detach().to(gaussians.feature.dtype).contiguous())
-    if order_early:
-      early["order"] = launch_depth_order_counted(depth_capacity, count_device, camera_params.image_size, config,
-                                                  use_depth16, (camera_params.near_plane, camera_params.far_plane))
+    early["order"] = launch_depth_order_counted(depth_capacity, count_device, camera_params.image_size, config,
+                                                use_depth16, (camera_params.near_plane, camera_params.far_plane))
   gaussians2d, depths, indexes = project_to_image(gaussians, camera_params, config,
-                                                  after_launch=early_work if (sh_early or order_early) else None)
+                                                  after_launch=early_work if order_early else None)
 
-  if use_sh:
-    pre = early["sh"][:indexes.shape[0]] if "sh" in early else None
+  fill_features = None
+  if use_sh and sh_early:
+    # The colours do not depend on the tile map: their kernel (the SH evaluation, or the gather of this view's rows of
+    # a batch evaluation) is enqueued by the tile mapper right before it waits for the overlap total, to keep the GPU
+    # busy across THAT read-back.  The autograd node is built now, around the buffer the kernel will fill.
+    pre = torch.empty((indexes.shape[0], gaussians.feature.shape[1]), dtype=gaussians.feature.dtype,
+                      device=gaussians.feature.device)
+    if sh_colors is not None:
+      assert sh_colors.shape == (gaussians.feature.shape[0], gaussians.feature.shape[1]) and sh_colors.is_contiguous()
+      fill_features = lambda: launch_gather_into(sh_colors, indexes, pre)   # noqa: E731
+    else:
+      cam_pos = camera_position.detach().to(gaussians.feature.dtype).contiguous()
+      fill_features = lambda: launch_sh_forward_into(gaussians.feature.detach(), gaussians.position.detach(),   # noqa: E731
+                                                     indexes, cam_pos, pre)
     features = evaluate_sh_at(gaussians.feature, gaussians.position.detach(), indexes,
                               camera_position, indexes_sorted_unique=True,   # visible set: ascending
                               precomputed=pre)
+  elif use_sh:
+    features = evaluate_sh_at(gaussians.feature, gaussians.position.detach(), indexes,
+                              camera_position, indexes_sorted_unique=True)
   else:
     features = gaussians.feature[indexes]
     assert len(features.shape) == 2, f"Features must be (N, C) if use_sh=False, got {features.shape}"
@@ -87,7 +94,8 @@ def render_gaussians(
   order = early["order"][:indexes.shape[0]] if "order" in early else None
   return render_projected(indexes, gaussians2d, features, depths, camera_params, config,
                           render_depth=render_depth, use_depth16=use_depth16,
-                          render_median_depth=render_median_depth, depth_order=order)
+                          render_median_depth=render_median_depth, depth_order=order,
+                          before_total_sync=fill_features)
 
 
 def compute_depth_variance(depth_depthsq, weight, eps=1e-6):
@@ -116,26 +124,32 @@ def render_projected(indexes: torch.Tensor, gaussians2d: torch.Tensor,
                      camera_params: CameraParams, config: RasterConfig,
                      render_depth: bool = False, use_depth16: bool = False,
                      render_median_depth: bool = False, use_ndc_depth: bool = False,
-                     depth_order: Optional[torch.Tensor] = None):
+                     depth_order: Optional[torch.Tensor] = None, before_total_sync=None):
   """Tile-map and rasterize gaussians that are already projected (renderer.py:183-231 of the reference).
   Gaussians are ordered by NDC depth inside every tile; depth features stay linear unless use_ndc_depth.
   ``depth_order`` (extension): the NDC depth ordering of exactly these gaussians when render_gaussians has already
-  enqueued it (mapper.tile_mapper.launch_depth_order_counted)."""
+  enqueued it (mapper.tile_mapper.launch_depth_order_counted); ``before_total_sync``: see _map_to_tiles (called exactly
+  once before the rasterizer is enqueued)."""
   size = camera_params.image_size
   ndc_range = (camera_params.near_plane, camera_params.far_plane)
 
   if render_depth:   # two extra leading channels: depth and depth^2, blended like any other feature
+    if before_total_sync is not None:   # the features are read right here: their kernel cannot wait for the mapper
+      before_total_sync()
+      before_total_sync = None
     if use_ndc_depth:
       depths = ndc_depth(depths, *ndc_range)
     features = torch.cat([depths, depths ** 2, features], dim=1)
 
   # gaussians are ordered by NDC depth inside every tile; the key kernel forms it from the linear depth
   if render_depth and use_ndc_depth:
+    if before_total_sync is not None:
+      before_total_sync()
     overlap_to_point, tile_ranges = map_to_tiles(gaussians2d, depths, image_size=size, config=config,
                                                  use_depth16=use_depth16)
   else:
     overlap_to_point, tile_ranges = _map_to_tiles(gaussians2d, depths, size, config, use_depth16, ndc_range=ndc_range,
-                                                  depth_order=depth_order)
+                                                  depth_order=depth_order, before_total_sync=before_total_sync)
   ranges = tile_ranges.view(-1, 2)
   raster = rasterize_with_tiles(gaussians2d, features, tile_overlap_ranges=ranges,
                                 overlap_to_point=overlap_to_point, image_size=size, config=config)

@@ -124,6 +124,22 @@ def evaluate_sh_views(sh_params: torch.Tensor, positions: torch.Tensor, camera_p
   return outs
 
 
+def launch_sh_forward_into(sh_params, positions, indexes, camera_pos, out):
+  """Enqueue the SH evaluation of ``indexes`` into the existing (V, K) buffer ``out`` (no autograd node: pair it with
+  ``evaluate_sh_at(..., precomputed=out)``; the node may be built before this launch, the data is only read by kernels
+  enqueued later on the same stream)."""
+  m, k, d = sh_params.shape
+  p = N.GsSHParams(N.dtype_code(sh_params.dtype), k, d, 1, m, indexes.shape[0], 0, 0)
+  N.call("gs_sh_fwd", ctypes.byref(p), N.ptr(sh_params), N.ptr(positions), N.ptr(indexes), N.ptr(camera_pos),
+         N.ptr(out), N.stream_ptr(sh_params.device))
+
+
+def launch_gather_into(dense: torch.Tensor, indexes: torch.Tensor, out: torch.Tensor):
+  """``out[:] = dense[indexes]`` (rows of 3 floats), enqueued; see launch_sh_forward_into."""
+  N.call("gs_gather_rows_counted", ctypes.c_int64(indexes.shape[0]), ctypes.c_int32(dense.shape[1]), N.ptr(dense),
+         N.ptr(indexes), N.ptr(None), N.ptr(out), N.stream_ptr(dense.device))
+
+
 def launch_gather_counted(dense: torch.Tensor, indexes_capacity: torch.Tensor, count_device: torch.Tensor) -> torch.Tensor:
   """``dense[indexes]`` for a visible set whose SIZE is still on the device (see launch_sh_forward_counted): returns
   the (capacity, K) buffer, rows past the count uninitialised."""
