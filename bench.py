@@ -117,7 +117,8 @@ KERNELS_PER_CALL = {  # kernels launched by each entry point (memsets not counte
   "gs_tile_emit_keys": 1, "gs_find_ranges": 1, "gs_raster_fwd": 2, "gs_raster_bwd": 2,
   "gs_depth_keys": 1, "gs_tile_count_perm": 1, "gs_tile_emit_tiles": 1, "gs_find_ranges_tiles": 1,
   "gs_camera_position": 1, "gs_sh_fwd_counted": 1, "gs_sh_bwd_stage": 1, "gs_sh_bwd_flush": 1,
-  "gs_sh_fwd_views": 1, "gs_gather_rows_counted": 1, "gs_depth_keys_counted": 1,
+  "gs_sh_fwd_views": 1, "gs_gather_rows_counted": 1, "gs_depth_keys_counted": 1, "gs_tile_count_perm_counted": 1,
+  "gs_full_cumsum_counted": 1,
 }
 
 
@@ -334,6 +335,7 @@ def run_ours(args):
     # ... and one flush per step reads the staged views + positions and adds to the coefficient rows (per frame share)
     "gs_sh_bwd_flush": (n * (12 * views + 12 + 2 * 4 * CD)) // views,
     "gs_full_cumsum": 8 * V,
+    "gs_full_cumsum_counted": 8 * V,
     "gs_tile_emit_tiles": 20 * V + 8 * K,
     "gs_radix_sort_pairs_counted": 4 * V + 16 * V * 4,          # depth keys: histogram read + 4 passes over 8 B pairs
     "gs_radix_sort_pairs": 4 * K + 16 * K * passes_k,            # tile ids

@@ -18,7 +18,7 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 
 import bench  # noqa: E402
-from taichi_gaussian_rasterizer_b200 import RasterConfig, render_gaussians  # noqa: E402
+from taichi_gaussian_rasterizer_b200 import RasterConfig, evaluate_sh_views, render_gaussians  # noqa: E402
 
 
 def main():
@@ -43,8 +43,10 @@ def main():
 
   def step():
     with bucket.fused_accumulation():
-      for cam, tgt in zip(cams, targets):
-        r = render_gaussians(g, cam, cfg, use_sh=True)
+      bucket.zero_()
+      colors = evaluate_sh_views(g.feature, g.position, [c.camera_position for c in cams])
+      for cam, tgt, col in zip(cams, targets, colors):
+        r = render_gaussians(g, cam, cfg, use_sh=True, sh_colors=col)
         torch.nn.functional.l1_loss(r.image, tgt).backward()
 
   for _ in range(3):

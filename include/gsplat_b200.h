@@ -165,6 +165,11 @@ int gs_tile_count(const GsTileParams* p, const float* gaussians, int32_t* counts
 size_t gs_full_cumsum_workspace_bytes(int64_t n, int32_t elem_bytes);
 int gs_full_cumsum(int64_t n, int32_t elem_bytes, const void* in, void* out, void* workspace,
                    size_t workspace_bytes, void* stream);
+/* Same over the first *count_dev of `capacity` elements (count on the device; the rest scan as zeros): out[i] for
+ * i <= *count_dev as above, and the total also at total_out (one element, a fixed address the host can copy back
+ * without knowing the count). */
+int gs_full_cumsum_counted(int64_t capacity, int32_t elem_bytes, const int32_t* count_dev, const void* in, void* out,
+                           void* total_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* gaussians (V,7) depth (V) cum (V) -> keys (K) u64|u32, values (K) int32 (gaussian index) */
 int gs_tile_emit_keys(const GsTileParams* p, const float* gaussians, const float* depth,
@@ -207,6 +212,9 @@ int gs_depth_keys_counted(const GsTileParams* p, const float* depth, double near
  * tile tests (spans above 32 tiles are flagged and recomputed).  Same outputs either way. */
 int gs_tile_count_perm(const GsTileParams* p, const float* gaussians, const int32_t* perm, int32_t* counts,
                        uint64_t* tile_masks, void* stream);
+/* Same with the number of gaussians still on the device (p->num_points = capacity of perm / counts / tile_masks). */
+int gs_tile_count_perm_counted(const GsTileParams* p, const float* gaussians, const int32_t* perm,
+                               const int32_t* count_dev, int32_t* counts, uint64_t* tile_masks, void* stream);
 int gs_tile_emit_tiles(const GsTileParams* p, const float* gaussians, const int32_t* perm, const int32_t* cum,
                        const uint64_t* tile_masks, uint32_t* tile_ids, int32_t* values, void* stream);
 int gs_find_ranges_tiles(const GsTileParams* p, int64_t num_overlaps, const uint32_t* sorted_tile_ids,

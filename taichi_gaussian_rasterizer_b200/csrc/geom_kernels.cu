@@ -159,13 +159,14 @@ __global__ void __launch_bounds__(kTileBlock)
 tile_query_kernel(const __grid_constant__ GsTileParams p, int img_w, int img_h, const float* __restrict__ g,
                   const float* __restrict__ depth, const int32_t* __restrict__ perm, const int32_t* __restrict__ cum,
                   int32_t* __restrict__ counts, KeyT* __restrict__ keys, int32_t* __restrict__ values,
-                  uint2* __restrict__ masks) {
+                  uint2* __restrict__ masks, const int32_t* __restrict__ n_dev = nullptr) {
   constexpr bool EMIT = MODE != 0;
   const int64_t slot = (int64_t)blockIdx.x * kTileBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const int ts = p.tile_size;
   const int tiles_wide = img_w / ts;
-  const bool valid = slot < p.num_points;
+  // counted variant (n_dev): p.num_points is the capacity, the number of gaussians is still on the device
+  const bool valid = slot < (n_dev ? min(p.num_points, (int64_t)*n_dev) : p.num_points);
 
   TileQuery qy;
   qy.span_x = qy.span_y = 0;
@@ -474,8 +475,8 @@ int gs_depth_keys_counted(const GsTileParams* p, const float* depth, double near
   return depth_keys_entry(p, depth, near_plane, far_plane, count_dev, keys, values, stream);
 }
 
-int gs_tile_count_perm(const GsTileParams* p, const float* gaussians, const int32_t* perm, int32_t* counts,
-                       uint64_t* tile_masks, void* stream) {
+static int tile_count_perm_entry(const GsTileParams* p, const float* gaussians, const int32_t* perm,
+                                 const int32_t* count_dev, int32_t* counts, uint64_t* tile_masks, void* stream) {
   int rc = check_tile_params(p, "gs_tile_count_perm");
   if (rc != GS_OK) return rc;
   if (p->num_points == 0) return GS_OK;
@@ -483,9 +484,20 @@ int gs_tile_count_perm(const GsTileParams* p, const float* gaussians, const int3
   int ts = p->tile_size;
   int img_w = (int)ceil_div(p->image_width, ts) * ts, img_h = (int)ceil_div(p->image_height, ts) * ts;
   tile_query_kernel<0, uint32_t><<<(unsigned)ceil_div(p->num_points, kTileBlock), kTileBlock, 0, (cudaStream_t)stream>>>(
-      *p, img_w, img_h, gaussians, nullptr, perm, nullptr, counts, nullptr, nullptr, (uint2*)tile_masks);
+      *p, img_w, img_h, gaussians, nullptr, perm, nullptr, counts, nullptr, nullptr, (uint2*)tile_masks, count_dev);
   GS_LAUNCH_CHECK();
   return GS_OK;
+}
+
+int gs_tile_count_perm(const GsTileParams* p, const float* gaussians, const int32_t* perm, int32_t* counts,
+                       uint64_t* tile_masks, void* stream) {
+  return tile_count_perm_entry(p, gaussians, perm, nullptr, counts, tile_masks, stream);
+}
+
+int gs_tile_count_perm_counted(const GsTileParams* p, const float* gaussians, const int32_t* perm,
+                               const int32_t* count_dev, int32_t* counts, uint64_t* tile_masks, void* stream) {
+  GS_CHECK_ARG(count_dev != nullptr, "gs_tile_count_perm_counted: null count");
+  return tile_count_perm_entry(p, gaussians, perm, count_dev, counts, tile_masks, stream);
 }
 
 int gs_tile_emit_tiles(const GsTileParams* p, const float* gaussians, const int32_t* perm, const int32_t* cum,

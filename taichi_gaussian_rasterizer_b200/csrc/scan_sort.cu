@@ -19,7 +19,10 @@ constexpr int kScanTile = kScanBlock * kScanItems;
 template <typename T>
 __global__ void __launch_bounds__(kScanBlock)
 full_cumsum_kernel(int64_t n, const T* __restrict__ in, T* __restrict__ out, unsigned long long* status,
-                   unsigned int* ticket) {
+                   unsigned int* ticket, const int32_t* __restrict__ n_dev = nullptr, T* __restrict__ total_out = nullptr) {
+  // counted variant: the grid covers the capacity n, only the first *n_dev elements count (the rest scan as zeros)
+  // and the total also goes to total_out, a fixed address the host can read without knowing the count
+  if (n_dev) n = min(n, (int64_t)*n_dev);
   __shared__ int s_tile;
   __shared__ unsigned long long s_warp_total[kScanBlock / 32];
   __shared__ unsigned long long s_prefix;
@@ -55,7 +58,10 @@ full_cumsum_kernel(int64_t n, const T* __restrict__ in, T* __restrict__ out, uns
     unsigned long long ex = lookback_exclusive(status, tile, block_total);
     if (lane == 0) {
       s_prefix = ex;
-      if (tile == (int)gridDim.x - 1) out[n] = (T)(ex + block_total);
+      if (tile == (int)gridDim.x - 1) {
+        out[n] = (T)(ex + block_total);
+        if (total_out) *total_out = (T)(ex + block_total);
+      }
     }
   }
   __syncthreads();
@@ -361,13 +367,14 @@ size_t gs_full_cumsum_workspace_bytes(int64_t n, int32_t /*elem_bytes*/) {
   return align_up((size_t)tiles * sizeof(unsigned long long) + 16, 256);
 }
 
-int gs_full_cumsum(int64_t n, int32_t elem_bytes, const void* in, void* out, void* workspace,
-                   size_t workspace_bytes, void* stream) {
+static int full_cumsum_entry(int64_t n, int32_t elem_bytes, const int32_t* count_dev, const void* in, void* out,
+                             void* total_out, void* workspace, size_t workspace_bytes, void* stream) {
   GS_CHECK_ARG(n >= 0 && out != nullptr, "gs_full_cumsum: bad arguments");
   GS_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "gs_full_cumsum: elem_bytes must be 4 or 8");
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) {
     GS_CUDA(cudaMemsetAsync(out, 0, elem_bytes, st));
+    if (total_out) GS_CUDA(cudaMemsetAsync(total_out, 0, elem_bytes, st));
     return GS_OK;
   }
   GS_CHECK_ARG(in != nullptr, "gs_full_cumsum: null input");
@@ -382,12 +389,24 @@ int gs_full_cumsum(int64_t n, int32_t elem_bytes, const void* in, void* out, voi
   unsigned int* ticket = (unsigned int*)(status + tiles);
   if (elem_bytes == 4)
     full_cumsum_kernel<int32_t><<<(unsigned)tiles, kScanBlock, 0, st>>>(n, (const int32_t*)in, (int32_t*)out, status,
-                                                                       ticket);
+                                                                       ticket, count_dev, (int32_t*)total_out);
   else
     full_cumsum_kernel<long long><<<(unsigned)tiles, kScanBlock, 0, st>>>(n, (const long long*)in, (long long*)out,
-                                                                         status, ticket);
+                                                                         status, ticket, count_dev,
+                                                                         (long long*)total_out);
   GS_LAUNCH_CHECK();
   return GS_OK;
+}
+
+int gs_full_cumsum(int64_t n, int32_t elem_bytes, const void* in, void* out, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  return full_cumsum_entry(n, elem_bytes, nullptr, in, out, nullptr, workspace, workspace_bytes, stream);
+}
+
+int gs_full_cumsum_counted(int64_t capacity, int32_t elem_bytes, const int32_t* count_dev, const void* in, void* out,
+                           void* total_out, void* workspace, size_t workspace_bytes, void* stream) {
+  GS_CHECK_ARG(count_dev != nullptr && total_out != nullptr, "gs_full_cumsum_counted: null count / total");
+  return full_cumsum_entry(capacity, elem_bytes, count_dev, in, out, total_out, workspace, workspace_bytes, stream);
 }
 
 size_t gs_radix_sort_pairs_workspace_bytes(int64_t n, int32_t key_bytes, int32_t begin_bit, int32_t end_bit) {

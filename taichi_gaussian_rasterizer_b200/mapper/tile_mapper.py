@@ -111,15 +111,53 @@ def launch_depth_order_counted(depth_capacity, count_device, image_size, config,
   return perm
 
 
+class MapperFront:
+  """What launch_mapper_front_counted leaves on the device (capacity-sized buffers, valid in their first V rows) and
+  the pending read-back of the overlap total."""
+  __slots__ = ("perm", "counts", "masks", "cum", "host_total", "total_ready")
+
+
+def launch_mapper_front_counted(points_capacity, depth_capacity, count_device, image_size, config, use_depth16=False,
+                                ndc_range=None) -> MapperFront:
+  """Everything of the depth-first mapping that does not need the overlap total, for a visible set whose SIZE is still
+  on the device: depth keys + their sort, the overlap count in depth order, its scan, and the asynchronous copy of the
+  total K into a pinned word.  render_gaussians enqueues this right behind the projection kernel: about 0.3 ms of GPU
+  work (3 M gaussians) that covers the host's read-back of the visible count AND the Python between that and the
+  first launch that needs K; ``_map_to_tiles(front=...)`` then only waits for K, emits and sorts the tile ids."""
+  f = MapperFront()
+  cap = depth_capacity.shape[0]
+  device = depth_capacity.device
+  f.perm = launch_depth_order_counted(depth_capacity, count_device, image_size, config, use_depth16, ndc_range)
+  p = _tile_params(cap, image_size, config, use_depth16)
+  stream = N.stream_ptr(device)
+  f.counts = torch.empty((cap,), dtype=torch.int32, device=device)
+  f.masks = torch.empty((cap,), dtype=torch.int64, device=device)
+  f.cum = torch.empty((cap + 1,), dtype=torch.int32, device=device)
+  total_dev = torch.empty((1,), dtype=torch.int32, device=device)
+  lib = N.lib()
+  if cap > 0:
+    N.call("gs_tile_count_perm_counted", ctypes.byref(p), N.ptr(points_capacity), N.ptr(f.perm), N.ptr(count_device),
+           N.ptr(f.counts), N.ptr(f.masks), stream)
+  ws = N.workspace(lib.gs_full_cumsum_workspace_bytes(cap, 4), device)
+  N.call("gs_full_cumsum_counted", ctypes.c_int64(cap), ctypes.c_int32(4), N.ptr(count_device), N.ptr(f.counts),
+         N.ptr(f.cum), N.ptr(total_dev), N.ptr(ws), ctypes.c_size_t(ws.numel()), stream)
+  f.host_total = _pinned_total(device)
+  f.host_total.copy_(total_dev, non_blocking=True)
+  f.total_ready = torch.cuda.Event()
+  f.total_ready.record(torch.cuda.current_stream(device))
+  return f
+
+
 def _map_to_tiles(gaussians, depth, image_size, config, use_depth16=False, ndc_range=None, depth_order=None,
-                  before_total_sync=None):
+                  before_total_sync=None, front=None):
   """map_to_tiles; with ``ndc_range=(near, far)`` the ``depth`` column is LINEAR camera depth and the sort depth is
   its NDC value, formed inside the key kernel with torch's own f32 operation sequence (bit-identical keys to
   ``map_to_tiles(g, ndc_depth(depth, near, far), ...)`` — tests/test_gpu_tile_mapper.py), which saves the
   render path four elementwise launches per frame (render_projected).  ``depth_order``: the (n,) permutation already
   produced by launch_depth_order_counted for exactly these depths.  ``before_total_sync()``: called once, after the
   overlap scan is enqueued and before the host waits for the overlap total — the caller's chance to enqueue work that
-  does not depend on the tile map, so that the GPU is busy across that read-back."""
+  does not depend on the tile map, so that the GPU is busy across that read-back.  ``front``: the MapperFront of
+  launch_mapper_front_counted for exactly these gaussians (then ``depth_order`` is not needed)."""
   shape = _check_inputs(gaussians, depth, image_size, config)
   near, far = (float(ndc_range[0]), float(ndc_range[1])) if ndc_range is not None else (0.0, 0.0)
   with torch.no_grad():
@@ -132,7 +170,15 @@ def _map_to_tiles(gaussians, depth, image_size, config, use_depth16=False, ndc_r
     tile_ranges = torch.empty((*shape, 2), dtype=torch.int32, device=device)
 
     total = 0
-    if n > 0:
+    if n > 0 and front is not None:
+      perm, masks, cum = front.perm, front.masks, front.cum
+      tile_bits = max(1, (shape[0] * shape[1] - 1).bit_length())
+      if before_total_sync is not None:
+        before_total_sync()
+        before_total_sync = None
+      front.total_ready.synchronize()
+      total = int(front.host_total.item())
+    elif n > 0:
       if depth_order is not None:
         assert depth_order.shape == (n,) and depth_order.dtype == torch.int32 and depth_order.is_contiguous()
         perm = depth_order

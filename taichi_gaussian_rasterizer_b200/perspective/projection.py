@@ -63,7 +63,7 @@ class _ProjectFunction(torch.autograd.Function):
       host_count.copy_(count, non_blocking=True)
       ready = torch.cuda.Event()
       ready.record(torch.cuda.current_stream(device))
-      after_launch(indexes, count, depth)
+      after_launch(indexes, count, depth, points)
       ready.synchronize()
       v = int(host_count.item())
     points, depth, indexes = points[:v], depth[:v], indexes[:v]
@@ -115,7 +115,7 @@ def apply(position: torch.Tensor, log_scaling: torch.Tensor,
           alpha_threshold: float = 1. / 255.,
           after_launch=None
           ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-  """``after_launch(indexes_capacity, count_device, depth_capacity)`` (extension): called after the projection kernel is enqueued and
+  """``after_launch(indexes_capacity, count_device, depth_capacity, points_capacity)`` (extension): called after the projection kernel is enqueued and
   before the visible count is read back; see render_gaussians."""
   dtype = position.dtype
   N.require_cuda(position, log_scaling, rotation, alpha_logit, T_camera_world, projection)

@@ -12,7 +12,7 @@ import torch
 from beartype import beartype
 
 from .data_types import Gaussians3D, RasterConfig
-from .mapper.tile_mapper import _map_to_tiles, launch_depth_order_counted, map_to_tiles
+from .mapper.tile_mapper import _map_to_tiles, launch_mapper_front_counted, map_to_tiles
 from .perspective import CameraParams
 from .perspective.projection import project_to_image
 from .rasterizer.function import rasterize_with_tiles
@@ -59,11 +59,12 @@ def render_gaussians(
   assert sh_colors is None or sh_early, "sh_colors needs use_sh and contiguous features / positions of one dtype"
 
   # Work that only needs the device-side visible set is enqueued right behind the projection kernel, BEFORE the host
-  # blocks on the visible count, so that the GPU does not idle across that read-back and the host's launches after it:
-  # the depth ordering of the tile mapper (0.18 ms at 3 M gaussians).
-  def early_work(indexes_capacity, count_device, depth_capacity):
-    early["order"] = launch_depth_order_counted(depth_capacity, count_device, camera_params.image_size, config,
-                                                use_depth16, (camera_params.near_plane, camera_params.far_plane))
+  # blocks on the visible count: the front half of the tile mapper (depth ordering, overlap count, scan: 0.3 ms at 3 M
+  # gaussians), so that the GPU idles neither across that read-back nor during the host's work after it.
+  def early_work(indexes_capacity, count_device, depth_capacity, points_capacity):
+    early["front"] = launch_mapper_front_counted(points_capacity, depth_capacity, count_device,
+                                                 camera_params.image_size, config, use_depth16,
+                                                 (camera_params.near_plane, camera_params.far_plane))
   gaussians2d, depths, indexes = project_to_image(gaussians, camera_params, config,
                                                   after_launch=early_work if order_early else None)
 
@@ -91,10 +92,9 @@ def render_gaussians(
     features = gaussians.feature[indexes]
     assert len(features.shape) == 2, f"Features must be (N, C) if use_sh=False, got {features.shape}"
 
-  order = early["order"][:indexes.shape[0]] if "order" in early else None
   return render_projected(indexes, gaussians2d, features, depths, camera_params, config,
                           render_depth=render_depth, use_depth16=use_depth16,
-                          render_median_depth=render_median_depth, depth_order=order,
+                          render_median_depth=render_median_depth, mapper_front=early.get("front"),
                           before_total_sync=fill_features)
 
 
@@ -124,11 +124,11 @@ def render_projected(indexes: torch.Tensor, gaussians2d: torch.Tensor,
                      camera_params: CameraParams, config: RasterConfig,
                      render_depth: bool = False, use_depth16: bool = False,
                      render_median_depth: bool = False, use_ndc_depth: bool = False,
-                     depth_order: Optional[torch.Tensor] = None, before_total_sync=None):
+                     mapper_front=None, before_total_sync=None):
   """Tile-map and rasterize gaussians that are already projected (renderer.py:183-231 of the reference).
   Gaussians are ordered by NDC depth inside every tile; depth features stay linear unless use_ndc_depth.
-  ``depth_order`` (extension): the NDC depth ordering of exactly these gaussians when render_gaussians has already
-  enqueued it (mapper.tile_mapper.launch_depth_order_counted); ``before_total_sync``: see _map_to_tiles (called exactly
+  ``mapper_front`` (extension): the front half of the tile mapping of exactly these gaussians when render_gaussians has
+  already enqueued it (mapper.tile_mapper.launch_mapper_front_counted); ``before_total_sync``: see _map_to_tiles (called exactly
   once before the rasterizer is enqueued)."""
   size = camera_params.image_size
   ndc_range = (camera_params.near_plane, camera_params.far_plane)
@@ -149,7 +149,7 @@ def render_projected(indexes: torch.Tensor, gaussians2d: torch.Tensor,
                                                  use_depth16=use_depth16)
   else:
     overlap_to_point, tile_ranges = _map_to_tiles(gaussians2d, depths, size, config, use_depth16, ndc_range=ndc_range,
-                                                  depth_order=depth_order, before_total_sync=before_total_sync)
+                                                  front=mapper_front, before_total_sync=before_total_sync)
   ranges = tile_ranges.view(-1, 2)
   raster = rasterize_with_tiles(gaussians2d, features, tile_overlap_ranges=ranges,
                                 overlap_to_point=overlap_to_point, image_size=size, config=config)
