@@ -32,7 +32,6 @@
 
 namespace gs {
 
-constexpr int kBwdBatch = 64;
 
 // The ellipse alpha0 p = thr in the form q(d) = d^T A d = qlim (log2 domain), for the block tests.
 struct CullConic {
@@ -63,21 +62,26 @@ __device__ __forceinline__ bool conic_may_touch(const CullConic& c, float x0, fl
 
 // NSUB = 4: two warps per tile, each owns a 16x8 region; NSUB = 8: one warp owns the whole 16x16 tile.
 // A region is NSUB sub-blocks of 8x4 pixels; lane l owns pixel (l & 7, l >> 3) of every sub-block.
-template <int F, int FP, bool HEUR, int NSUB>
-__global__ void __launch_bounds__((8 / NSUB) * 32)
+// SOLO: one warp per CTA ((8 / NSUB) CTAs per tile): every warp stages the tile list for itself and never waits for
+// its neighbour at a block barrier.
+template <int F, int FP, bool HEUR, int NSUB, bool SOLO = false, int BATCH = 64>
+__global__ void __launch_bounds__(SOLO ? 32 : (8 / NSUB) * 32)
 raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
                        const float* __restrict__ featP, const int32_t* __restrict__ ranges,
                        const int32_t* __restrict__ o2p, const float* __restrict__ image,
                        const float* __restrict__ grad_image, float* __restrict__ grad_pts,
                        float* __restrict__ grad_feat, float* __restrict__ heuristic) {
-  constexpr int kThreads = (8 / NSUB) * 32;
+  constexpr int kThreads = SOLO ? 32 : (8 / NSUB) * 32;
+  constexpr int kBwdBatch = BATCH;   // staged tile-list entries per buffer
   constexpr int NM = 6;  // moments: g, g u, g w, g u^2, g w^2, g u w
   constexpr int NV = NM + F + (HEUR ? 2 : 0);
   __shared__ __align__(16) float4 s_r0[2][kBwdBatch];
   __shared__ __align__(16) float4 s_r1[2][kBwdBatch];
   __shared__ __align__(16) float s_feat[2][kBwdBatch][FP];
 
-  const int tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int t = threadIdx.x, lane = t & 31;
+  const int tile = SOLO ? blockIdx.x / (8 / NSUB) : blockIdx.x;
+  const int warp = SOLO ? blockIdx.x % (8 / NSUB) : t >> 5;
   const int tw = (p.image_width + kFastTile - 1) / kFastTile;
   const int ox = (tile % tw) * kFastTile, oy = (tile / tw) * kFastTile + warp * (NSUB * 2);
   const int x0 = ox + (lane & 7), y0 = oy + (lane >> 3);
@@ -151,7 +155,7 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
     } else {
       cp_async_wait<0>();
     }
-    __syncthreads();
+    if (SOLO) __syncwarp(); else __syncthreads();
     const int n_in = min(kBwdBatch, C - b * kBwdBatch);
     if (!warp_done) {
       for (int c0 = 0; c0 < n_in; c0 += 32) {
@@ -238,7 +242,12 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
       }
       warp_done = __all_sync(kFull, lane_done());
     }
-    if (__syncthreads_and(warp_done)) break;
+    if (SOLO) {
+      __syncwarp();   // the buffer this iteration read is the one the next issue_load overwrites
+      if (warp_done) break;
+    } else if (__syncthreads_and(warp_done)) {
+      break;
+    }
   }
   cp_async_wait<0>();
 }
@@ -281,9 +290,24 @@ static int launch_bwd_fast(const GsRasterParams& p, const RasterArgs& a, const f
       p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,   \
       (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr)
   // NSUB = 4 (two warps per tile) measured faster than NSUB = 8 (one warp per tile, 96 registers): 1.58 vs 1.70 ms
-  static const int nsub = getenv("GS_BWD_NSUB") ? atoi(getenv("GS_BWD_NSUB")) : 4;   // experiment switch
-  if (nsub == 8) { if (heur) GS_BWD_LAUNCH(true, 8); else GS_BWD_LAUNCH(false, 8); }
+  static const int nsub = getenv("GS_BWD_NSUB") ? atoi(getenv("GS_BWD_NSUB")) : 4;   // experiment switches
+  static const int solo = getenv("GS_BWD_SOLO") ? atoi(getenv("GS_BWD_SOLO")) : 1;   // measured: 1.236 vs 1.251 ms
+  static const int batch = getenv("GS_BWD_BATCH") ? atoi(getenv("GS_BWD_BATCH")) : 64;
+#define GS_BWD_LAUNCH_SOLO_(HEURV, BATCHV)                                                                       \
+  raster_bwd_fast_kernel<F, FP, HEURV, 4, true, BATCHV><<<tiles * 2, 32, 0, st>>>(                              \
+      p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,   \
+      (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr)
+#define GS_BWD_LAUNCH_SOLO(HEURV)                                  \
+  do {                                                             \
+    if (batch == 32) GS_BWD_LAUNCH_SOLO_(HEURV, 32);               \
+    else if (batch == 128) GS_BWD_LAUNCH_SOLO_(HEURV, 128);        \
+    else GS_BWD_LAUNCH_SOLO_(HEURV, 64);                           \
+  } while (0)
+  if (solo) { if (heur) GS_BWD_LAUNCH_SOLO(true); else GS_BWD_LAUNCH_SOLO(false); }
+  else if (nsub == 8) { if (heur) GS_BWD_LAUNCH(true, 8); else GS_BWD_LAUNCH(false, 8); }
   else if (heur) GS_BWD_LAUNCH(true, 4); else GS_BWD_LAUNCH(false, 4);
+#undef GS_BWD_LAUNCH_SOLO
+#undef GS_BWD_LAUNCH_SOLO_
 #undef GS_BWD_LAUNCH
   GS_LAUNCH_CHECK();
   if (p.points_requires_grad && a.grad_gaussians != nullptr && p.num_points > 0) {
