@@ -38,7 +38,7 @@ _pinned = {}
 def _pinned_total(device) -> torch.Tensor:
   """One pinned int32 per device for the asynchronous read-back of the overlap total (reads are serialised by the
   event wait that follows each copy)."""
-  key = (device.type, device.index)
+  key = (device.type, device.index, N.stream_ptr(device).value)   # one word per stream: streams do not serialise
   if key not in _pinned:
     _pinned[key] = torch.zeros((1,), dtype=torch.int32).pin_memory()
   return _pinned[key]
