@@ -94,11 +94,35 @@ class GradientBucket:
     return self.flat.numel() * self.flat.element_size()
 
   def all_reduce(self, group=None, async_op: bool = False):
-    """Sum the bucket over ranks (no-op without an initialised process group / single rank)."""
-    self.flush()
-    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+    """Sum the bucket over ranks (no-op without an initialised process group / single rank).  With deferred SH
+    gradients pending, the part of the bucket that is already final (the geometry gradients in front of the SH slices)
+    is reduced while the flush kernel forms the SH rows, then the SH part follows."""
+    active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if not active:
+      self.flush()
       return None
-    return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    from . import grad_sinks
+    pending = [p for p in self.params if (d := grad_sinks.deferred_sh(p)) is not None and (d.pending or d.overwrite_next)]
+    split = None
+    if pending and not async_op:
+      # element offset of the first pending parameter; everything behind it must be pending too (the usual layout:
+      # [position, log_scaling, rotation, alpha_logit | feature])
+      off, offs = 0, {}
+      for p in self.params:
+        offs[id(p)] = off
+        off += p.numel()
+      first = min(offs[id(p)] for p in pending)
+      tail = [p for p in self.params if offs[id(p)] >= first]
+      if 0 < first and all(any(q is p for q in pending) for p in tail):
+        split = first
+    if split is None:
+      self.flush()
+      return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    head = dist.all_reduce(self.flat[:split], op=dist.ReduceOp.SUM, group=group, async_op=True)
+    self.flush()
+    dist.all_reduce(self.flat[split:], op=dist.ReduceOp.SUM, group=group)
+    head.wait()
+    return None
 
 
 def all_reduce_statistics(tensors: Iterable[Optional[torch.Tensor]], group=None):
