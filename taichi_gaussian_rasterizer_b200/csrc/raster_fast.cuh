@@ -15,10 +15,11 @@ inline int fast_feature_pad(int F) { return F <= 4 ? 4 : F <= 8 ? 8 : F <= 16 ? 
 // Workspace layout (all 256 B aligned):
 //   recF  V x 2 float4 : {mx, my, a1x, a1y} {a2x, a2y, log2(alpha), idx}       (forward records)
 //   featP V x FP float  : features padded to FP
+//   mask  K bytes        : per tile-list entry, which of the tile's eight 8x4 pixel blocks it can reach
 //   recB  V x 2 float4 : {mx, my, ax, ay} {1/sx, 1/sy, alpha, idx}             (records of the wide backward, F > 7;
 //                                                                               the narrow one walks recF)
 struct FastLayout {
-  size_t off_recF, off_feat, off_recB, total;
+  size_t off_recF, off_feat, off_recB, off_mask, total;
   int FP;
 };
 
@@ -30,6 +31,8 @@ inline FastLayout fast_layout(const GsRasterParams& p) {
   L.off_recF = off; off += align_up(V * 32, 256);
   L.off_feat = off; off += align_up(V * (size_t)L.FP * 4, 256);
   L.off_recB = off; off += align_up(V * 32, 256);
+  // one byte per tile-list entry: bit w = the entry can reach the 8x4 pixel block w of its tile (raster_cull_mask)
+  L.off_mask = off; off += align_up((size_t)(p.num_overlaps > 0 ? p.num_overlaps : 1), 256);
   L.total = off;
   return L;
 }
@@ -121,6 +124,8 @@ __device__ __forceinline__ int reduce_owner(int lane) {
 }
 
 int raster_fast_pack(const GsRasterParams& p, const RasterArgs& a, bool forward, bool features, cudaStream_t st);
+// cull masks of every tile-list entry against the eight 8x4 pixel blocks of its tile (needs the forward records)
+int raster_cull_mask(const GsRasterParams& p, const RasterArgs& a, cudaStream_t st);
 
 // raster_fast_bwd_wide.cu: backward for 8..64 feature channels (one pixel per lane, image gradient in registers)
 int raster_bwd_wide(const GsRasterParams& p, const RasterArgs& a, const float4* rec, const float* featP, cudaStream_t st);

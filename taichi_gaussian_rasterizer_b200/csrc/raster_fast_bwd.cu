@@ -8,9 +8,10 @@
 //     same pixel of each sub-block, so a splat that reaches one or two sub-blocks costs one or two evaluations
 //     per lane instead of four (the reference's 2x2 quads always pay four);
 //   * cp.async double-buffered staging of 32 B records + padded feature rows, batches of 64;
-//   * lane-parallel cull: 32 gaussians at a time, one per lane, each tested against the four sub-blocks (exact
-//     minimum of the ellipse's quadratic form over the block) -> four ballot masks; a sub-block is evaluated only
-//     if its bit is set (warp-uniform branch);
+//   * cull: raster_cull_mask_kernel (raster_fast_fwd.cu) has tested every tile-list entry against the eight 8x4
+//     blocks of its tile once per frame (exact minimum of the ellipse's quadratic form over the block); the byte
+//     is staged with the entry and turned into four ballot masks; a sub-block is evaluated only if its bit is set
+//     (warp-uniform branch);
 //   * per pixel state is {W, G_c, RG = sum_c R_c G_c}: the replay needs the remaining features only through R . G
 //     (dL/dalpha = T (f . G) - (R . G) / (1 - alpha), and R_c -= f_c w  <=>  RG -= (f . G) w), which halves the
 //     per hit arithmetic and the register state compared with carrying R_c;
@@ -33,33 +34,6 @@
 namespace gs {
 
 
-// The ellipse alpha0 p = thr in the form q(d) = d^T A d = qlim (log2 domain), for the block tests.
-struct CullConic {
-  float mx, my, A00, A01, A11, r00, r11, qlim;
-};
-
-__device__ __forceinline__ CullConic make_cull_conic(const float4 r0, const float4 r1, float l2thr) {
-  CullConic c;   // forward record: {mx, my, a1x, a1y} {a2x, a2y, log2(alpha0), idx}, a1 / a2 = scaled axes
-  const float a1x = r0.z, a1y = r0.w, a2x = r1.x, a2y = r1.y;
-  c.mx = r0.x; c.my = r0.y;
-  c.A00 = a1x * a1x + a2x * a2x; c.A01 = a1x * a1y + a2x * a2y; c.A11 = a1y * a1y + a2y * a2y;
-  c.r00 = fast_rcp(c.A00); c.r11 = fast_rcp(c.A11);
-  c.qlim = (r1.z - l2thr) * 1.001f + 1e-3f;
-  return c;
-}
-
-// Exact minimum of q over the rectangle of pixel centres [x0, x1] x [y0, y1] (see block_may_touch).
-__device__ __forceinline__ bool conic_may_touch(const CullConic& c, float x0, float x1, float y0, float y1) {
-  const float dx0 = x0 - c.mx, dx1 = x1 - c.mx, dy0 = y0 - c.my, dy1 = y1 - c.my;
-  const float dxc = fminf(fmaxf(0.f, dx0), dx1);
-  const float dyc = fminf(fmaxf(0.f, dy0), dy1);
-  const float dyv = fminf(fmaxf(-c.A01 * dxc * c.r11, dy0), dy1);
-  const float qv = c.A00 * dxc * dxc + 2.f * c.A01 * dxc * dyv + c.A11 * dyv * dyv;
-  const float dxh = fminf(fmaxf(-c.A01 * dyc * c.r00, dx0), dx1);
-  const float qh = c.A00 * dxh * dxh + 2.f * c.A01 * dxh * dyc + c.A11 * dyc * dyc;
-  return fminf(qv, qh) < c.qlim;
-}
-
 // NSUB = 4: two warps per tile, each owns a 16x8 region; NSUB = 8: one warp owns the whole 16x16 tile.
 // A region is NSUB sub-blocks of 8x4 pixels; lane l owns pixel (l & 7, l >> 3) of every sub-block.
 // SOLO: one warp per CTA ((8 / NSUB) CTAs per tile): every warp stages the tile list for itself and never waits for
@@ -70,7 +44,8 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
                        const float* __restrict__ featP, const int32_t* __restrict__ ranges,
                        const int32_t* __restrict__ o2p, const float* __restrict__ image,
                        const float* __restrict__ grad_image, float* __restrict__ grad_pts,
-                       float* __restrict__ grad_feat, float* __restrict__ heuristic) {
+                       float* __restrict__ grad_feat, float* __restrict__ heuristic,
+                       const unsigned char* __restrict__ cull_mask) {
   constexpr int kThreads = SOLO ? 32 : (8 / NSUB) * 32;
   constexpr int kBwdBatch = BATCH;   // staged tile-list entries per buffer
   constexpr int NM = 6;  // moments: g, g u, g w, g u^2, g w^2, g u w
@@ -78,6 +53,7 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
   __shared__ __align__(16) float4 s_r0[2][kBwdBatch];
   __shared__ __align__(16) float4 s_r1[2][kBwdBatch];
   __shared__ __align__(16) float s_feat[2][kBwdBatch][FP];
+  __shared__ unsigned char s_mask[2][kBwdBatch];   // cull bytes of the staged entries (raster_cull_mask_kernel)
 
   const int t = threadIdx.x, lane = t & 31;
   const int tile = SOLO ? blockIdx.x / (8 / NSUB) : blockIdx.x;
@@ -130,10 +106,12 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
       const int v = b * kBwdBatch + s;
       if (v < C) {
         const int idx = o2p[start + v];
+        const unsigned char m = cull_mask[start + v];   // in flight together with the index load
         cp_async16(&s_r0[buf][s], rec + 2 * (int64_t)idx);
         cp_async16(&s_r1[buf][s], rec + 2 * (int64_t)idx + 1);
 #pragma unroll
         for (int c = 0; c < FP; c += 4) cp_async16(&s_feat[buf][s][c], featP + (int64_t)idx * FP + c);
+        s_mask[buf][s] = m;
       }
     }
     cp_async_commit();
@@ -160,22 +138,12 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
     if (!warp_done) {
       for (int c0 = 0; c0 < n_in; c0 += 32) {
         const int e = c0 + lane;
-        // lane-parallel cull: gaussian e against each of the region's sub-blocks
+        // cull: bit (warp NSUB + i) of the entry's byte = it can reach sub-block i of this warp's region
         unsigned bm[NSUB];
         {
-          bool hit[NSUB];
+          const unsigned m = e < n_in ? (unsigned)s_mask[buf][e] >> (warp * NSUB) : 0u;
 #pragma unroll
-          for (int i = 0; i < NSUB; ++i) hit[i] = false;
-          if (e < n_in) {
-            const CullConic cc = make_cull_conic(s_r0[buf][e], s_r1[buf][e], l2thr);
-#pragma unroll
-            for (int i = 0; i < NSUB; ++i) {
-              const float sx0 = bx + 8.f * (i & 1), sy0 = by + 4.f * (i >> 1);
-              hit[i] = conic_may_touch(cc, sx0, sx0 + 7.f, sy0, sy0 + 3.f);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < NSUB; ++i) bm[i] = __ballot_sync(kFull, hit[i]);
+          for (int i = 0; i < NSUB; ++i) bm[i] = __ballot_sync(kFull, (m >> i) & 1u);
         }
         unsigned any = 0;
 #pragma unroll
@@ -285,10 +253,11 @@ static int launch_bwd_fast(const GsRasterParams& p, const RasterArgs& a, const f
                            cudaStream_t st) {
   const int tiles = tiles_wide(p) * tiles_high(p);
   const bool heur = p.compute_point_heuristic && a.point_heuristic != nullptr;
+  const unsigned char* cmask = (const unsigned char*)a.workspace + fast_layout(p).off_mask;
 #define GS_BWD_LAUNCH(HEURV, NSUBV)                                                                              \
   raster_bwd_fast_kernel<F, FP, HEURV, NSUBV><<<tiles, (8 / NSUBV) * 32, 0, st>>>(                              \
       p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,   \
-      (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr)
+      (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr, cmask)
   // NSUB = 4 (two warps per tile) measured faster than NSUB = 8 (one warp per tile, 96 registers): 1.58 vs 1.70 ms
   static const int nsub = getenv("GS_BWD_NSUB") ? atoi(getenv("GS_BWD_NSUB")) : 4;   // experiment switches
   static const int solo = getenv("GS_BWD_SOLO") ? atoi(getenv("GS_BWD_SOLO")) : 1;   // measured: 1.236 vs 1.251 ms
@@ -296,7 +265,7 @@ static int launch_bwd_fast(const GsRasterParams& p, const RasterArgs& a, const f
 #define GS_BWD_LAUNCH_SOLO_(HEURV, BATCHV)                                                                       \
   raster_bwd_fast_kernel<F, FP, HEURV, 4, true, BATCHV><<<tiles * 2, 32, 0, st>>>(                              \
       p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,   \
-      (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr)
+      (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr, cmask)
 #define GS_BWD_LAUNCH_SOLO(HEURV)                                  \
   do {                                                             \
     if (batch == 32) GS_BWD_LAUNCH_SOLO_(HEURV, 32);               \
@@ -324,6 +293,10 @@ int raster_bwd_fast(const GsRasterParams& p, const RasterArgs& a, cudaStream_t s
   if (!p.workspace_holds_packed) {  // otherwise gs_raster_fwd (called with the requires_grad flags) left both there
     int rc = raster_fast_pack(p, a, /*forward=*/false, /*features=*/true, st);
     if (rc != GS_OK) return rc;
+    if (p.num_features <= 7) {   // the narrow kernel reads the cull masks the forward would have left
+      rc = raster_cull_mask(p, a, st);
+      if (rc != GS_OK) return rc;
+    }
   }
   const FastLayout L = fast_layout(p);
   unsigned char* ws = (unsigned char*)a.workspace;

@@ -6,10 +6,12 @@
 //   * one CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel block (one pixel per lane);
 //   * the tile's sorted gaussians are staged in batches of 128 through shared memory with cp.async
 //     (16 B gathers of pre-packed 32 B records + padded feature rows), double buffered;
-//   * per batch each warp first tests 32 gaussians at a time, one per lane, against ITS pixel block
-//     (exact minimum of the ellipse's quadratic form over the block) and then only walks the survivors
-//     (ballot mask) — a gaussian that cannot pass alpha_threshold anywhere in the block contributes
-//     exactly nothing, so results do not change, but most (warp, gaussian) pairs of a tile list vanish;
+//   * raster_cull_mask_kernel tests every tile-list entry ONCE per frame against the eight 8x4 pixel blocks of
+//     its tile (exact minimum of the ellipse's quadratic form over the block) and leaves a byte per entry; the
+//     byte is staged with the entry, each warp gathers its bit into ballot masks and only walks the survivors —
+//     a gaussian that cannot pass alpha_threshold anywhere in the block contributes exactly nothing, so results
+//     do not change, but most (warp, gaussian) pairs of a tile list vanish (the test used to run in every warp
+//     of both rasterizer passes: 17 % of the forward's instructions);
 //   * exp via ex2.approx on a pre-scaled exponent (alpha = 2^(log2 alpha0 - |M d|^2));
 //   * a warp stops when every lane's transmittance is <= forward_exit_transmittance (0 = exact: no
 //     later term can change anything); the CTA stops when all warps have;
@@ -78,6 +80,54 @@ int raster_fast_pack(const GsRasterParams& p, const RasterArgs& a, bool forward,
   return GS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ cull masks
+// One pass over the tile lists: entry k of tile t gets a byte whose bit w says whether the gaussian can pass
+// alpha_threshold anywhere in the 8x4 pixel block w of the tile (w = 2 * block row + block column; exact minimum of
+// the ellipse's quadratic form over the block, with the slack of block_may_touch).  The forward (eight warps, one block
+// each) and the narrow backward (two warps, four blocks each) read the byte instead of repeating the test per warp.
+__global__ void __launch_bounds__(128)
+raster_cull_mask_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
+                        const int32_t* __restrict__ ranges, const int32_t* __restrict__ o2p,
+                        unsigned char* __restrict__ mask) {
+  const int tile = blockIdx.x;
+  const int tw = (p.image_width + kFastTile - 1) / kFastTile;
+  const float x0 = (float)((tile % tw) * kFastTile) + 0.5f, y0 = (float)((tile / tw) * kFastTile) + 0.5f;
+  const float l2thr = log2f((float)p.alpha_threshold);
+  const int start = ranges[2 * tile], end = ranges[2 * tile + 1];
+  for (int k = start + threadIdx.x; k < end; k += blockDim.x) {
+    const int idx = o2p[k];
+    const float4 r0 = rec[2 * (int64_t)idx], r1 = rec[2 * (int64_t)idx + 1];
+    const float a1x = r0.z, a1y = r0.w, a2x = r1.x, a2y = r1.y;
+    const float A00 = a1x * a1x + a2x * a2x, A01 = a1x * a1y + a2x * a2y, A11 = a1y * a1y + a2y * a2y;
+    const float n01r11 = -A01 * fast_rcp(A11), n01r00 = -A01 * fast_rcp(A00);
+    const float qlim = (r1.z - l2thr) * 1.001f + 1e-3f;
+    unsigned bits = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float dx0 = x0 + (float)((w & 1) * 8) - r0.x, dx1 = dx0 + 7.f;
+      const float dy0 = y0 + (float)((w >> 1) * 4) - r0.y, dy1 = dy0 + 3.f;
+      const float dxc = fminf(fmaxf(0.f, dx0), dx1), dyc = fminf(fmaxf(0.f, dy0), dy1);
+      const float dyv = fminf(fmaxf(n01r11 * dxc, dy0), dy1);
+      const float qv = A00 * dxc * dxc + 2.f * A01 * dxc * dyv + A11 * dyv * dyv;
+      const float dxh = fminf(fmaxf(n01r00 * dyc, dx0), dx1);
+      const float qh = A00 * dxh * dxh + 2.f * A01 * dxh * dyc + A11 * dyc * dyc;
+      bits |= (fminf(qv, qh) < qlim ? 1u : 0u) << w;
+    }
+    mask[k] = (unsigned char)bits;
+  }
+}
+
+int raster_cull_mask(const GsRasterParams& p, const RasterArgs& a, cudaStream_t st) {
+  if (p.num_overlaps == 0) return GS_OK;
+  const FastLayout L = fast_layout(p);
+  unsigned char* ws = (unsigned char*)a.workspace;
+  const int tiles = tiles_wide(p) * tiles_high(p);
+  raster_cull_mask_kernel<<<tiles, 128, 0, st>>>(p, (const float4*)(ws + L.off_recF), a.tile_ranges, a.overlap_to_point,
+                                                 ws + L.off_mask);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 // BATCH = staged tile-list entries per buffer: 128 for narrow features, 64 for FP >= 16 (shared memory budget).
 // FOURTH: with FP = 4 the fourth accumulator is only needed when F = 4 (it is padding for F <= 3).
@@ -86,12 +136,13 @@ __global__ void __launch_bounds__(kFwdThreads)
 raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
                        const float* __restrict__ featP, const int32_t* __restrict__ ranges,
                        const int32_t* __restrict__ o2p, float* __restrict__ image, float* __restrict__ image_alpha,
-                       float* __restrict__ visibility) {
+                       float* __restrict__ visibility, const unsigned char* __restrict__ cull_mask) {
   constexpr int kFwdBatch = BATCH;
   // one staged entry = {record (2 x float4), feature row (FP / 4 x float4)} in consecutive 16 B units: one address
   // per entry in the inner loop.  U is odd so that a lane-per-entry LDS.128 (the cull) is bank-conflict free.
   constexpr int U = (2 + FP / 4) | 1;
   __shared__ __align__(16) float4 s_e[2][kFwdBatch][U];
+  __shared__ unsigned char s_mask[2][kFwdBatch];   // cull bytes of the staged entries (raster_cull_mask_kernel)
 
   const int tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int tw = (p.image_width + kFastTile - 1) / kFastTile;
@@ -127,8 +178,10 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
         const int k = v < C ? v : v - kFastTileArea;
         const int idx = o2p[start + k];
         if (t < kFwdBatch) {
+          const unsigned char m = cull_mask[start + k];   // in flight together with the index load
           cp_async16(&s_e[buf][slot][0], rec + 2 * (int64_t)idx);
           cp_async16(&s_e[buf][slot][1], rec + 2 * (int64_t)idx + 1);
+          s_mask[buf][slot] = m;
         } else {
 #pragma unroll
           for (int c = 0; c < FP; c += 4) cp_async16(&s_e[buf][slot][2 + c / 4], featP + (int64_t)idx * FP + c);
@@ -138,9 +191,12 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
       if (t < kFwdBatch) {
         const int v = b * kFwdBatch + t;
         if (v < total) {
-          const int idx = o2p[start + (v < C ? v : v - kFastTileArea)];
+          const int k = v < C ? v : v - kFastTileArea;
+          const int idx = o2p[start + k];
+          const unsigned char m = cull_mask[start + k];
           cp_async16(&s_e[buf][t][0], rec + 2 * (int64_t)idx);
           cp_async16(&s_e[buf][t][1], rec + 2 * (int64_t)idx + 1);
+          s_mask[buf][t] = m;
         }
       }
       constexpr int CH = FP / 4;
@@ -174,11 +230,7 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
     if (!warp_done) {
       for (int c0 = 0; c0 < n_in; c0 += 32) {
         const int e = c0 + lane;
-        bool hit = false;
-        if (e < n_in) {
-          const float4 r0 = s_e[buf][e][0], r1 = s_e[buf][e][1];
-          hit = block_may_touch(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z - l2thr, bx0, bx1, by0, by1);
-        }
+        const bool hit = e < n_in && ((s_mask[buf][e] >> warp) & 1u);
         unsigned mask = __ballot_sync(kFull, hit);
         while (mask) {
           const int j = c0 + __ffs(mask) - 1;
@@ -240,8 +292,11 @@ size_t raster_fast_workspace_bytes(const GsRasterParams& p) { return fast_layout
 int raster_fwd_fast(const GsRasterParams& p, const RasterArgs& a, cudaStream_t st) {
   int rc = raster_fast_pack(p, a, /*forward=*/true, /*features=*/true, st);
   if (rc != GS_OK) return rc;
+  rc = raster_cull_mask(p, a, st);
+  if (rc != GS_OK) return rc;
   const FastLayout L = fast_layout(p);
   unsigned char* ws = (unsigned char*)a.workspace;
+  const unsigned char* cmask = ws + L.off_mask;
   const float4* rec = (const float4*)(ws + L.off_recF);
   const float* featP = (const float*)(ws + L.off_feat);
   const int tiles = tiles_wide(p) * tiles_high(p);
@@ -251,11 +306,11 @@ int raster_fwd_fast(const GsRasterParams& p, const RasterArgs& a, cudaStream_t s
     if (FPV == 4 && p.num_features < 4)                                                                            \
       raster_fwd_fast_kernel<FPV, VISV, BATCHV, false><<<tiles, kFwdThreads, 0, st>>>(                             \
           p, rec, featP, a.tile_ranges, a.overlap_to_point, (float*)a.image, (float*)a.image_alpha,                \
-          (float*)a.visibility);                                                                                   \
+          (float*)a.visibility, cmask);                                                                            \
     else                                                                                                           \
       raster_fwd_fast_kernel<FPV, VISV, BATCHV, true><<<tiles, kFwdThreads, 0, st>>>(                              \
           p, rec, featP, a.tile_ranges, a.overlap_to_point, (float*)a.image, (float*)a.image_alpha,                \
-          (float*)a.visibility);                                                                                   \
+          (float*)a.visibility, cmask);                                                                            \
   } while (0)
 #define GS_FWD_CASE(FPV, BATCHV) \
   case FPV: if (vis) GS_FWD_LAUNCH(FPV, true, BATCHV); else GS_FWD_LAUNCH(FPV, false, BATCHV); break
