@@ -610,7 +610,9 @@ project_bwd_kernel(const __grid_constant__ GsProjectParams p, int64_t num_visibl
     }
     cam_grad[12] = dfx; cam_grad[13] = dfy; cam_grad[14] = dcx; cam_grad[15] = dcy;
 
-    auto put = [](T* dst, T v) { *dst = ACC ? *dst + v : v; };  // rows are unique: plain read-modify-write
+    // ACC: rows are unique, so a reduction without return value (red.global.add, resolved at the L2) gives the same
+    // sum as a read-modify-write and the thread does not wait for eleven loads at its very end
+    auto put = [](T* dst, T v) { if (ACC) red_add(dst, v); else *dst = v; };
     if (g_position) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) put(g_position + 3 * idx + k, d_pos[k]);
