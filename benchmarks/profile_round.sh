@@ -15,5 +15,5 @@ SMALL="python bench.py --no-cpu-baseline --steps 2 --warmup 1 --views-per-rank 2
 $SMALL > $OUT/plain_$TAG.log 2>&1; echo "plain rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches_$TAG.csv $SMALL > $OUT/ncu_launches_$TAG.log 2>&1; echo "launch list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'raster_.wd_fast' -s 6 -c 2 -f -o $OUT/prof_raster_$TAG $SMALL > $OUT/ncu_raster_$TAG.log 2>&1; echo "raster capture rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'project_|sh_|onesweep|tile_query|full_cumsum|radix_hist|find_ranges|depth_keys|raster_pack|raster_bwd_moments|camera_position|gather_rows' -s 92 -c 24 -f -o $OUT/prof_points_$TAG $SMALL > $OUT/ncu_points_$TAG.log 2>&1; echo "point kernel capture rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'project_|sh_|onesweep|tile_query|full_cumsum|radix_hist|find_ranges|depth_keys|raster_pack|raster_bwd_moments|camera_position|gather_rows|raster_cull_mask' -s 96 -c 25 -f -o $OUT/prof_points_$TAG $SMALL > $OUT/ncu_points_$TAG.log 2>&1; echo "point kernel capture rc=$?"
 ls -la $OUT/*$TAG*
