@@ -247,3 +247,30 @@ def test_counted_sort_and_depth_order(cuda_device, count):
   b = _map_to_tiles(g2d[:v].contiguous(), depths[:v].contiguous(), cam.image_size, cfg, False, ndc_range=rng,
                     depth_order=order[:v])
   assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("n,size,margin", [(1, (17, 13), 0.0), (2, (64, 48), 0.0), (31, (33, 65), 0.3), (33, (640, 360), 0.3),
+                                           (1000, (255, 257), 2.0), (50000, (1920, 1080), 0.3), (300, (320, 240), -0.9)])
+def test_render_gaussians_equals_stagewise_composition(cuda_device, n, size, margin):
+  """render_gaussians (mapper front enqueued with the count on the device, colour kernel before the overlap-total
+  read-back, cull masks) against the same pipeline composed from the public stage operators (project_to_image ->
+  evaluate_sh_at -> map_to_tiles -> rasterize_with_tiles): identical visible set and tile-dependent outputs, bit for
+  bit, on odd image sizes, one or two gaussians, mostly culled and (margin < 0) possibly empty views."""
+  from taichi_gaussian_rasterizer_b200 import evaluate_sh_at, map_to_tiles, rasterize_with_tiles
+  from taichi_gaussian_rasterizer_b200.perspective.projection import project_to_image
+  from taichi_gaussian_rasterizer_b200.torch_lib.projection import ndc_depth
+  cfg = RasterConfig()
+  g, cam = scene3d(100 + n, n, image_size=size, scale_factor=0.8, sh_degree=3, margin=max(margin, 0.0))
+  if margin < 0:   # push most gaussians behind the far plane / out of view
+    g.position = g.position + torch.tensor([0.0, 0.0, 1.0]) * 1e4 * (torch.rand(n, 1) < 0.9)
+  gd, camd = g.to(device=cuda_device), cam.to(device=cuda_device)
+  out = render_gaussians(gd, camd, cfg, use_sh=True)
+
+  g2d, depths, idx = project_to_image(gd, camd, cfg)
+  feats = evaluate_sh_at(gd.feature, gd.position, idx, camd.camera_position)
+  o2p, ranges = map_to_tiles(g2d, ndc_depth(depths, camd.near_plane, camd.far_plane), camd.image_size, cfg)
+  ref = rasterize_with_tiles(g2d, feats, o2p, ranges.view(-1, 2), camd.image_size, cfg)
+  assert torch.equal(out.points_in_view, idx)
+  assert torch.equal(out.gaussians2d, g2d)
+  assert torch.equal(out.image, ref.image)
+  assert torch.equal(out.image_weight, ref.image_weight)
