@@ -333,7 +333,7 @@ def run_ours(args):
     "gs_sh_fwd_views": (n * (4 * CD + 12 + 12 * views)) // views,
     "gs_gather_rows_counted": V * (8 + 12 + 12),
     # ... and one flush per step reads the staged views + positions and adds to the coefficient rows (per frame share)
-    "gs_sh_bwd_flush": (n * (12 * views + 12 + 2 * 4 * CD)) // views,
+    "gs_sh_bwd_flush": (n * (12 * views + 12 + 4 * CD)) // views,   # rows written, not read: zero_() marked them clean
     "gs_full_cumsum": 8 * V,
     "gs_full_cumsum_counted": 8 * V,
     "gs_tile_emit_tiles": 20 * V + 8 * K,
