@@ -184,10 +184,13 @@ tile_query_kernel(const __grid_constant__ GsTileParams p, int img_w, int img_h, 
         const int min_x = m.y & 0xfff, min_y = (m.y >> 12) & 0xfff, span_y = (m.y >> 24) & 0x3f;
         unsigned bits = m.x;
         int c = 0;
+        // b / span_y for b < 32, span_y <= 32 without the integer division sequence: (b + 0.5) / span_y stays at
+        // least 1 / 64 away from every integer, far more than the rounding of the float product
+        const float inv_span = 1.0f / (float)span_y;
         while (bits) {
           const int b = __ffs(bits) - 1;
           bits &= bits - 1;
-          const int tu = b / span_y, tv = b - tu * span_y;
+          const int tu = (int)(((float)b + 0.5f) * inv_span), tv = b - tu * span_y;
           keys[base + c] = (KeyT)((tu + min_x) + (tv + min_y) * tiles_wide);
           values[base + c] = (int32_t)i;
           ++c;
