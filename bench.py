@@ -310,11 +310,11 @@ def run_ours(args):
   fwd_calls, fwd_ms = stage.get("gs_raster_fwd", (0, 0.0))
   stage_ms = {k: round(v[1] / args.steps / views, 4) for k, v in sorted(stage.items())}
   launches = sum(KERNELS_PER_CALL.get(k, 0) * v[0] for k, v in stage.items())
-  # two sorts per frame, each = histogram + scan + one kernel per 8 bit pass: the depth keys (32 bits, enqueued with
+  # two sorts per frame, each = histogram + one kernel per 8 bit pass: the depth keys (32 bits, enqueued with
   # the count still on the device: gs_radix_sort_pairs_counted) and the tile ids (tile_bits)
   tile_bits = max(1, (int(ranges.shape[0] * ranges.shape[1]) - 1).bit_length())
-  launches += stage.get("gs_radix_sort_pairs_counted", (0, 0.0))[0] * (2 + 4)
-  launches += stage.get("gs_radix_sort_pairs", (0, 0.0))[0] * (2 + -(-tile_bits // 8))
+  launches += stage.get("gs_radix_sort_pairs_counted", (0, 0.0))[0] * (1 + 4)
+  launches += stage.get("gs_radix_sort_pairs", (0, 0.0))[0] * (1 + -(-tile_bits // 8))
   launches = launches // max(args.steps, 1)
 
   # HBM rooflines of the bandwidth-bound stages: SURVEY.md §8(d) algorithmic bytes per launch over the live CUDA-event

@@ -117,25 +117,6 @@ radix_histogram_kernel(int64_t n, const KeyT* __restrict__ keys, int begin_bit, 
     if (h[i]) atomicAdd(&global_hist[i], h[i]);
 }
 
-// In-place exclusive scan of each pass's 256 bins.  grid = passes, block = 256.
-__global__ void radix_histogram_scan_kernel(unsigned* __restrict__ global_hist) {
-  __shared__ unsigned s_warp[kSortWarps];
-  unsigned* h = global_hist + blockIdx.x * kRadix;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned c = h[threadIdx.x];
-  unsigned incl = c;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    unsigned t = __shfl_up_sync(kFull, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  unsigned off = 0;
-  for (int wi = 0; wi < warp; ++wi) off += s_warp[wi];
-  h[threadIdx.x] = off + incl - c;
-}
-
 // One onesweep pass: rank keys of a tile by the current digit (warp match-any multi-split + per-warp
 // shared histograms), chain the per-digit tile counts through decoupled look-back, reorder the tile in
 // shared memory and write digit runs back coalesced.  Stable: ranks follow input order.
@@ -144,7 +125,7 @@ template <typename KeyT, bool FULL>
 __global__ void __launch_bounds__(kSortBlock, 3)
 onesweep_pass_kernel(int64_t n, const KeyT* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
                      KeyT* __restrict__ keys_out, int32_t* __restrict__ vals_out, int shift, unsigned mask,
-                     const unsigned* __restrict__ global_excl, unsigned* __restrict__ status,
+                     const unsigned* __restrict__ global_hist, unsigned* __restrict__ status,
                      unsigned* __restrict__ ticket, const int32_t* __restrict__ n_dev) {
   constexpr int ITEMS = SortCfg<KeyT>::kItems;
   if (n_dev) n = min(n, (int64_t)*n_dev);   // counted variant: the grid covers the capacity
@@ -156,7 +137,7 @@ onesweep_pass_kernel(int64_t n, const KeyT* __restrict__ keys_in, const int32_t*
   unsigned* s_digit_off = s_warp_hist + kSortWarps * kRadix;           // [kRadix] exclusive offset in tile
   unsigned* s_global = s_digit_off + kRadix;                           // [kRadix] global base of the digit
   __shared__ int s_tile;
-  __shared__ unsigned s_scan_warp[kSortWarps];
+  __shared__ unsigned s_scan_warp[kSortWarps], s_scan_warp_g[kSortWarps];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
@@ -167,6 +148,9 @@ onesweep_pass_kernel(int64_t n, const KeyT* __restrict__ keys_in, const int32_t*
   if (tile_base >= n) return;   // (counted) tiles past the end: no items, and no later tile looks back at them
   const int valid = (int)min((int64_t)TILE, n - tile_base);
   const int64_t warp_base = tile_base + (int64_t)warp * (32 * ITEMS);
+  // this pass's global digit counts (raw, from radix_histogram_kernel): every block scans the 256 of them itself,
+  // together with its own tile counts, instead of a separate scan launch per sort
+  const unsigned gcount = global_hist[tid];
 
   KeyT key[ITEMS];
 #pragma unroll
@@ -219,9 +203,9 @@ onesweep_pass_kernel(int64_t n, const KeyT* __restrict__ keys_in, const int32_t*
     s_warp_hist[w * kRadix + tid] = tile_count;
     tile_count += c;
   }
+  unsigned exclusive = 0;
   {
     unsigned* st = status + (size_t)tile * kRadix + tid;
-    unsigned exclusive = 0;
     if (tile == 0) {
       st_relaxed_u32(st, kSortFlagPrefix | tile_count);
     } else {
@@ -247,23 +231,23 @@ onesweep_pass_kernel(int64_t n, const KeyT* __restrict__ keys_in, const int32_t*
       }
       st_relaxed_u32(st, kSortFlagPrefix | ((exclusive + tile_count) & kSortValueMask));
     }
-    s_global[tid] = global_excl[tid] + exclusive;
   }
-  // exclusive scan of tile_count over the 256 digits
+  // exclusive scans over the 256 digits: of tile_count (offsets inside the tile) and of the global counts
   {
-    unsigned incl = tile_count;
+    unsigned incl = tile_count, gincl = gcount;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      unsigned t = __shfl_up_sync(kFull, incl, o);
-      if (lane >= o) incl += t;
+      const unsigned t = __shfl_up_sync(kFull, incl, o), g = __shfl_up_sync(kFull, gincl, o);
+      if (lane >= o) { incl += t; gincl += g; }
     }
-    if (lane == 31) s_scan_warp[warp] = incl;
+    if (lane == 31) { s_scan_warp[warp] = incl; s_scan_warp_g[warp] = gincl; }
     __syncthreads();
-    unsigned off = 0;
+    unsigned off = 0, goff = 0;
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w)
-      if (w < warp) off += s_scan_warp[w];
+      if (w < warp) { off += s_scan_warp[w]; goff += s_scan_warp_g[w]; }
     s_digit_off[tid] = off + incl - tile_count;
+    s_global[tid] = (goff + gincl - gcount) + exclusive;
   }
   __syncthreads();
 
@@ -329,8 +313,6 @@ static int radix_sort_impl(int64_t n, const KeyT* keys_in, const int32_t* vals_i
   GS_CUDA(cudaMemsetAsync(ws, 0, L.zero_bytes, st));
   int hist_blocks = (int)min((int64_t)148 * 8, ceil_div(n, 256));
   radix_histogram_kernel<KeyT><<<hist_blocks, 256, 0, st>>>(n, keys_in, begin_bit, end_bit, L.passes, hist, n_dev);
-  GS_LAUNCH_CHECK();
-  radix_histogram_scan_kernel<<<L.passes, kRadix, 0, st>>>(hist);
   GS_LAUNCH_CHECK();
 
   const size_t smem = sort_smem_bytes<KeyT>();
