@@ -50,9 +50,10 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
   constexpr int kBwdBatch = BATCH;   // staged tile-list entries per buffer
   constexpr int NM = 6;  // moments: g, g u, g w, g u^2, g w^2, g u w
   constexpr int NV = NM + F + (HEUR ? 2 : 0);
-  __shared__ __align__(16) float4 s_r0[2][kBwdBatch];
-  __shared__ __align__(16) float4 s_r1[2][kBwdBatch];
-  __shared__ __align__(16) float s_feat[2][kBwdBatch][FP];
+  // one staged entry = {record (2 x float4), feature row (FP / 4 x float4)} in consecutive 16 B units: one address per
+  // entry in the walk (all reads are warp-uniform, so the stride needs no padding)
+  constexpr int U = 2 + FP / 4;
+  __shared__ __align__(16) float4 s_e[2][kBwdBatch][U];
   __shared__ unsigned char s_mask[2][kBwdBatch];   // cull bytes of the staged entries (raster_cull_mask_kernel)
 
   const int t = threadIdx.x, lane = t & 31;
@@ -107,10 +108,10 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
       if (v < C) {
         const int idx = o2p[start + v];
         const unsigned char m = cull_mask[start + v];   // in flight together with the index load
-        cp_async16(&s_r0[buf][s], rec + 2 * (int64_t)idx);
-        cp_async16(&s_r1[buf][s], rec + 2 * (int64_t)idx + 1);
+        cp_async16(&s_e[buf][s][0], rec + 2 * (int64_t)idx);
+        cp_async16(&s_e[buf][s][1], rec + 2 * (int64_t)idx + 1);
 #pragma unroll
-        for (int c = 0; c < FP; c += 4) cp_async16(&s_feat[buf][s][c], featP + (int64_t)idx * FP + c);
+        for (int c = 0; c < FP; c += 4) cp_async16(&s_e[buf][s][2 + c / 4], featP + (int64_t)idx * FP + c);
         s_mask[buf][s] = m;
       }
     }
@@ -152,11 +153,12 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
           const int jl = __ffs(any) - 1;
           any &= any - 1;
           const int j = c0 + jl;
-          const float4 r0 = s_r0[buf][j], r1 = s_r1[buf][j];
+          const float4* ent = s_e[buf][j];
+          const float4 r0 = ent[0], r1 = ent[1];
           const float mx = r0.x, my = r0.y, a1x = r0.z, a1y = r0.w, a2x = r1.x, a2y = r1.y, l2a = r1.z;
           float f[F];
 #pragma unroll
-          for (int c = 0; c < F; ++c) f[c] = s_feat[buf][j][c];
+          for (int c = 0; c < F; ++c) f[c] = reinterpret_cast<const float*>(ent + 2)[c];
 
           float M0 = 0.f, Mu = 0.f, Mw = 0.f, Muu = 0.f, Mww = 0.f, Muw = 0.f, h0 = 0.f, h1 = 0.f;
           float gf[F];
