@@ -28,29 +28,32 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-CPU_SAMPLE_STRIDE = 16   # the CPU legs render every 16th gaussian of the scene
-
-WORKLOAD = dict(num_gaussians=3_000_000, image_size=(2048, 1365), sh_degree=3, scale_factor=1.5,
-                alpha_range=(0.1, 0.9), tile_size=16, seed=0)
+# The CPU legs (cpu_baseline, --impl reference) render the SAME scene at FULL size: same 3 M gaussians, camera and
+# resolution as the GPU arm (full size whenever a frame takes under a minute; it takes a few seconds).
+WORKLOADS = {
+  # BASELINE.json metric: "fwd+bwd ms/frame & Gaussians*px/s at 3M Gauss 2048px"
+  "bench": dict(scene="bench", tile_size=16, seed=0),
+  # BASELINE.json config 5: batched multi-view step, 64 cameras x 3 M gaussians at 1600x1064 (use --total-views 64)
+  "c5": dict(scene="c5", tile_size=16, seed=0),
+}
 
 
 # ----------------------------------------------------------------------------------------------- scene
-def build_scene(n, image_size, sh_degree, scale_factor, alpha_range, seed, num_views):
-  from taichi_gaussian_rasterizer_b200.synthetic import random_3d_gaussians, random_camera
+def build_scene(scene, seed, num_views, num_gaussians=None, image_size=None):
+  """The scene of a BASELINE.json configuration (synthetic.baseline_scene) and `num_views` cameras: the scene's own
+  camera first, then small pose jitters around it so that every view sees a comparable part of the scene."""
+  from taichi_gaussian_rasterizer_b200.synthetic import baseline_scene
   from taichi_gaussian_rasterizer_b200.torch_lib.projection import join_rt, quat_to_mat
-  torch.manual_seed(seed)
-  base = random_camera(image_size=image_size)
-  gaussians = random_3d_gaussians(n, base, scale_factor=scale_factor, alpha_range=alpha_range, sh_degree=sh_degree)
+  gaussians, base, spec = baseline_scene(scene, seed=seed, n=num_gaussians or None, image_size=image_size)
   cameras = []
   g = torch.Generator().manual_seed(seed + 1)
   for i in range(num_views):
-    # small pose jitter around the base view so that every view sees a comparable part of the scene
     axis = torch.nn.functional.normalize(torch.randn(3, generator=g), dim=0)
     angle = (torch.rand(1, generator=g) * 2 - 1) * 0.02
     q = torch.cat([axis * torch.sin(angle / 2), torch.cos(angle / 2)])
     delta = join_rt(quat_to_mat(q), (torch.rand(3, generator=g) * 2 - 1) * 0.02)
     cameras.append(base.transformed(delta) if i > 0 else base)
-  return gaussians, cameras
+  return gaussians, cameras, spec
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -122,6 +125,28 @@ KERNELS_PER_CALL = {  # kernels launched by each entry point (memsets not counte
 }
 
 
+def resolve_workload(args):
+  """(workload dict, views per rank, scaling) from the command line: `--workload bench` (default; weak scaling, a fixed
+  number of views per rank) or `--workload c5 --total-views 64` (BASELINE config 5: the batch is fixed and split over
+  the ranks = strong scaling)."""
+  from taichi_gaussian_rasterizer_b200.synthetic import BASELINE_SCENES
+  W = dict(WORKLOADS[args.workload])
+  spec = dict(BASELINE_SCENES[W["scene"]])
+  W.update(num_gaussians=args.num_gaussians or spec["n"], image_size=tuple(args.image_size or spec["image_size"]),
+           sh_degree=spec["sh_degree"], scale_factor=spec.get("scale_factor", 1.0))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  if args.total_views:
+    assert args.total_views % world == 0, f"--total-views {args.total_views} does not divide over {world} ranks"
+    return W, args.total_views // world, "strong"
+  return W, args.views_per_rank, "weak"
+
+
+def workload_name(W):
+  w, h = W["image_size"]
+  return (f"render_gaussians fwd+bwd, {W['num_gaussians']} random gaussians, SH degree {W['sh_degree']}, "
+          f"{w}x{h}, tile {W['tile_size']}, L1 loss")
+
+
 def run_ours(args):
   import torch.distributed as dist
   from taichi_gaussian_rasterizer_b200 import RasterConfig, _native, evaluate_sh_views, render_gaussians
@@ -137,15 +162,9 @@ def run_ours(args):
   if world > 1:
     dist.init_process_group("nccl", device_id=device)
 
-  W = dict(WORKLOAD)
-  if args.num_gaussians:
-    W["num_gaussians"] = args.num_gaussians
-  if args.image_size:
-    W["image_size"] = tuple(args.image_size)
-  views = args.views_per_rank
+  W, views, scaling = resolve_workload(args)
   w, h = W["image_size"]
-  gaussians_cpu, cameras = build_scene(W["num_gaussians"], W["image_size"], W["sh_degree"], W["scale_factor"],
-                                       W["alpha_range"], W["seed"], num_views=views * world)
+  gaussians_cpu, cameras, _ = build_scene(W["scene"], W["seed"], views * world, W["num_gaussians"], W["image_size"])
   my_cameras = cameras[rank::world][:views]
   gaussians = gaussians_cpu.to(device=device)
   if args.morton:
@@ -168,8 +187,12 @@ def run_ours(args):
   dev_targets = [t.to(device) for t in host_targets]
   dev_cams = [c.to(device=device) for c in my_cameras]
   h2d_bytes = sum(t.numel() * 4 for t in host_targets) + sum(p.numel() * 4 for p in host_proj + host_pose)
-  loss_host = torch.zeros(1).pin_memory()
-  stats = {}
+  # the step's result (its loss) is read on the host one step late, from the slot the previous step filled: the host
+  # never drains the stream inside the timed region, every step still delivers its 4 bytes
+  loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+  loss_ready = [torch.cuda.Event() for _ in range(2)]
+  losses_read = []
+  stats = {"e2e_step": 0}
 
   def step(from_host: bool):
     with bucket.fused_accumulation():
@@ -218,6 +241,8 @@ def run_ours(args):
         target = st["target"]
       else:
         target = dev_targets[i]
+      if i == views - 1 and views > 1 and args.reduce_early:
+        bucket.reduce_early()   # N > 1: the SH slices are all-reduced under the last view (distributed.py)
       rendering = render_gaussians(gaussians, cam, config, use_sh=True, sh_colors=colors[i])
       loss = torch.nn.functional.l1_loss(rendering.image, target)   # mean |image - target|, one fused ATen op each way
       loss.backward()
@@ -227,22 +252,37 @@ def run_ours(args):
       stats["V"] = rendering.points_in_view.shape[0]
     bucket.all_reduce()
     if from_host:
-      loss_host.copy_(total.reshape(1), non_blocking=True)
-      torch.cuda.current_stream().synchronize()   # the step's result is read on the host
+      k = stats["e2e_step"]
+      slot = k & 1
+      loss_host[slot].copy_(total.reshape(1), non_blocking=True)
+      loss_ready[slot].record(compute)
+      if k > 0:   # read the PREVIOUS step's loss: it has long arrived, the host does not wait for this step's work
+        loss_ready[slot ^ 1].synchronize()
+        losses_read.append(float(loss_host[slot ^ 1].item()))
+      stats["e2e_step"] = k + 1
     return total
+
+  def stock_step():
+    """The reference's call sequence, nothing else: render_gaussians(use_sh=True) per view (per view SH evaluation),
+    plain autograd accumulation into .grad (no bucket sinks, no deferred SH gradient, no batched colours)."""
+    for p in params:
+      p.grad = None
+    for i in range(views):
+      rendering = render_gaussians(gaussians, dev_cams[i], config, use_sh=True)
+      torch.nn.functional.l1_loss(rendering.image, dev_targets[i]).backward()
 
   def barrier():
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize()
 
-  def timed(from_host, steps, timer=None):
+  def timed(fn, steps, timer=None):
     barrier()
     _native.set_stage_timer(timer)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(steps):
-      step(from_host)
+      fn()
     b.record()
     barrier()
     _native.set_stage_timer(None)
@@ -259,18 +299,26 @@ def run_ours(args):
   if rank == 0:
     sampler.start()
   timer = _native.StageTimer()
-  ms_dev = timed(False, args.steps, timer)
+  ms_dev = timed(lambda: step(False), args.steps, timer)
   stage = timer.summary()
   clocks = sampler.stop() if rank == 0 else None
   step(True)
-  ms_e2e = timed(True, args.steps)
+  ms_e2e = timed(lambda: step(True), args.steps)
+  stock_ms = None
+  if world == 1 and not args.no_stock:
+    saved = [p.grad for p in params]
+    stock_steps = max(2, min(args.steps, 5))
+    stock_step()
+    stock_ms = timed(stock_step, stock_steps) / stock_steps / views
+    for p, gr in zip(params, saved):   # the bucket's views back in place
+      p.grad = gr
 
   n, px = W["num_gaussians"], w * h
   units_per_step = n * px * views * world
   value = units_per_step / (ms_dev / args.steps / 1e3)
   e2e = units_per_step / (ms_e2e / args.steps / 1e3)
 
-  # K of the last view, for the roofline's algorithmic bytes
+  # K of the first view, for the roofline's algorithmic bytes
   from taichi_gaussian_rasterizer_b200 import map_to_tiles
   from taichi_gaussian_rasterizer_b200.perspective.projection import project_to_image
   from taichi_gaussian_rasterizer_b200.torch_lib.projection import ndc_depth
@@ -307,10 +355,9 @@ def run_ours(args):
     ach_ips = warp_inst / (bwd_avg_ms * 1e-3)
     issue = {"warp_inst_per_launch": warp_inst, "achieved_warp_inst_per_s": ach_ips, "peak_warp_inst_per_s": peak_ips,
              "frac": ach_ips / peak_ips, "source": traffic_src}
-  fwd_calls, fwd_ms = stage.get("gs_raster_fwd", (0, 0.0))
   stage_ms = {k: round(v[1] / args.steps / views, 4) for k, v in sorted(stage.items())}
   launches = sum(KERNELS_PER_CALL.get(k, 0) * v[0] for k, v in stage.items())
-  # two sorts per frame, each = histogram + one kernel per 8 bit pass: the depth keys (32 bits, enqueued with
+  # two sorts per frame, each = histogram + one kernel per digit pass: the depth keys (32 bits, enqueued with
   # the count still on the device: gs_radix_sort_pairs_counted) and the tile ids (tile_bits)
   tile_bits = max(1, (int(ranges.shape[0] * ranges.shape[1]) - 1).bit_length())
   launches += stage.get("gs_radix_sort_pairs_counted", (0, 0.0))[0] * (1 + 4)
@@ -353,11 +400,12 @@ def run_ours(args):
     "metric": "gaussians_px_per_s_fwd_bwd", "value": value, "unit": "gaussian*pixel/s",
     "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
     "ms_per_step": ms_dev / args.steps, "ms_per_frame": ms_dev / args.steps / views,
-    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-    "config": {"workload": f"render_gaussians fwd+bwd, {n} random gaussians, SH degree {W['sh_degree']}, "
-                           f"{w}x{h}, tile {W['tile_size']}, L1 loss",
+    "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    "config": {"workload": workload_name(W),
                "views_per_rank": views, "parallelism": f"view-parallel x{world}, replicated gaussians, "
-                                                       "one gradient all-reduce per step",
+                                                       "one gradient all-reduce per step"
+                                                       + (" (SH slices reduced under the last view, its staged colour "
+                                                          "gradients all-gathered)" if world > 1 and args.reduce_early else ""),
                "V_in_view": V, "K_overlaps": K, "K_per_tile_mean": float(counts.mean()),
                "K_per_tile_max": int(counts.max()), "scale_factor": W["scale_factor"],
                "l2_policy": "inputs larger than L2 (708 MB of gaussians per view)", "gaussian_order": "morton" if args.morton else "as generated (random)",
@@ -365,7 +413,13 @@ def run_ours(args):
                "sh": "colours of all views of a step evaluated in one pass over the coefficients, coefficient gradient "
                      "formed once per step" if args.batched_sh else "evaluated per view, coefficient gradient formed once per step"},
     "e2e": {"value": e2e, "unit": "gaussian*pixel/s", "ms_per_step": ms_e2e / args.steps,
-            "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "ms_per_frame": ms_e2e / args.steps / views,
+            "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+            "note": "a training step: cameras + target images of the step's views go host -> device from pinned memory "
+                    "inside the timed region, the step's loss comes back (read one step late, so the host never drains "
+                    "the stream); the gaussians' parameters and their gradient bucket are RESIDENT on the device, as "
+                    "they are for a trainer",
+            "losses_read_on_host": len(losses_read)},
     "gpu_launches": launches,
     "roofline": {"kernel": "raster_bwd_fast_kernel (gs_raster_bwd)", "bound": "hbm", "achieved": achieved,
                  "peak": peak_gbs, "peak_source": peak_src, "unit": "GB/s",
@@ -380,39 +434,67 @@ def run_ours(args):
     "hbm_stage_rooflines": hbm_stages,
     "clocks": clocks,
   }
+  if stock_ms is not None:
+    out["stock_api_ms_per_frame"] = stock_ms
+    out["stock_api_note"] = ("the reference's call sequence only: render_gaussians(use_sh=True) per view, plain autograd "
+                             "accumulation (no sh_colors, no GradientBucket.fused_accumulation); the headline uses those "
+                             "two extensions")
+  if world > 1:
+    dist.destroy_process_group()
+  if rank == 0 and world == 1 and not args.no_configs:
+    # BASELINE.json's five configurations at full size, fwd+bwd ms per frame through the public API (V, K recorded)
+    del gaussians, bucket, params, dev_targets, staged, host_targets
+    torch.cuda.empty_cache()
+    out["configs"] = run_configs(device)
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     out["cpu_baseline"] = cpu_baseline(W, budget_s=args.cpu_budget)
   if rank == 0:
     print(json.dumps(out))
-  if world > 1:
-    dist.destroy_process_group()
+
+
+def run_configs(device, steps=5):
+  sys.path.insert(0, str(ROOT / "benchmarks"))
+  import configs as cfgs
+  res = {}
+  for name in ("c1", "c2", "c3", "c4", "c5"):
+    try:
+      step = cfgs.CONFIGS[name](device)
+      ms, stages, info = cfgs.timed(step, steps)
+      res[name] = {"ms_per_frame": round(ms, 3), "what": cfgs.CONFIGS[name].__doc__.strip(), **info,
+                   "raster_fwd_ms": stages.get("gs_raster_fwd"), "raster_bwd_ms": stages.get("gs_raster_bwd")}
+    except Exception as e:   # noqa: BLE001 - report and continue
+      res[name] = {"error": f"{type(e).__name__}: {e}"}
+    torch.cuda.empty_cache()
+  res["note"] = ("single view fwd+bwd, per view SH evaluation; c3 is a synthetic stand-in for the bicycle scene whose only "
+                 "published figure is 17.1 ms on an RTX 4090 (reference benchmarks/benchmark-4090.csv:16; target <= 5.7 ms)")
+  return res
 
 
 # ----------------------------------------------------------------------------------------------- CPU legs
 def oracle_frame(gaussians, camera, config):
-  """One forward + backward frame of the CPU restatement (oracle/): C++/OpenMP for projection forward, SH
-  forward, tile mapping, rasterizer forward / backward; torch (CPU) autograd for the per point backward."""
+  """One forward + backward frame of the CPU restatement of the reference algorithm (oracle/): C++/OpenMP for the
+  projection forward AND backward, SH forward, tile mapping, rasterizer forward / backward; torch (CPU) autograd only
+  for the SH coefficient gradient.  Returns (V, K)."""
   import oracle
   from oracle import torch_ref
   g = gaussians
-  pts, depth, idx = torch_ref.projection_apply(*g.shape_tensors(), camera.T_camera_world, camera.projection,
-                                               camera.image_size, camera.depth_range, config.blur_cov,
-                                               config.clamp_margin, config.alpha_threshold)
+  pts, depth, idx = oracle.project_to_image(g, camera, config)
   feats = torch_ref.evaluate_sh_at(g.feature, g.position.detach(), idx, camera.camera_position)
   ndc = torch_ref.ndc_depth(depth, camera.near_plane, camera.far_plane)
-  o2p, ranges = oracle.map_to_tiles(pts.detach(), ndc.detach(), camera.image_size, config)
+  o2p, ranges = oracle.map_to_tiles(pts, ndc, camera.image_size, config)
+  pts.requires_grad_(True)
   raster = oracle.rasterize_with_tiles(pts, feats, o2p, ranges.view(-1, 2), camera.image_size, config)
   raster.image.abs().mean().backward()
+  grads, _ = oracle.projection_backward(*g.shape_tensors(), camera.T_camera_world, camera.projection, camera.image_size,
+                                        idx, pts.grad, None, blur_cov=config.blur_cov, clamp_margin=config.clamp_margin)
   return int(idx.shape[0]), int(o2p.shape[0])
 
 
-def cpu_sample(W, stride):
-  """Every `stride`-th gaussian of the benchmark scene (same sizes, opacities and camera as the GPU arm)."""
-  gaussians, cameras = build_scene(W["num_gaussians"], W["image_size"], W["sh_degree"], W["scale_factor"],
-                                   W["alpha_range"], W["seed"], num_views=1)
-  gaussians = gaussians[::stride].contiguous()
-  gaussians.requires_grad_(True)
-  return gaussians.batch_size[0], gaussians, cameras[0]
+def cpu_scene(W):
+  """The benchmark scene at FULL size on the host (same gaussians, camera and resolution as the GPU arm)."""
+  gaussians, cameras, _ = build_scene(W["scene"], W["seed"], 1, W["num_gaussians"], W["image_size"])
+  gaussians.feature.requires_grad_(True)
+  return gaussians, cameras[0]
 
 
 def cpu_baseline(W, budget_s=12.0):
@@ -420,12 +502,12 @@ def cpu_baseline(W, budget_s=12.0):
   from taichi_gaussian_rasterizer_b200 import RasterConfig
   use_all_host_threads()
   config = RasterConfig(tile_size=W["tile_size"])
-  n, gaussians, camera = cpu_sample(W, CPU_SAMPLE_STRIDE)
+  gaussians, camera = cpu_scene(W)
+  n = W["num_gaussians"]
   t0 = time.perf_counter()
   frames = 0
   while True:
-    for p in (gaussians.position, gaussians.log_scaling, gaussians.rotation, gaussians.alpha_logit, gaussians.feature):
-      p.grad = None
+    gaussians.feature.grad = None
     V, K = oracle_frame(gaussians, camera, config)
     frames += 1
     if time.perf_counter() - t0 > budget_s or frames >= 200:
@@ -433,8 +515,8 @@ def cpu_baseline(W, budget_s=12.0):
   dt = (time.perf_counter() - t0) / frames
   w, h = W["image_size"]
   return {"value": n * w * h / dt, "unit": "gaussian*pixel/s", "cores": oracle.num_threads(), "kind": "port",
-          "sample": f"{frames} frame(s) of every {CPU_SAMPLE_STRIDE}th gaussian of the benchmark scene ({n} gaussians, "
-                    f"same camera, {w}x{h}, SH3, fwd+bwd): {dt:.2f} s/frame, V={V}, K={K}"}
+          "sample": f"{frames} frame(s) of the benchmark scene at FULL size ({n} gaussians, same camera, {w}x{h}, SH3, "
+                    f"fwd+bwd): {dt:.2f} s/frame, V={V}, K={K}"}
 
 
 def use_all_host_threads():
@@ -450,46 +532,42 @@ def use_all_host_threads():
 def run_reference(args):
   """The reference's algorithm on the host cores: the Taichi package cannot be installed here (no wheel, no
   network; its rasterizer has no CPU arch anyway, SURVEY.md header), so this arm times oracle/ — the C++/OpenMP
-  + torch restatement — with all host threads on a bounded sample of the same workload."""
+  + torch restatement — with all host threads on the SAME workload at full size; a step is ONE view (the GPU arm's
+  step is `views_per_rank` views; the metric is normalised per gaussian and pixel)."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
   import oracle
   from taichi_gaussian_rasterizer_b200 import RasterConfig
   use_all_host_threads()
-  W = dict(WORKLOAD)
-  if args.num_gaussians:
-    W["num_gaussians"] = args.num_gaussians
-  if args.image_size:
-    W["image_size"] = tuple(args.image_size)
+  W, _, scaling = resolve_workload(args)
   config = RasterConfig(tile_size=W["tile_size"])
-  n, gaussians, camera = cpu_sample(W, CPU_SAMPLE_STRIDE)
+  gaussians, camera = cpu_scene(W)
+  n = W["num_gaussians"]
   w, h = W["image_size"]
 
   def frame():
-    for p in (gaussians.position, gaussians.log_scaling, gaussians.rotation, gaussians.alpha_logit, gaussians.feature):
-      p.grad = None
+    gaussians.feature.grad = None
     return oracle_frame(gaussians, camera, config)
 
-  warmup = min(args.warmup, 3)
+  warmup = min(args.warmup, 1)           # a full-size frame takes seconds: one warm-up frame is enough for a CPU
   for _ in range(warmup):
     frame()
-  steps = max(1, min(args.steps, 100))   # ~0.3 s per step on 16 host threads
+  steps = max(1, min(args.steps, 10))
   t0 = time.perf_counter()
   for _ in range(steps):
     V, K = frame()
   dt = (time.perf_counter() - t0) / steps
   value = n * w * h / dt
-  sample = (f"each step = 1 frame fwd+bwd of every {CPU_SAMPLE_STRIDE}th gaussian of the benchmark scene ({n} gaussians, "
-            f"same camera), {w}x{h}, SH3; V={V}, K={K}; {steps} timed steps")
+  sample = (f"each step = 1 frame fwd+bwd of the benchmark scene at FULL size ({n} gaussians, same camera), {w}x{h}, "
+            f"SH3; V={V}, K={K}; {steps} timed steps, {dt:.2f} s/frame")
   print(json.dumps({
     "impl": "reference", "metric": "gaussians_px_per_s_fwd_bwd", "value": value, "unit": "gaussian*pixel/s",
-    "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3,
-    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-    "config": {"workload": f"render_gaussians fwd+bwd, {W['num_gaussians']} random gaussians, SH degree {W['sh_degree']}, "
-                           f"{w}x{h}, tile {W['tile_size']}, L1 loss",
-               "sample": f"CPU restatement of the reference algorithm (oracle/) on every {CPU_SAMPLE_STRIDE}th gaussian "
-                         f"({n} gaussians), all host threads"},
+    "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "ms_per_frame": dt * 1e3,
+    "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    "config": {"workload": workload_name(W),
+               "sample": "CPU restatement of the reference algorithm (oracle/, C++/OpenMP) on the full workload, one "
+                         "view per step, all host threads"},
     "cpu_baseline": {"value": value, "unit": "gaussian*pixel/s", "cores": oracle.num_threads(), "kind": "port",
                      "sample": sample},
     "e2e": {"value": value, "unit": "gaussian*pixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -510,6 +588,13 @@ def main():
                   help="evaluate the SH colours per view (evaluate_sh_at) instead of once per step for all views")
   ap.add_argument("--morton", action="store_true", help="store the gaussians in Morton order of their positions")
   ap.add_argument("--cpu-budget", type=float, default=12.0)
+  ap.add_argument("--workload", choices=sorted(WORKLOADS), default="bench")
+  ap.add_argument("--total-views", type=int, default=0,
+                  help="fixed batch split over the ranks (strong scaling), e.g. --workload c5 --total-views 64")
+  ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration (c1..c5) timings at N = 1")
+  ap.add_argument("--no-stock", action="store_true", help="skip the stock-API (no extensions) timing at N = 1")
+  ap.add_argument("--no-reduce-early", dest="reduce_early", action="store_false",
+                  help="N > 1: one all-reduce of the whole bucket after the last view (round-1 behaviour)")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)

@@ -14,9 +14,11 @@ import torch
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 
-from taichi_gaussian_rasterizer_b200 import RasterConfig, _native, rasterize, render_gaussians  # noqa: E402
+from taichi_gaussian_rasterizer_b200 import RasterConfig, _native, map_to_tiles, rasterize, render_gaussians  # noqa: E402
 from taichi_gaussian_rasterizer_b200.misc.renderer2d import project_gaussians2d  # noqa: E402
-from taichi_gaussian_rasterizer_b200.synthetic import random_2d_gaussians, random_3d_gaussians, random_camera  # noqa: E402
+from taichi_gaussian_rasterizer_b200.perspective.projection import project_to_image  # noqa: E402
+from taichi_gaussian_rasterizer_b200.synthetic import baseline_scene, random_2d_gaussians  # noqa: E402
+from taichi_gaussian_rasterizer_b200.torch_lib.projection import ndc_depth  # noqa: E402
 
 
 def timed(fn, steps, warmup=3):
@@ -52,25 +54,31 @@ def c1(dev):
     r = rasterize(packed, g.z_depth.clamp(0, 1), g.feature, size, cfg)
     loss = torch.nn.functional.mse_loss(torch.sigmoid(r.image), target)
     loss.backward()
-    return {"N": 20_000, "image": size}
+    return {"V": 20_000, "K": K}
+  with torch.no_grad():
+    K = int(map_to_tiles(project_gaussians2d(g), g.z_depth.clamp(0, 1), size, cfg)[0].shape[0])
   return step
 
 
-def scene3d(n, size, dev, sh_degree=None, channels=3, scale_factor=1.0, seed=0, bimodal=False):
-  torch.manual_seed(seed)
-  cam = random_camera(image_size=size)
-  g = random_3d_gaussians(n, cam, scale_factor=scale_factor, sh_degree=sh_degree, num_channels=channels)
-  if bimodal:   # Mip-NeRF360-like: log-normal scales (sigma_ln = 1), opacity mass near 0.05 and 0.95
-    g.log_scaling = g.log_scaling + torch.randn(n, 1)
-    u = torch.rand(n)
-    alpha = torch.where(u < 0.5, 0.02 + 0.08 * torch.rand(n), 0.9 + 0.09 * torch.rand(n))
-    g.alpha_logit = torch.logit(alpha).unsqueeze(1)
+def scene3d(name, dev):
+  """BASELINE.json configuration `name` (synthetic.baseline_scene: shared with bench.py and the full-size parity tests)."""
+  g, cam, spec = baseline_scene(name)
   g = g.to(device=dev)
   g.requires_grad_(True)
   return g, cam.to(device=dev)
 
 
+def count_overlaps(g, cam, cfg):
+  """(V, K) of the view: visible gaussians and tile overlaps (recorded next to the timings)."""
+  with torch.no_grad():
+    g2d, depth, idx = project_to_image(g, cam, cfg)
+    o2p, _ = map_to_tiles(g2d, ndc_depth(depth, cam.near_plane, cam.far_plane), cam.image_size, cfg)
+  return int(idx.shape[0]), int(o2p.shape[0])
+
+
 def render_step(g, cam, cfg, **kw):
+  V, K = count_overlaps(g, cam, cfg)
+
   def step():
     for t in (g.position, g.log_scaling, g.rotation, g.alpha_logit, g.feature):
       t.grad = None
@@ -79,31 +87,31 @@ def render_step(g, cam, cfg, **kw):
     if r.depth is not None:
       loss = loss + r.depth.mean() * 1e-3
     loss.backward()
-    return {"V": int(r.points_in_view.shape[0])}
+    return {"V": V, "K": K}
   return step
 
 
 def c2(dev):
   """render_gaussians 3D: 1M gaussians, SH degree 3, 1920x1080."""
-  g, cam = scene3d(1_000_000, (1920, 1080), dev, sh_degree=3)
+  g, cam = scene3d("c2", dev)
   return render_step(g, cam, RasterConfig(), use_sh=True)
 
 
 def c3(dev):
   """bicycle-scale: 6M gaussians, log-normal scales / bimodal opacity, 2048x1365, visibility + split/prune stats."""
-  g, cam = scene3d(6_000_000, (2048, 1365), dev, sh_degree=3, bimodal=True)
+  g, cam = scene3d("c3", dev)
   return render_step(g, cam, RasterConfig(compute_visibility=True, compute_point_heuristic=True), use_sh=True)
 
 
 def c4(dev):
   """feature lifting: 2M gaussians, 32-channel features + depth / depth variance, 3840x2160."""
-  g, cam = scene3d(2_000_000, (3840, 2160), dev, channels=32)
+  g, cam = scene3d("c4", dev)
   return render_step(g, cam, RasterConfig(), use_sh=False, render_depth=True)
 
 
 def c5(dev):
   """one rank's share of the batched multi-view step: 8 of 64 cameras x 3M gaussians, 1600x1064 (see bench.py --gpus)."""
-  g, cam = scene3d(3_000_000, (1600, 1064), dev, sh_degree=3, scale_factor=1.5)
+  g, cam = scene3d("c5", dev)
   return render_step(g, cam, RasterConfig(), use_sh=True)
 
 

@@ -117,6 +117,30 @@ def projection_forward(position, log_scaling, rotation, alpha_logit, T_camera_wo
   return points[indexes], depth[indexes].unsqueeze(1), indexes
 
 
+def projection_backward(position, log_scaling, rotation, alpha_logit, T_camera_world, projection, image_size,
+                        indexes, grad_points, grad_depth=None, blur_cov=0.0, clamp_margin=0.15):
+  """Gradients of (points, depth) = project_to_image(...) w.r.t. the six inputs, in the inputs' dtype: the reverse
+  sweep of project_one (oracle.cpp project_bwd; the reference differentiates indexed_project_kernel with Taichi
+  autodiff, perspective/projection.py:83-118, :164-185).  Returns (grads dict, cond (V, 2)) where
+  cond[:, 0] = sqrt(gap) / trace and cond[:, 1] = |n| / trace of the projected covariance: the two quantities the
+  eigen decomposition divides by (small = ill conditioned in float32 for any implementation)."""
+  dtype = position.dtype
+  n, nv = position.shape[0], indexes.shape[0]
+  args = [t.detach().contiguous() for t in (position, log_scaling, rotation, alpha_logit.reshape(-1),
+                                            T_camera_world.to(dtype), projection.to(dtype))]
+  out = dict(position=torch.zeros((n, 3), dtype=dtype), log_scaling=torch.zeros((n, 3), dtype=dtype),
+             rotation=torch.zeros((n, 4), dtype=dtype), alpha_logit=torch.zeros((n, 1), dtype=dtype),
+             T_camera_world=torch.zeros((4, 4), dtype=dtype), projection=torch.zeros((4,), dtype=dtype))
+  cond = torch.zeros((nv, 2), dtype=dtype)
+  gd = None if grad_depth is None else grad_depth.detach().to(dtype).reshape(-1).contiguous()
+  fn = getattr(lib(), f"orc_project_bwd_{_suffix(dtype)}")
+  fn(ctypes.c_int64(nv), _p(indexes.contiguous()), *[_p(a) for a in args], ctypes.c_int(int(image_size[0])),
+     ctypes.c_int(int(image_size[1])), ctypes.c_double(blur_cov), ctypes.c_double(clamp_margin),
+     _p(grad_points.detach().to(dtype).contiguous()), _p(gd), *[_p(out[k]) for k in
+     ("position", "log_scaling", "rotation", "alpha_logit", "T_camera_world", "projection")], _p(cond))
+  return out, cond
+
+
 def project_to_image(gaussians, camera_params, config):
   return projection_forward(*gaussians.shape_tensors(), camera_params.T_camera_world, camera_params.projection,
                             camera_params.image_size, camera_params.depth_range, config.blur_cov,

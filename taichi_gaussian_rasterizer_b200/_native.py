@@ -69,6 +69,14 @@ class GsOptParams(ctypes.Structure):
 _lib = None
 
 
+def use_library(path):
+  """Load a differently built copy of the library instead of the default one (benchmarks/fast_math_cost.py: the build
+  without --use_fast_math).  Must be called before the first operator runs."""
+  global LIB_PATH
+  assert _lib is None, "the library is already loaded"
+  LIB_PATH = Path(path)
+
+
 def lib():
   global _lib
   if _lib is None:
@@ -124,19 +132,42 @@ def set_stage_timer(timer):
   return timer
 
 
+class StreamHandle(ctypes.c_void_p):
+  """A ``cudaStream_t`` for the C ABI that remembers which device it belongs to (see ``call``)."""
+  index = None
+
+
 def call(name: str, *args):
-  """Invoke an entry point of the library, raising RuntimeError with its message on failure."""
+  """Invoke an entry point of the library, raising RuntimeError with its message on failure.
+
+  Device guard: the library launches on the calling thread's CURRENT device, while the pointers and the stream belong
+  to the tensors' device.  The stream handle made by ``stream_ptr(device)`` carries that device's index; when it is
+  not the current device the call (and the stage timer's events) run inside ``torch.cuda.device(index)``, as torch's
+  own operators do.  The common case (same device) costs one integer comparison."""
   fn = getattr(lib(), name)
-  if _timer is None:
-    rc = fn(*args)
+  index = None
+  for a in reversed(args):   # the stream is the last argument of every launching entry point
+    if isinstance(a, StreamHandle):
+      index = a.index
+      break
+  if index is not None and index != torch.cuda.current_device():
+    with torch.cuda.device(index):
+      rc = _invoke(fn, name, args)
   else:
-    a = torch.cuda.Event(enable_timing=True)
-    b = torch.cuda.Event(enable_timing=True)
-    a.record()
-    rc = fn(*args)
-    b.record()
-    _timer.records.append((name, a, b))
+    rc = _invoke(fn, name, args)
   check(rc, name)
+
+
+def _invoke(fn, name, args):
+  if _timer is None:
+    return fn(*args)
+  a = torch.cuda.Event(enable_timing=True)
+  b = torch.cuda.Event(enable_timing=True)
+  a.record()
+  rc = fn(*args)
+  b.record()
+  _timer.records.append((name, a, b))
+  return rc
 
 
 def dtype_code(dtype: torch.dtype) -> int:
@@ -171,17 +202,44 @@ _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
 def stream_ptr(device=None):
-  """The current CUDA stream of ``device`` as a ``cudaStream_t``.  torch.cuda.current_stream() builds a Stream object
-  (10 us, fourteen times per frame); the raw handle is all the C ABI needs."""
-  if _raw_stream is not None:
-    if device is None:
+  """The current CUDA stream of ``device`` as a ``cudaStream_t`` (a StreamHandle: ``call`` reads the device index off
+  it).  torch.cuda.current_stream() builds a Stream object (10 us, fourteen times per frame); the raw handle is all
+  the C ABI needs."""
+  if device is None:
+    index = torch.cuda.current_device()
+  else:
+    index = device.index if isinstance(device, torch.device) else int(device)
+    if index is None:
       index = torch.cuda.current_device()
-    else:
-      index = device.index if isinstance(device, torch.device) else int(device)
-      if index is None:
-        index = torch.cuda.current_device()
-    return ctypes.c_void_p(_raw_stream(index))
-  return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+  if _raw_stream is not None:
+    h = StreamHandle(_raw_stream(index))
+  else:
+    h = StreamHandle(torch.cuda.current_stream(index).cuda_stream)
+  h.index = index
+  return h
+
+
+class PinnedWords:
+  """Ring of pinned int32 words per device for asynchronous read-backs of device-side counts (visible gaussians,
+  tile overlaps).  Every read-back takes the NEXT word, so a second projection / mapper front enqueued on the same
+  stream before the first one's count has been consumed (pipelined views) cannot overwrite it; pinned allocations are
+  made once per device (cudaHostAlloc is a millisecond-scale call)."""
+  SLOTS = 64
+
+  def __init__(self):
+    self._rings = {}
+
+  def take(self, device) -> torch.Tensor:
+    key = (device.type, device.index)
+    ring = self._rings.get(key)
+    if ring is None:
+      ring = self._rings[key] = [torch.zeros((self.SLOTS,), dtype=torch.int32).pin_memory(), 0]
+    words, nxt = ring
+    ring[1] = (nxt + 1) % self.SLOTS
+    return words[nxt:nxt + 1]
+
+
+pinned_words = PinnedWords()
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:

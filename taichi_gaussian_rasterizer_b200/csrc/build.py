@@ -63,17 +63,30 @@ def _compile(src: str, verbose: bool, ptxas_info: bool) -> Path:
   return obj
 
 
-def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> Path:
-  if not force and OUT.exists() and OUT.stat().st_mtime >= _newest_input():
-    return OUT
+def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False, precise_point_kernels: bool = False) -> Path:
+  """``precise_point_kernels``: a second library, libgsplat_b200_precise.so, whose point_kernels.cu is compiled WITHOUT
+  --use_fast_math — only for benchmarks/fast_math_cost.py, which measures what the flag costs in gradient accuracy and
+  buys in time (the product library is always the default build)."""
+  out = PKG / "libgsplat_b200_precise.so" if precise_point_kernels else OUT
+  if not force and out.exists() and out.stat().st_mtime >= _newest_input():
+    return out
   OBJ.mkdir(parents=True, exist_ok=True)
-  with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as pool:
-    objs = list(pool.map(lambda s: _compile(s, verbose, ptxas_info), SOURCES))
-  cmd = [nvcc(), *host_compiler_args(), *ARCH, "-shared", "-o", str(OUT), *[str(o) for o in objs]]
+  if precise_point_kernels:   # every other object is shared with the default build
+    build(force, verbose, ptxas_info)
+    obj = OBJ / "point_kernels_precise.o"
+    cmd = [nvcc(), *host_compiler_args(), *ARCH, *COMMON, "-c", str(CSRC / "point_kernels.cu"), "-o", str(obj)]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+      raise RuntimeError(f"nvcc failed for point_kernels.cu (precise):\n{r.stdout}")
+    objs = [obj if s == "point_kernels.cu" else OBJ / s.replace(".cu", ".o") for s in SOURCES]
+  else:
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as pool:
+      objs = list(pool.map(lambda s: _compile(s, verbose, ptxas_info), SOURCES))
+  cmd = [nvcc(), *host_compiler_args(), *ARCH, "-shared", "-o", str(out), *[str(o) for o in objs]]
   r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
   if r.returncode != 0:
     raise RuntimeError(f"link failed:\n{' '.join(cmd)}\n{r.stdout}")
-  return OUT
+  return out
 
 
 if __name__ == "__main__":
@@ -81,5 +94,6 @@ if __name__ == "__main__":
   ap.add_argument("--force", action="store_true")
   ap.add_argument("--verbose", action="store_true")
   ap.add_argument("--ptxas-info", action="store_true")
+  ap.add_argument("--precise-point-kernels", action="store_true")
   args = ap.parse_args()
-  print(build(args.force, args.verbose, args.ptxas_info))
+  print(build(args.force, args.verbose, args.ptxas_info, args.precise_point_kernels))

@@ -27,8 +27,6 @@
 // them, no shuffles) was built and measured in round 1: same instruction count, lower issue rate (1.74 vs 1.58 ms
 // on the bench workload), so it was dropped (kernel table).
 // F is a template parameter (1..7 here, wider F takes raster_generic.cu).
-#include <cstdlib>
-
 #include "raster_fast.cuh"
 
 namespace gs {
@@ -236,6 +234,9 @@ raster_bwd_moments_kernel(int64_t V, const float* __restrict__ g2d, float* __res
   float* m = grad_pts + 7 * i;
   const float* g = g2d + 7 * i;
   const float M0 = m[0], Mt = m[1], Ms = m[2], Mtt = m[3], Mss = m[4], Mts = m[5];
+  // a gaussian no pixel accumulated into keeps its zero row: rows with alpha == 0 or sigma == 0 (padding, inactive
+  // points handed to rasterize() directly) would otherwise turn 0 / 0 and 0 * inf into NaN
+  if (M0 == 0.f && Mt == 0.f && Ms == 0.f && Mtt == 0.f && Mss == 0.f && Mts == 0.f) return;
   const float c = g[2], s = g[3], sx = g[4], sy = g[5], a0 = g[6];
   const float isx = 1.0f / sx, isy = 1.0f / sy;
   constexpr float ik = 1.f / kSqrtHalfLog2e, ik2 = 1.f / kHalfLog2e;
@@ -256,30 +257,15 @@ static int launch_bwd_fast(const GsRasterParams& p, const RasterArgs& a, const f
   const int tiles = tiles_wide(p) * tiles_high(p);
   const bool heur = p.compute_point_heuristic && a.point_heuristic != nullptr;
   const unsigned char* cmask = (const unsigned char*)a.workspace + fast_layout(p).off_mask;
-#define GS_BWD_LAUNCH(HEURV, NSUBV)                                                                              \
-  raster_bwd_fast_kernel<F, FP, HEURV, NSUBV><<<tiles, (8 / NSUBV) * 32, 0, st>>>(                              \
+  // one warp per CTA, two CTAs per tile (NSUB = 4, SOLO), staged batches of 64 entries: the variant measured fastest
+  // in round 1 (1.236 ms against 1.251 ms with two warps per CTA, 1.70 ms with one warp per tile; batches of 32 / 128
+  // entries 1.243 / 1.460 ms).  The other instantiations were removed with their environment switches.
+#define GS_BWD_LAUNCH_SOLO(HEURV)                                                                                \
+  raster_bwd_fast_kernel<F, FP, HEURV, 4, true, 64><<<tiles * 2, 32, 0, st>>>(                                  \
       p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,   \
       (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr, cmask)
-  // NSUB = 4 (two warps per tile) measured faster than NSUB = 8 (one warp per tile, 96 registers): 1.58 vs 1.70 ms
-  static const int nsub = getenv("GS_BWD_NSUB") ? atoi(getenv("GS_BWD_NSUB")) : 4;   // experiment switches
-  static const int solo = getenv("GS_BWD_SOLO") ? atoi(getenv("GS_BWD_SOLO")) : 1;   // measured: 1.236 vs 1.251 ms
-  static const int batch = getenv("GS_BWD_BATCH") ? atoi(getenv("GS_BWD_BATCH")) : 64;
-#define GS_BWD_LAUNCH_SOLO_(HEURV, BATCHV)                                                                       \
-  raster_bwd_fast_kernel<F, FP, HEURV, 4, true, BATCHV><<<tiles * 2, 32, 0, st>>>(                              \
-      p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,   \
-      (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr, cmask)
-#define GS_BWD_LAUNCH_SOLO(HEURV)                                  \
-  do {                                                             \
-    if (batch == 32) GS_BWD_LAUNCH_SOLO_(HEURV, 32);               \
-    else if (batch == 128) GS_BWD_LAUNCH_SOLO_(HEURV, 128);        \
-    else GS_BWD_LAUNCH_SOLO_(HEURV, 64);                           \
-  } while (0)
-  if (solo) { if (heur) GS_BWD_LAUNCH_SOLO(true); else GS_BWD_LAUNCH_SOLO(false); }
-  else if (nsub == 8) { if (heur) GS_BWD_LAUNCH(true, 8); else GS_BWD_LAUNCH(false, 8); }
-  else if (heur) GS_BWD_LAUNCH(true, 4); else GS_BWD_LAUNCH(false, 4);
+  if (heur) GS_BWD_LAUNCH_SOLO(true); else GS_BWD_LAUNCH_SOLO(false);
 #undef GS_BWD_LAUNCH_SOLO
-#undef GS_BWD_LAUNCH_SOLO_
-#undef GS_BWD_LAUNCH
   GS_LAUNCH_CHECK();
   if (p.points_requires_grad && a.grad_gaussians != nullptr && p.num_points > 0) {
     raster_bwd_moments_kernel<<<(unsigned)ceil_div(p.num_points, 256), 256, 0, st>>>(

@@ -30,6 +30,8 @@ class GradientBucket:
     dtype, device = self.params[0].dtype, self.params[0].device
     sizes = [p.numel() for p in self.params]
     self.flat = torch.zeros((sum(sizes),), dtype=dtype, device=device)
+    self._early = None            # state of reduce_early(): (split offset, deferred objects on hold, work handle)
+    self._gather_buffers = {}     # all-gather targets of the last views' staged colour gradients, kept across steps
     off = 0
     for p, n in zip(self.params, sizes):
       p.grad = self.flat[off:off + n].view_as(p)
@@ -40,6 +42,7 @@ class GradientBucket:
     their deferred state is marked clean and the batch's first flush overwrites them (no 4 K D bytes per gaussian of
     zero fill, no read of the rows by that flush)."""
     from . import grad_sinks
+    assert self._early is None, "reduce_early() must be followed by all_reduce() before the bucket is zeroed"
     clean = [(p, grad_sinks.deferred_sh(p)) for p in self.params]
     clean = [(p, d) for p, d in clean if d is not None]
     if not clean:
@@ -93,28 +96,90 @@ class GradientBucket:
   def nbytes(self) -> int:
     return self.flat.numel() * self.flat.element_size()
 
+  # ------------------------------------------------------------------------------------------------ collectives
+  def _pending_split(self):
+    """(element offset where the deferred SH slices start, the deferred objects) when the bucket is laid out
+    [parameters without deferred state | parameters with it] and something is pending; else (None, [])."""
+    from . import grad_sinks
+    offs, off = {}, 0
+    for p in self.params:
+      offs[id(p)] = off
+      off += p.numel()
+    deferred = [(p, grad_sinks.deferred_sh(p)) for p in self.params]
+    deferred = [(p, d) for p, d in deferred if d is not None]
+    live = [(p, d) for p, d in deferred if d.pending or d.overwrite_next]
+    if not live:
+      return None, []
+    first = min(offs[id(p)] for p, _ in live)
+    tail = [p for p in self.params if offs[id(p)] >= first]
+    if 0 < first and all(any(q is p for q, _ in live) for p in tail):
+      return first, [d for _, d in live]
+    return None, []
+
+  def reduce_early(self, group=None):
+    """Call when all views of the batch EXCEPT THE LAST ONE of this rank have been back-propagated (every rank must
+    call it at the same point; no-op on a single rank).  The deferred SH coefficient gradients of the views so far are
+    flushed into the bucket and the SH slices — four fifths of the bucket's bytes — are all-reduced right away, on the
+    communicator's stream, UNDER the rendering of the last view.  The last view only stages its (N, 3) colour gradient
+    (the deferred state is put on hold, the slices are not touched while they are inside the collective);
+    ``all_reduce()`` then all-gathers those small staged gradients and camera centres from all ranks and adds
+    sum_ranks staged (x) basis to the reduced rows locally.  All-reduce is linear, so the result is the same sum."""
+    active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if not active or self._early is not None:
+      return
+    split, deferred = self._pending_split()
+    if split is None:
+      return
+    for d in deferred:
+      d.flush()
+      d.hold = True
+    work = dist.all_reduce(self.flat[split:], op=dist.ReduceOp.SUM, group=group, async_op=True)
+    self._early = (split, deferred, work)
+
+  def _finish_early(self, group):
+    split, deferred, work = self._early
+    self._early = None
+    world = dist.get_world_size(group)
+    gathered = []
+    for d in deferred:
+      pending, points = d.take_pending()
+      if not pending:
+        continue
+      # this rank's staged colour gradients (P, N, 3) and camera centres (P, 3) -> every rank's (world P, ...)
+      local = torch.stack([t for t, _ in pending])
+      cams = torch.stack([c.reshape(3) for _, c in pending])
+      key = (id(d), tuple(local.shape))
+      buf = self._gather_buffers.get(key)
+      if buf is None:
+        buf = self._gather_buffers[key] = (local.new_empty((world * local.shape[0], *local.shape[1:])),
+                                           cams.new_empty((world * cams.shape[0], 3)))
+      w1 = dist.all_gather_into_tensor(buf[0], local, group=group, async_op=True)
+      w2 = dist.all_gather_into_tensor(buf[1], cams, group=group, async_op=True)
+      gathered.append((d, points, buf, w1, w2))
+    # the geometry head follows the gathers on the communicator's stream and runs while the flush below computes
+    head = dist.all_reduce(self.flat[:split], op=dist.ReduceOp.SUM, group=group, async_op=True)
+    from . import grad_sinks
+    work.wait()
+    for d, points, (staged_all, cams_all), w1, w2 in gathered:
+      w1.wait()
+      w2.wait()
+      grad_sinks.flush_sh_views(d.sink, points, list(staged_all.unbind(0)), list(cams_all.unbind(0)), overwrite=False)
+    head.wait()
+
   def all_reduce(self, group=None, async_op: bool = False):
     """Sum the bucket over ranks (no-op without an initialised process group / single rank).  With deferred SH
     gradients pending, the part of the bucket that is already final (the geometry gradients in front of the SH slices)
-    is reduced while the flush kernel forms the SH rows, then the SH part follows."""
+    is reduced while the flush kernel forms the SH rows, then the SH part follows; after ``reduce_early()`` only the
+    geometry head and the last view's staged colour gradients are left to exchange."""
     active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     if not active:
       self.flush()
       return None
-    from . import grad_sinks
-    pending = [p for p in self.params if (d := grad_sinks.deferred_sh(p)) is not None and (d.pending or d.overwrite_next)]
-    split = None
-    if pending and not async_op:
-      # element offset of the first pending parameter; everything behind it must be pending too (the usual layout:
-      # [position, log_scaling, rotation, alpha_logit | feature])
-      off, offs = 0, {}
-      for p in self.params:
-        offs[id(p)] = off
-        off += p.numel()
-      first = min(offs[id(p)] for p in pending)
-      tail = [p for p in self.params if offs[id(p)] >= first]
-      if 0 < first and all(any(q is p for q in pending) for p in tail):
-        split = first
+    if self._early is not None:
+      assert not async_op, "all_reduce(async_op=True) after reduce_early() is not supported"
+      self._finish_early(group)
+      return None
+    split, deferred = (None, []) if async_op else self._pending_split()
     if split is None:
       self.flush()
       return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)

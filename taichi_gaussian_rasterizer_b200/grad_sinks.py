@@ -24,11 +24,27 @@ def grad_sink(param: torch.Tensor) -> Optional[torch.Tensor]:
 
 
 # ---------------------------------------------------------------------------------------------- deferred SH gradient
+def flush_sh_views(sink: torch.Tensor, points: torch.Tensor, staged, camera_positions, overwrite: bool):
+  """sink (N, K, D) (+)= sum_v staged_v (x) basis(points - camera_v): gs_sh_bwd_flush in chunks of MAX_VIEWS views
+  (the first chunk overwrites the rows when ``overwrite``, the others add)."""
+  import ctypes
+  from . import _native as N
+  n, k, d = sink.shape
+  for c0 in range(0, len(staged), DeferredSH.MAX_VIEWS):
+    chunk_s, chunk_c = staged[c0:c0 + DeferredSH.MAX_VIEWS], camera_positions[c0:c0 + DeferredSH.MAX_VIEWS]
+    nv = len(chunk_s)
+    p = N.GsSHParams(N.dtype_code(sink.dtype), k, d, 1, n, 0, 0 if (overwrite and c0 == 0) else 1, 1)
+    arr = ctypes.c_void_p * nv
+    N.call("gs_sh_bwd_flush", ctypes.byref(p), ctypes.c_int32(nv), arr(*[t.data_ptr() for t in chunk_s]),
+           arr(*[c.data_ptr() for c in chunk_c]), N.ptr(points), N.ptr(sink), N.stream_ptr(sink.device))
+
+
 class DeferredSH:
   """Pending spherical-harmonics coefficient gradients of a multi-view batch (csrc/point_kernels.cu, "deferred SH
   bwd"): every view stages its masked colour gradient (N, 3) with gs_sh_bwd_stage; ``flush`` adds
   sum_v staged_v (x) basis(position - camera_v) to the sink with ONE pass over the (N, 3, D) rows instead of one
-  read-modify-write pass per view.  Flushes by itself after GS_SH_MAX_DEFERRED_VIEWS views."""
+  read-modify-write pass per view.  Flushes by itself after MAX_VIEWS views, unless ``hold`` is set: then the sink is
+  not touched until someone takes the pending views (GradientBucket.reduce_early: the sink is inside an all-reduce)."""
   MAX_VIEWS = 16
 
   def __init__(self, sink: torch.Tensor):
@@ -36,6 +52,7 @@ class DeferredSH:
     self.pending = []      # (staged (N,3), camera_pos (3,))
     self.points = None     # (N,3) positions shared by the pending views
     self.overwrite_next = False   # the sink holds nothing yet (mark_clean): the next flush writes instead of adding
+    self.hold = False
 
   def mark_clean(self):
     """The caller declares the sink's content void (start of a batch): pending views are dropped and the next flush
@@ -43,34 +60,34 @@ class DeferredSH:
     self.pending = []
     self.points = None
     self.overwrite_next = True
+    self.hold = False
 
   def add(self, staged: torch.Tensor, camera_pos: torch.Tensor, points: torch.Tensor):
     if self.points is not None and (self.points.data_ptr() != points.data_ptr() or self.points.shape != points.shape):
+      assert not self.hold, "positions changed while the SH sink is held by an all-reduce"
       self.flush()
     self.points = points
     self.pending.append((staged, camera_pos))
-    if len(self.pending) >= self.MAX_VIEWS:
+    if len(self.pending) >= self.MAX_VIEWS and not self.hold:
       self.flush()
+
+  def take_pending(self):
+    """Hand the pending views to the caller (who will flush them itself) and release the hold."""
+    pending, points = self.pending, self.points
+    self.pending, self.points, self.hold = [], None, False
+    return pending, points
 
   def flush(self):
     if not self.pending and not self.overwrite_next:
       self.points = None
       return
-    import ctypes
-    from . import _native as N
-    n, k, d = self.sink.shape
-    nv = len(self.pending)
-    if nv == 0:   # clean sink, nothing staged: the rows become zeros
+    if len(self.pending) == 0:   # clean sink, nothing staged: the rows become zeros
       self.sink.zero_()
       self.overwrite_next = False
       return
-    p = N.GsSHParams(N.dtype_code(self.sink.dtype), k, d, 1, n, 0, 0 if self.overwrite_next else 1, 1)
+    flush_sh_views(self.sink, self.points, [t for t, _ in self.pending], [c for _, c in self.pending],
+                   self.overwrite_next)
     self.overwrite_next = False
-    arr = ctypes.c_void_p * nv
-    staged = arr(*[t.data_ptr() for t, _ in self.pending])
-    cams = arr(*[c.data_ptr() for _, c in self.pending])
-    N.call("gs_sh_bwd_flush", ctypes.byref(p), ctypes.c_int32(nv), staged, cams, N.ptr(self.points), N.ptr(self.sink),
-           N.stream_ptr(self.sink.device))
     self.pending = []
     self.points = None
 

@@ -32,16 +32,10 @@ from ..data_types import RasterConfig
 MAX_TILE = 65535  # 16 bit tile id inside the sorted key bits (tile_mapper.py:29)
 
 
-_pinned = {}
-
-
 def _pinned_total(device) -> torch.Tensor:
-  """One pinned int32 per device for the asynchronous read-back of the overlap total (reads are serialised by the
-  event wait that follows each copy)."""
-  key = (device.type, device.index, N.stream_ptr(device).value)   # one word per stream: streams do not serialise
-  if key not in _pinned:
-    _pinned[key] = torch.zeros((1,), dtype=torch.int32).pin_memory()
-  return _pinned[key]
+  """A pinned int32 word for the asynchronous read-back of the overlap total: the next slot of a per-device ring
+  (_native.PinnedWords), so overlapping read-backs on one stream never share a word."""
+  return N.pinned_words.take(device)
 
 
 def pad_to_tile(image_size: Tuple[Integral, Integral], tile_size: int):

@@ -21,16 +21,10 @@ from ..data_types import Gaussians3D, RasterConfig
 from .params import CameraParams
 
 
-_pinned = {}
-
-
 def _pinned_count(device) -> torch.Tensor:
-  """One pinned int32 per device for the asynchronous read-back of the visible count (reads are serialised by the
-  event wait that follows each copy)."""
-  key = (device.type, device.index, N.stream_ptr(device).value)   # one word per stream: streams do not serialise
-  if key not in _pinned:
-    _pinned[key] = torch.zeros((1,), dtype=torch.int32).pin_memory()
-  return _pinned[key]
+  """A pinned int32 word for the asynchronous read-back of the visible count: the next slot of a per-device ring
+  (_native.PinnedWords), so overlapping read-backs on one stream never share a word."""
+  return N.pinned_words.take(device)
 
 
 class _ProjectFunction(torch.autograd.Function):

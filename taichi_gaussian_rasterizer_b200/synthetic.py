@@ -85,3 +85,41 @@ def random_2d_gaussians(n, image_size: Tuple[int, int], num_channels=3, scale_fa
   return Gaussians2D(position=position, z_depth=depth, log_scaling=torch.log(scaling), rotation=rotation,
                      alpha_logit=torch_proj.inverse_sigmoid(alpha), feature=torch.rand(n, num_channels),
                      batch_size=(n,))
+
+
+# ----------------------------------------------------------------------------------------------- BASELINE.json scenes
+# The five configurations of BASELINE.json plus the workload its metric is quoted on ("bench"), as seeded synthetic
+# scenes: one definition shared by bench.py, benchmarks/configs.py and the full-size parity tests.
+BASELINE_SCENES = {
+  # metric workload: 3 M gaussians, SH degree 3, 2048x1365
+  "bench": dict(n=3_000_000, image_size=(2048, 1365), sh_degree=3, scale_factor=1.5),
+  # config 2: render_gaussians 3D, 1 M gaussians, SH degree 3, 1920x1080
+  "c2": dict(n=1_000_000, image_size=(1920, 1080), sh_degree=3),
+  # config 3: bicycle-scale, 6 M gaussians, Mip-NeRF360-like scale / opacity distribution, visibility + split/prune stats
+  "c3": dict(n=6_000_000, image_size=(2048, 1365), sh_degree=3, bimodal=True, stats=True),
+  # config 4: feature lifting, 2 M gaussians, 32 feature channels + depth / depth variance at 3840x2160
+  "c4": dict(n=2_000_000, image_size=(3840, 2160), channels=32, render_depth=True),
+  # config 5: one view of the batched multi-view step, 3 M gaussians at 1600x1064
+  "c5": dict(n=3_000_000, image_size=(1600, 1064), sh_degree=3, scale_factor=1.5),
+}
+
+
+def baseline_scene(name: str, seed: int = 0, n: Optional[int] = None, image_size: Optional[Tuple[int, int]] = None):
+  """(gaussians, camera, spec) of a BASELINE.json configuration on the CPU; ``n`` / ``image_size`` override the size
+  (the per gaussian scale follows n as in the recipe, so the screen coverage stays comparable).
+  ``bimodal`` = log-normal scales (sigma_ln = 1) and opacity mass near 0.05 and 0.95."""
+  spec = dict(BASELINE_SCENES[name])
+  if n is not None:
+    spec["n"] = n
+  if image_size is not None:
+    spec["image_size"] = tuple(image_size)
+  torch.manual_seed(seed)
+  cam = random_camera(image_size=spec["image_size"])
+  g = random_3d_gaussians(spec["n"], cam, scale_factor=spec.get("scale_factor", 1.0), sh_degree=spec.get("sh_degree"),
+                          num_channels=spec.get("channels", 3))
+  if spec.get("bimodal"):
+    g.log_scaling = g.log_scaling + torch.randn(spec["n"], 1)
+    u = torch.rand(spec["n"])
+    alpha = torch.where(u < 0.5, 0.02 + 0.08 * torch.rand(spec["n"]), 0.9 + 0.09 * torch.rand(spec["n"]))
+    g.alpha_logit = torch.logit(alpha).unsqueeze(1)
+  return g, cam, spec

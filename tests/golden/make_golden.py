@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Generates the golden fixtures of tests/golden/*.npz FROM THE REFERENCE ITSELF (needs /root/reference).
 
-  python tests/golden/make_golden.py [--only tile_map,raster,projection,sh,optim] [--quick]
+  python tests/golden/make_golden.py [--only tile_map,raster,raster2,projection,sh,optim,morton] [--quick]
 
 Two sources, both the reference's own code, unmodified, imported from /root/reference:
 
@@ -125,6 +125,46 @@ def make_raster(out, quick=False):
                 f"c{i}_visibility": np_(r.visibility), f"c{i}_point_heuristic": np_(r.point_heuristic),
                 f"c{i}_grad_gaussians": np_(gg.grad), f"c{i}_grad_features": np_(ff.grad)})
   out["num_cases"] = np.array(len(cases))
+
+
+# Round 2: the configuration the measured kernels run (tile 16, stride (2, 2), statistics on) with tile lists LONGER
+# than one group of 256 and C mod 256 != 0 (the reference's stale shared-memory slots, SURVEY Q1, now at tile 16 —
+# case 1 above only reaches it at tile 8), three groups per tile, 34 feature channels (BASELINE config 4) and the
+# antialiased pdf at tile 16.  Low opacities keep the pixels unsaturated so that the re-read stale slots show in the
+# image.  The emulator needs 5-30 minutes per case; `--cases` selects some, `--merge` joins per case files.
+RASTER2_CASES = [  # seed, n, (w, h), tile_size, pixel_stride, F, antialias, scale_factor, alpha_range
+  (6, 330, (16, 16), 16, (2, 2), 3, False, 6.0, (0.02, 0.1)),     # one tile, C = 330: two groups, 182 stale slots
+  (7, 48, (16, 16), 16, (2, 2), 34, False, 4.0, (0.1, 0.9)),      # F = 34
+  (8, 620, (32, 16), 16, (2, 2), 3, False, 6.0, (0.02, 0.08)),    # two tiles, three groups each
+  (9, 300, (16, 16), 16, (2, 2), 3, True, 6.0, (0.02, 0.1)),      # antialiased, two groups
+]
+
+
+def make_raster2(out, only=None):
+  for i, (seed, n, size, ts, stride, F, aa, sf, arange) in enumerate(RASTER2_CASES):
+    if only is not None and i not in only:
+      continue
+    g, depth, feat = scene2d(seed, n, size, F, sf, alpha_range=arange)
+    cfg = RasterConfig(tile_size=ts, pixel_stride=stride, antialias=aa, compute_visibility=True,
+                       compute_point_heuristic=True, blur_cov=0.0 if aa else 0.3)
+    o2p, ranges = map_to_tiles(g, depth, size, cfg)
+    torch.manual_seed(1000 + seed)
+    grad_image = torch.rand(size[1], size[0], F)
+    gg, ff = g.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    t0 = time.time()
+    r = rasterize_with_tiles(gg, ff, o2p, ranges.view(-1, 2), size, cfg)
+    t1 = time.time()
+    (r.image * grad_image).sum().backward()
+    counts = (ranges[..., 1] - ranges[..., 0]).view(-1)
+    print(f"raster2 case {i}: n={n} {size} tile {ts} stride {stride} F={F} aa={aa} tile lists {counts.tolist()} "
+          f"(fwd {t1 - t0:.0f}s bwd {time.time() - t1:.0f}s)", flush=True)
+    out.update({f"c{i}_gaussians": np_(g), f"c{i}_features": np_(feat), f"c{i}_image_size": np.array(size),
+                f"c{i}_tile_size": np.array(ts), f"c{i}_pixel_stride": np.array(stride), f"c{i}_antialias": np.array(int(aa)),
+                f"c{i}_overlap_to_point": np_(o2p), f"c{i}_tile_ranges": np_(ranges), f"c{i}_grad_image": np_(grad_image),
+                f"c{i}_image": np_(r.image), f"c{i}_image_weight": np_(r.image_weight),
+                f"c{i}_visibility": np_(r.visibility), f"c{i}_point_heuristic": np_(r.point_heuristic),
+                f"c{i}_grad_gaussians": np_(gg.grad), f"c{i}_grad_features": np_(ff.grad)})
+  out["num_cases"] = np.array(len(RASTER2_CASES))
 
 
 # ----------------------------------------------------------------------------------------------- projection
@@ -294,15 +334,27 @@ def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--only", default="tile_map,projection,sh,raster,optim,morton")
   ap.add_argument("--quick", action="store_true", help="raster: only the two cheapest cases")
+  ap.add_argument("--cases", default=None, help="raster2: comma separated case numbers (written to --out)")
+  ap.add_argument("--out", default=None, help="output path (default tests/golden/<name>.npz)")
+  ap.add_argument("--merge", nargs="*", default=None, help="raster2: join per case .npz files into raster2.npz")
   args = ap.parse_args()
+  if args.merge is not None:
+    out = {}
+    for f in args.merge:
+      out.update({k: v for k, v in np.load(f).items()})
+    np.savez_compressed(HERE / "raster2.npz", **out)
+    print(f"wrote {HERE / 'raster2.npz'} from {len(args.merge)} files, keys {len(out)}")
+    return
   for name in args.only.split(","):
     out = {}
     t0 = time.time()
     if name == "raster":
       make_raster(out, quick=args.quick)
+    elif name == "raster2":
+      make_raster2(out, only=None if args.cases is None else [int(c) for c in args.cases.split(",")])
     else:
       MAKERS[name](out)
-    path = HERE / f"{name}.npz"
+    path = Path(args.out) if args.out else HERE / f"{name}.npz"
     np.savez_compressed(path, **out)
     print(f"wrote {path} ({path.stat().st_size / 1024:.0f} KiB, {time.time() - t0:.0f}s)")
 

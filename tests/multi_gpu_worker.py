@@ -3,7 +3,9 @@
 GradientBucket.fused_accumulation (deferred SH gradient, batched SH colours) and the ranks all-reduce once; rank 0 then
 renders ALL views alone with plain autograd accumulation and compares.
 
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 benchmarks/check_multi_gpu.py
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_worker.py
+
+Launched by tests/test_gpu_multi.py (pytest -m gpu; skipped on boxes with fewer than two GPUs).  Exit code 0 = parity.
 """
 import os
 import sys
@@ -37,7 +39,7 @@ def main():
   cams = [c.to(device=dev) for c in cams]
   cfg = RasterConfig()
 
-  def grads(view_ids, fused):
+  def grads(view_ids, fused, early=False):
     g = g_cpu.to(device=dev)
     g.requires_grad_(True)
     bucket = GradientBucket([g.position, g.log_scaling, g.rotation, g.alpha_logit, g.feature])
@@ -46,7 +48,9 @@ def main():
         bucket.zero_()
         mine = [cams[i] for i in view_ids]
         colors = evaluate_sh_views(g.feature, g.position, [c.camera_position for c in mine])
-        for c, col in zip(mine, colors):
+        for vi, (c, col) in enumerate(zip(mine, colors)):
+          if early and vi == len(mine) - 1:
+            bucket.reduce_early()   # SH slices reduced under the last view; its colour gradients are all-gathered
           render_gaussians(g, c, cfg, use_sh=True, sh_colors=col).image.square().mean().backward()
         bucket.all_reduce()
     else:
@@ -54,13 +58,16 @@ def main():
         render_gaussians(g, cams[i], cfg, use_sh=True).image.square().mean().backward()
     return bucket.flat.clone()
 
-  reduced = grads(partition_views(views, rank, world), fused=True)
+  mine = partition_views(views, rank, world)
+  reduced = {"all-reduce at the end": grads(mine, fused=True), "reduce_early + gather": grads(mine, fused=True, early=True)}
   ok = True
   if rank == 0:
     ref = grads(list(range(views)), fused=False)
-    err = ((reduced.double() - ref.double()).norm() / ref.double().norm()).item()
-    ok = err < 1e-5 and ref.abs().sum().item() > 0
-    print(f"world {world}: all-reduced gradient of {views} views vs single-GPU sum: rel l2 {err:.2e} -> {'OK' if ok else 'FAIL'}")
+    for what, flat in reduced.items():
+      err = ((flat.double() - ref.double()).norm() / ref.double().norm()).item()
+      good = err < 1e-5 and ref.abs().sum().item() > 0
+      ok = ok and good
+      print(f"world {world}: {what}: gradient of {views} views vs single-GPU sum: rel l2 {err:.2e} -> {'OK' if good else 'FAIL'}")
   dist.barrier()
   dist.destroy_process_group()
   sys.exit(0 if ok else 1)

@@ -119,3 +119,70 @@ def test_view_parallel_gradients_equal_serial_sum(tmp_path):
   assert bucket.flat.abs().sum() > 0
   assert rel_l2(results[0]["flat"], bucket.flat) < 1e-4
   assert rel_l2(results[0]["vis"], vis) < 1e-4
+
+
+# ------------------------------------------------------------------------------------- reduce_early (host logic on gloo)
+def _torch_flush(sink, points, staged, camera_positions, overwrite):
+  """What gs_sh_bwd_flush computes, in torch: sink (+)= sum_v staged_v (x) basis(points - camera_v)."""
+  from oracle import torch_ref
+  n, k, d = sink.shape
+  degree = int(round(d ** 0.5)) - 1
+  total = torch.zeros_like(sink)
+  for g, c in zip(staged, camera_positions):
+    dirs = torch.nn.functional.normalize(points - c.reshape(1, 3), dim=1)
+    total += g.unsqueeze(2) * torch_ref.rsh_cart(degree, dirs).unsqueeze(1)
+  if overwrite:
+    sink.copy_(total)
+  else:
+    sink.add_(total)
+
+
+def _early_worker(rank, world, port, out_dir):
+  from taichi_gaussian_rasterizer_b200 import grad_sinks
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    torch.set_num_threads(1)
+    grad_sinks.flush_sh_views = _torch_flush   # the CUDA flush kernel's arithmetic, on the CPU
+    n, views = 50, 3
+    g = torch.Generator().manual_seed(3)
+    points = torch.randn(n, 3, generator=g)
+    geometry = torch.zeros(n, 3, requires_grad=True)
+    sh = torch.zeros(n, 3, 4, requires_grad=True)
+    bucket = GradientBucket([geometry, sh])
+    deferred = grad_sinks.register_deferred_sh(sh, sh.grad)
+    bucket.zero_()
+    expected_sh = torch.zeros(n, 3, 4)
+    expected_geo = torch.zeros(n, 3)
+    gen = torch.Generator().manual_seed(100)
+    for r in range(world):          # every rank draws every rank's inputs, and uses its own
+      for v in range(views):
+        staged, cam, geo = torch.randn(n, 3, generator=gen), torch.randn(3, generator=gen), torch.randn(n, 3, generator=gen)
+        _torch_flush(expected_sh, points, [staged], [cam], overwrite=False)
+        expected_geo += geo
+        if r == rank:
+          geometry.grad.add_(geo)
+          deferred.add(staged, cam, points)
+          if v == views - 2:
+            bucket.reduce_early()   # everything but the last view: SH slice reduced now, deferred state on hold
+            assert deferred.hold and not deferred.pending
+    assert len(deferred.pending) == 1
+    bucket.all_reduce()
+    assert not deferred.hold and not deferred.pending and bucket._early is None
+    grad_sinks.unregister_deferred_sh(sh)
+    torch.save({"sh": sh.grad.clone(), "geo": geometry.grad.clone(), "expected_sh": expected_sh,
+                "expected_geo": expected_geo}, os.path.join(out_dir, f"early{rank}.pt"))
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_reduce_early_then_gather_equals_plain_sum(tmp_path):
+  """GradientBucket.reduce_early(): SH slices all-reduced before the last view, the last view's staged colour
+  gradients all-gathered and flushed by every rank — same sums as flushing everything and reducing once."""
+  world = 2
+  mp.spawn(_early_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+  for r in range(world):
+    res = torch.load(tmp_path / f"early{r}.pt")
+    assert rel_l2(res["sh"], res["expected_sh"]) < 1e-6
+    assert rel_l2(res["geo"], res["expected_geo"]) < 1e-6

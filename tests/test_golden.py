@@ -147,6 +147,29 @@ def test_oracle_sh_matches_reference(i):
     assert torch.allclose(g, T(d[f"c{i}_grad_{n}"]), rtol=1e-7, atol=1e-10), f"grad {n}"
 
 
+@pytest.mark.parametrize("i", cases("projection"))
+def test_oracle_projection_backward_matches_reference(i):
+  """oracle.projection_backward (the hand restated reverse sweep, f64) against the gradients torch autograd gave
+  through the reference's UNMODIFIED torch_lib/projection.py `apply` (make_golden.py), all six inputs; and its f32
+  instantiation against the same gradients where the eigen decomposition is well conditioned."""
+  d = load("projection")
+  names, ts, size, drange, blur = proj_inputs(d, i, torch.float64)
+  idx = T(d[f"c{i}_torch_indexes"])
+  go_p, go_z = T(d[f"c{i}_grad_out_points"]), T(d[f"c{i}_grad_out_depth"])
+  grads, cond = oracle.projection_backward(*ts, size, idx, go_p, go_z, blur_cov=blur)
+  for n in names:
+    ref = T(d[f"c{i}_grad_{n}"])
+    assert torch.allclose(grads[n].reshape(ref.shape), ref, rtol=1e-7, atol=1e-10), f"{n}: {rel_l2(grads[n].reshape(ref.shape), ref)}"
+  _, ts32, _, _, _ = proj_inputs(d, i, torch.float32)
+  g32, cond32 = oracle.projection_backward(*ts32, size, idx, go_p.float(), go_z.float(), blur_cov=blur)
+  good = torch.zeros(ts[0].shape[0], dtype=torch.bool)
+  good[idx[(cond.min(dim=1).values > 0.05)]] = True
+  assert int(good.sum()) > 0.5 * idx.shape[0]
+  for n in ("position", "log_scaling", "rotation", "alpha_logit"):
+    ref = T(d[f"c{i}_grad_{n}"])[good]
+    assert rel_l2(g32[n][good], ref) < GRAD_REL_L2, f"f32 {n}: {rel_l2(g32[n][good], ref)}"
+
+
 # ----------------------------------------------------------------------------------------------- CUDA path
 @pytest.mark.gpu
 @pytest.mark.parametrize("i", cases("tile_map"))

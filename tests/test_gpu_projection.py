@@ -81,6 +81,49 @@ def test_projection_f32_grads_within_tolerance(cuda_device):
     assert errs[n] < max(GRAD_REL_L2, 1.5 * base[n]), f"{n}: cuda {errs} torch-f32 {base}"
 
 
+COND_MIN = 0.02   # sqrt(gap) / trace and |n| / trace of the projected covariance, both above this
+
+
+@pytest.mark.parametrize("seed,n,scale,blur", [(7, 20000, 0.3, 0.3), (8, 60000, 1.0, 0.3), (9, 20000, 0.5, 0.0)])
+def test_projection_f32_grads_vs_f32_restatement(cuda_device, seed, n, scale, blur):
+  """north_star: gradients within 1e-4 relative L2.  The reference pins the projection gradients in float64 only
+  (tests/test_projection.py:76-96); for float32 the comparator is oracle.projection_backward<float>: the same reverse
+  sweep in plain IEEE binary operations (no MUFU approximations, no FMA contraction), itself pinned in f64 against the
+  reference's torch_lib autograd (tests/test_golden.py).  The eigen decomposition divides by sqrt(gap) and |n|
+  (generic.py:216-230): where either is below COND_MIN of the trace (1 % of the gaussians of these scenes) ANY f32
+  evaluation carries O(1/cond) relative error - the f32 restatement differs from its own f64 instantiation by 1e-2 /
+  1e-1 (log_scaling / rotation) over all gaussians and by 4e-6 / 1e-5 on the conditioned ones - so the 1e-4 bound is
+  asserted on the conditioned set, against both the f32 and the f64 restatement, and the fraction kept is asserted."""
+  g, cam = scene3d(seed, n, margin=0.3, scale_factor=scale)
+  torch.manual_seed(seed + 100)
+  ts = [t.detach().clone().to(device=cuda_device).requires_grad_(True) for t in
+        (*g.shape_tensors(), cam.T_camera_world, cam.projection)]
+  pts, depth, idx = gpu_proj.apply(*ts, cam.image_size, cam.depth_range, blur_cov=blur)
+  go_p, go_z = torch.randn(idx.shape[0], 7), torch.randn(idx.shape[0], 1)
+  ((pts * go_p.to(cuda_device)).sum() + (depth * go_z.to(cuda_device)).sum()).backward()
+  names = ["position", "log_scaling", "rotation", "alpha_logit", "T_camera_world", "projection"]
+  got = {k: t.grad.cpu() for k, t in zip(names, ts)}
+  args = (*g.shape_tensors(), cam.T_camera_world, cam.projection)
+  r32, cond = oracle.projection_backward(*args, cam.image_size, idx.cpu(), go_p, go_z, blur_cov=blur)
+  r64, _ = oracle.projection_backward(*[a.double() for a in args], cam.image_size, idx.cpu(), go_p.double(),
+                                      go_z.double(), blur_cov=blur)
+  good = torch.zeros(n, dtype=torch.bool)
+  good[idx.cpu()[cond.min(dim=1).values > COND_MIN]] = True
+  frac = float(good.sum()) / idx.shape[0]
+  errs = {k: (rel_l2(got[k][good], r32[k][good]), rel_l2(got[k][good], r64[k][good]), rel_l2(got[k], r64[k]))
+          for k in names[:4]}
+  cam_errs = {k: rel_l2(got[k], r64[k]) for k in names[4:]}
+  print(f"conditioned fraction {frac:.4f}; (vs f32, vs f64, all vs f64): {errs}; camera: {cam_errs}")
+  assert frac > 0.97
+  for k, (e32, e64, _) in errs.items():
+    assert e32 < GRAD_REL_L2 and e64 < GRAD_REL_L2, f"{k}: {errs}"
+  # camera gradients are sums over ALL gaussians, the ill conditioned ones included: what plain f32 gives (the f32
+  # restatement itself is 1e-3 from f64 there)
+  base = {k: rel_l2(r32[k], r64[k]) for k in names[4:]}
+  for k in names[4:]:
+    assert cam_errs[k] < max(GRAD_REL_L2, 3 * base[k]), f"{k}: cuda {cam_errs} f32 restatement {base}"
+
+
 def test_projection_gradcheck_f64(cuda_device):
   for seed in range(5):
     g, cam = scene3d(200 + seed, 12, margin=0.2, scale_factor=0.3)
