@@ -238,7 +238,8 @@ typedef struct GsRasterParams {
   int32_t workspace_holds_packed;    /* bwd: the workspace is untouched since a gs_raster_fwd call made with the same
                                         gaussians / features AND a requires_grad flag set (fwd then packs the
                                         backward records too); 0 = repack */
-  int32_t reserved_;
+  int32_t kernel_variant;            /* 0 = the shipped kernels; other values select alternative instantiations for
+                                        A/B timing (benchmarks/variants.py); every value gives the same results */
   int64_t num_points;                /* V */
   int64_t num_overlaps;              /* K */
   double clamp_max_alpha, alpha_threshold, saturate_threshold;

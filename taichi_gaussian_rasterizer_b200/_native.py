@@ -53,7 +53,7 @@ class GsRasterParams(ctypes.Structure):
               ("compute_point_heuristic", ctypes.c_int32), ("points_requires_grad", ctypes.c_int32),
               ("features_requires_grad", ctypes.c_int32), ("emulate_stale_tail", ctypes.c_int32),
               ("pixel_stride_x", ctypes.c_int32), ("pixel_stride_y", ctypes.c_int32),
-              ("workspace_holds_packed", ctypes.c_int32), ("reserved_", ctypes.c_int32),
+              ("workspace_holds_packed", ctypes.c_int32), ("kernel_variant", ctypes.c_int32),
               ("num_points", ctypes.c_int64), ("num_overlaps", ctypes.c_int64),
               ("clamp_max_alpha", ctypes.c_double), ("alpha_threshold", ctypes.c_double),
               ("saturate_threshold", ctypes.c_double), ("forward_exit_transmittance", ctypes.c_double)]

@@ -32,20 +32,22 @@
 namespace gs {
 
 
-// NSUB = 4: two warps per tile, each owns a 16x8 region; NSUB = 8: one warp owns the whole 16x16 tile.
-// A region is NSUB sub-blocks of 8x4 pixels; lane l owns pixel (l & 7, l >> 3) of every sub-block.
-// SOLO: one warp per CTA ((8 / NSUB) CTAs per tile): every warp stages the tile list for itself and never waits for
-// its neighbour at a block barrier.
-template <int F, int FP, bool HEUR, int NSUB, bool SOLO = false, int BATCH = 64>
-__global__ void __launch_bounds__(SOLO ? 32 : (8 / NSUB) * 32)
+// One warp per CTA, two CTAs per tile: a warp owns a 16x8 region = NSUB = 4 sub-blocks of 8x4 pixels, lane l owns pixel
+// (l & 7, l >> 3) of every sub-block, stages the tile list for itself and never waits for its neighbour at a block
+// barrier (measured against two warps per CTA and one warp per tile in round 1).
+// PAIR: survivors are reduced two at a time — one transposed butterfly over 2 NV values (every exchange step halves
+// the live values, so 18 values cost 9 + 5 + 3 + 2 + 1 shuffles where two separate reductions of 9 cost 2 x 12) and
+// one red.global.add instruction with 2 NV owning lanes; an odd survivor left at the end of the tile is reduced alone.
+template <int F, int FP, bool HEUR, bool PAIR>
+__global__ void __launch_bounds__(32, PAIR ? 32 : 1)
 raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
                        const float* __restrict__ featP, const int32_t* __restrict__ ranges,
                        const int32_t* __restrict__ o2p, const float* __restrict__ image,
                        const float* __restrict__ grad_image, float* __restrict__ grad_pts,
                        float* __restrict__ grad_feat, float* __restrict__ heuristic,
                        const unsigned char* __restrict__ cull_mask) {
-  constexpr int kThreads = SOLO ? 32 : (8 / NSUB) * 32;
-  constexpr int kBwdBatch = BATCH;   // staged tile-list entries per buffer
+  constexpr int NSUB = 4;
+  constexpr int kBwdBatch = 64;   // staged tile-list entries per buffer (32 / 128 measured slower)
   constexpr int NM = 6;  // moments: g, g u, g w, g u^2, g w^2, g u w
   constexpr int NV = NM + F + (HEUR ? 2 : 0);
   // one staged entry = {record (2 x float4), feature row (FP / 4 x float4)} in consecutive 16 B units: one address per
@@ -54,27 +56,33 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
   __shared__ __align__(16) float4 s_e[2][kBwdBatch][U];
   __shared__ unsigned char s_mask[2][kBwdBatch];   // cull bytes of the staged entries (raster_cull_mask_kernel)
 
-  const int t = threadIdx.x, lane = t & 31;
-  const int tile = SOLO ? blockIdx.x / (8 / NSUB) : blockIdx.x;
-  const int warp = SOLO ? blockIdx.x % (8 / NSUB) : t >> 5;
+  const int lane = threadIdx.x;
+  const int tile = blockIdx.x >> 1, warp = blockIdx.x & 1;
   const int tw = (p.image_width + kFastTile - 1) / kFastTile;
   const int ox = (tile % tw) * kFastTile, oy = (tile / tw) * kFastTile + warp * (NSUB * 2);
   const int x0 = ox + (lane & 7), y0 = oy + (lane >> 3);
   const float px0 = (float)x0 + 0.5f, py0 = (float)y0 + 0.5f;
-  const float bx = (float)ox + 0.5f, by = (float)oy + 0.5f;
   const float thr = (float)p.alpha_threshold, cmax = (float)p.clamp_max_alpha, sat = (float)p.saturate_threshold;
-  const float l2thr = log2f(thr);
 
-  // which reduced value this lane commits, and where
-  const int own = reduce_owner<NV>(lane);
-  float* own_base = nullptr;
-  unsigned own_stride = 0;   // element offsets stay below 2^31 (raster_fast_supported caps the point count)
-  if (own >= 0 && own < NM) {
-    if (p.points_requires_grad && grad_pts != nullptr) { own_base = grad_pts + own; own_stride = 7; }
-  } else if (own >= NM && own < NM + F) {
-    if (p.features_requires_grad && grad_feat != nullptr) { own_base = grad_feat + (own - NM); own_stride = F; }
-  } else if (HEUR && own >= NM + F && own < NV) {
-    own_base = heuristic + (own - NM - F); own_stride = 2;
+  // which reduced value this lane commits, and where: value `own` of a single reduction; in a paired reduction values
+  // 0 .. NV-1 belong to the first gaussian of the pair and NV .. 2 NV-1 to the second
+  auto owner_target = [&](int own, float*& base, unsigned& stride) {
+    base = nullptr; stride = 0;   // element offsets stay below 2^31 (raster_fast_supported caps the point count)
+    if (own >= 0 && own < NM) {
+      if (p.points_requires_grad && grad_pts != nullptr) { base = grad_pts + own; stride = 7; }
+    } else if (own >= NM && own < NM + F) {
+      if (p.features_requires_grad && grad_feat != nullptr) { base = grad_feat + (own - NM); stride = F; }
+    } else if (HEUR && own >= NM + F && own < NV) {
+      base = heuristic + (own - NM - F); stride = 2;
+    }
+  };
+  float* own_base; unsigned own_stride;
+  owner_target(reduce_owner<NV>(lane), own_base, own_stride);
+  float* pair_base = nullptr; unsigned pair_stride = 0; bool pair_second = false;
+  if constexpr (PAIR) {
+    const int own2 = reduce_owner<2 * NV>(lane);
+    pair_second = own2 >= NV;
+    owner_target(own2 < 0 ? -1 : (pair_second ? own2 - NV : own2), pair_base, pair_stride);
   }
 
   // Per pixel state: W, the image gradient G and RG = sum_c R_c G_c.  The replay only ever needs the remaining
@@ -101,7 +109,7 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
   auto issue_load = [&](int b) {
     const int buf = b & 1;
 #pragma unroll
-    for (int s = t; s < kBwdBatch; s += kThreads) {
+    for (int s = lane; s < kBwdBatch; s += 32) {
       const int v = b * kBwdBatch + s;
       if (v < C) {
         const int idx = o2p[start + v];
@@ -116,12 +124,71 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
     cp_async_commit();
   };
 
+  // One survivor: the partial sums of this lane's (up to four) pixels in v[0 .. NV), the gaussian's index returned.
+  // bm[i] bit jl = sub-block i can be reached at all (warp-uniform).
+  auto evaluate = [&](const float4* ent, const unsigned (&bm)[NSUB], int jl, float* v) -> unsigned {
+    const float4 r0 = ent[0], r1 = ent[1];
+    const float mx = r0.x, my = r0.y, a1x = r0.z, a1y = r0.w, a2x = r1.x, a2y = r1.y, l2a = r1.z;
+    float f[F];
+#pragma unroll
+    for (int c = 0; c < F; ++c) f[c] = reinterpret_cast<const float*>(ent + 2)[c];
+
+    float M0 = 0.f, Mu = 0.f, Mw = 0.f, Muu = 0.f, Mww = 0.f, Muw = 0.f, h0 = 0.f, h1 = 0.f;
+    float gf[F];
+#pragma unroll
+    for (int c = 0; c < F; ++c) gf[c] = 0.f;
+    const float dxb = px0 - mx, dyb = py0 - my;
+#pragma unroll
+    for (int i = 0; i < NSUB; ++i) {
+      if ((bm[i] >> jl) & 1u) {  // warp-uniform: this sub-block can be reached at all
+        const float dx = (i & 1) ? dxb + 8.f : dxb, dy = (i >> 1) ? dyb + 4.f * (i >> 1) : dyb;   // no x + 0.f
+        const float tx = fmaf(dy, a1y, dx * a1x), ty = fmaf(dy, a2y, dx * a2x);   // k x offset / sigma, own frame
+        const float araw = fast_ex2(fmaf(-ty, ty, fmaf(-tx, tx, l2a)));   // alpha0 p, as the forward forms it
+        if (araw > thr && W[i] < sat) {
+          const float alpha = fminf(araw, cmax);
+          const float Ti = 1.f - W[i];
+          const float w = alpha * Ti;
+          W[i] += w;
+          const float rinv = fast_rcp(1.f - alpha);
+          float fG = 0.f;
+#pragma unroll
+          for (int c = 0; c < F; ++c) {
+            fG = fmaf(f[c], Gd[i][c], fG);
+            gf[c] = fmaf(w, Gd[i][c], gf[c]);
+          }
+          RG[i] = fmaf(-fG, w, RG[i]);
+          const float ag = fmaf(fG, Ti, -RG[i] * rinv);   // dL/dalpha
+          const float gp = ag * araw;                     // alpha0 x the dL/dalpha0 share of this pixel
+          const float gu = gp * tx, gw = gp * ty;
+          M0 += gp; Mu += gu; Mw += gw;
+          Muu = fmaf(gu, tx, Muu); Mww = fmaf(gw, ty, Mww); Muw = fmaf(gu, ty, Muw);
+          if (HEUR) {
+            const float aag = fast_ex2(l2a) * ag;
+            h0 = fmaf(aag, aag, h0);   // |d/dmean| of this pixel: g (tx a1 + ty a2) / k^2
+            h1 += (fabsf(fmaf(gu, a1x, gw * a2x)) + fabsf(fmaf(gu, a1y, gw * a2y))) * (1.f / kHalfLog2e);
+          }
+        }
+      }
+    }
+    v[0] = M0; v[1] = Mu; v[2] = Mw; v[3] = Muu; v[4] = Mww; v[5] = Muw;
+#pragma unroll
+    for (int c = 0; c < F; ++c) v[NM + c] = gf[c];
+    if (HEUR) { v[NM + F] = h0; v[NM + F + 1] = h1; }
+    return (unsigned)__float_as_int(r1.w);
+  };
+
   auto lane_done = [&]() {
     bool d = true;
 #pragma unroll
     for (int i = 0; i < NSUB; ++i) d = d && (W[i] >= sat);
     return d;
   };
+
+  // PAIR: the first survivor of a pair waits here (warp-uniform state) until the second one has been evaluated
+  float held[PAIR ? NV : 1];
+  unsigned held_idx = 0;
+  bool holding = false;
+
   bool warp_done = __all_sync(kFull, lane_done());
   if (nb > 0) issue_load(0);
   for (int b = 0; b < nb; ++b) {
@@ -132,7 +199,7 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
     } else {
       cp_async_wait<0>();
     }
-    if (SOLO) __syncwarp(); else __syncthreads();
+    __syncwarp();
     const int n_in = min(kBwdBatch, C - b * kBwdBatch);
     if (!warp_done) {
       for (int c0 = 0; c0 < n_in; c0 += 32) {
@@ -147,77 +214,43 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
         unsigned any = 0;
 #pragma unroll
         for (int i = 0; i < NSUB; ++i) any |= bm[i];
+        // the cull is tight (a survivor without a single hit is a fraction of a percent), so every survivor is
+        // reduced: no vote, a miss adds zeros
         while (any) {
           const int jl = __ffs(any) - 1;
           any &= any - 1;
-          const int j = c0 + jl;
-          const float4* ent = s_e[buf][j];
-          const float4 r0 = ent[0], r1 = ent[1];
-          const float mx = r0.x, my = r0.y, a1x = r0.z, a1y = r0.w, a2x = r1.x, a2y = r1.y, l2a = r1.z;
-          float f[F];
-#pragma unroll
-          for (int c = 0; c < F; ++c) f[c] = reinterpret_cast<const float*>(ent + 2)[c];
-
-          float M0 = 0.f, Mu = 0.f, Mw = 0.f, Muu = 0.f, Mww = 0.f, Muw = 0.f, h0 = 0.f, h1 = 0.f;
-          float gf[F];
-#pragma unroll
-          for (int c = 0; c < F; ++c) gf[c] = 0.f;
-          const float dxb = px0 - mx, dyb = py0 - my;
-#pragma unroll
-          for (int i = 0; i < NSUB; ++i) {
-            if ((bm[i] >> jl) & 1u) {  // warp-uniform: this sub-block can be reached at all
-              const float dx = (i & 1) ? dxb + 8.f : dxb, dy = (i >> 1) ? dyb + 4.f * (i >> 1) : dyb;   // no x + 0.f
-              const float tx = fmaf(dy, a1y, dx * a1x), ty = fmaf(dy, a2y, dx * a2x);   // k x offset / sigma, own frame
-              const float araw = fast_ex2(fmaf(-ty, ty, fmaf(-tx, tx, l2a)));   // alpha0 p, as the forward forms it
-              if (araw > thr && W[i] < sat) {
-                const float alpha = fminf(araw, cmax);
-                const float Ti = 1.f - W[i];
-                const float w = alpha * Ti;
-                W[i] += w;
-                const float rinv = fast_rcp(1.f - alpha);
-                float fG = 0.f;
-#pragma unroll
-                for (int c = 0; c < F; ++c) {
-                  fG = fmaf(f[c], Gd[i][c], fG);
-                  gf[c] = fmaf(w, Gd[i][c], gf[c]);
-                }
-                RG[i] = fmaf(-fG, w, RG[i]);
-                const float ag = fmaf(fG, Ti, -RG[i] * rinv);   // dL/dalpha
-                const float gp = ag * araw;                     // alpha0 x the dL/dalpha0 share of this pixel
-                const float gu = gp * tx, gw = gp * ty;
-                M0 += gp; Mu += gu; Mw += gw;
-                Muu = fmaf(gu, tx, Muu); Mww = fmaf(gw, ty, Mww); Muw = fmaf(gu, ty, Muw);
-                if (HEUR) {
-                  const float aag = fast_ex2(l2a) * ag;
-                  h0 = fmaf(aag, aag, h0);   // |d/dmean| of this pixel: g (tx a1 + ty a2) / k^2
-                  h1 += (fabsf(fmaf(gu, a1x, gw * a2x)) + fabsf(fmaf(gu, a1y, gw * a2y))) * (1.f / kHalfLog2e);
-                }
-              }
-            }
-          }
-          // the cull is tight (a survivor without a single hit is a fraction of a percent), so every survivor is
-          // reduced: no vote, a miss adds zeros
-          {
+          const float4* ent = s_e[buf][c0 + jl];
+          if constexpr (!PAIR) {
             float v[NV];
-            v[0] = M0; v[1] = Mu; v[2] = Mw; v[3] = Muu; v[4] = Mww; v[5] = Muw;
-#pragma unroll
-            for (int c = 0; c < F; ++c) v[NM + c] = gf[c];
-            if (HEUR) { v[NM + F] = h0; v[NM + F + 1] = h1; }
+            const unsigned idx = evaluate(ent, bm, jl, v);
             reduce_scatter_step<NV, 16>(v, lane);
-            if (own_base != nullptr) atomicAdd(own_base + (unsigned)__float_as_int(r1.w) * own_stride, v[0]);
+            if (own_base != nullptr) atomicAdd(own_base + idx * own_stride, v[0]);
+          } else if (!holding) {
+            held_idx = evaluate(ent, bm, jl, held);
+            holding = true;
+          } else {
+            float v[2 * NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] = held[k];
+            const unsigned idx = evaluate(ent, bm, jl, v + NV);
+            reduce_scatter_step<2 * NV, 16>(v, lane);
+            if (pair_base != nullptr) atomicAdd(pair_base + (pair_second ? idx : held_idx) * pair_stride, v[0]);
+            holding = false;
           }
         }
       }
       warp_done = __all_sync(kFull, lane_done());
     }
-    if (SOLO) {
-      __syncwarp();   // the buffer this iteration read is the one the next issue_load overwrites
-      if (warp_done) break;
-    } else if (__syncthreads_and(warp_done)) {
-      break;
-    }
+    __syncwarp();   // the buffer this iteration read is the one the next issue_load overwrites
+    if (warp_done) break;
   }
   cp_async_wait<0>();
+  if constexpr (PAIR) {
+    if (holding) {   // an odd survivor is left: reduce it alone
+      reduce_scatter_step<NV, 16>(held, lane);
+      if (own_base != nullptr) atomicAdd(own_base + held_idx * own_stride, held[0]);
+    }
+  }
 }
 
 // Moments -> gradient of the packed gaussian, in place in grad_gaussians (rows hold {M0, Mt, Ms, Mtt, Mss, Mts, 0}).
@@ -257,15 +290,15 @@ static int launch_bwd_fast(const GsRasterParams& p, const RasterArgs& a, const f
   const int tiles = tiles_wide(p) * tiles_high(p);
   const bool heur = p.compute_point_heuristic && a.point_heuristic != nullptr;
   const unsigned char* cmask = (const unsigned char*)a.workspace + fast_layout(p).off_mask;
-  // one warp per CTA, two CTAs per tile (NSUB = 4, SOLO), staged batches of 64 entries: the variant measured fastest
-  // in round 1 (1.236 ms against 1.251 ms with two warps per CTA, 1.70 ms with one warp per tile; batches of 32 / 128
-  // entries 1.243 / 1.460 ms).  The other instantiations were removed with their environment switches.
-#define GS_BWD_LAUNCH_SOLO(HEURV)                                                                                \
-  raster_bwd_fast_kernel<F, FP, HEURV, 4, true, 64><<<tiles * 2, 32, 0, st>>>(                                  \
+  // kernel_variant (benchmark A/B switch, 0 in production): bit 0 = reduce every survivor on its own
+  const bool pair = (p.kernel_variant & 1) == 0;
+#define GS_BWD_LAUNCH(HEURV, PAIRV)                                                                              \
+  raster_bwd_fast_kernel<F, FP, HEURV, PAIRV><<<tiles * 2, 32, 0, st>>>(                                        \
       p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,   \
       (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr, cmask)
-  if (heur) GS_BWD_LAUNCH_SOLO(true); else GS_BWD_LAUNCH_SOLO(false);
-#undef GS_BWD_LAUNCH_SOLO
+  if (heur) { if (pair) GS_BWD_LAUNCH(true, true); else GS_BWD_LAUNCH(true, false); }
+  else { if (pair) GS_BWD_LAUNCH(false, true); else GS_BWD_LAUNCH(false, false); }
+#undef GS_BWD_LAUNCH
   GS_LAUNCH_CHECK();
   if (p.points_requires_grad && a.grad_gaussians != nullptr && p.num_points > 0) {
     raster_bwd_moments_kernel<<<(unsigned)ceil_div(p.num_points, 256), 256, 0, st>>>(

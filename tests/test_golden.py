@@ -80,6 +80,41 @@ def test_oracle_rasterizer_matches_reference_kernels(i):
   check_raster(d, i, out, g.grad, f.grad)
 
 
+def cases2():
+  d = load("raster2")
+  return [i for i in range(int(d["num_cases"])) if f"c{i}_gaussians" in d.files]
+
+
+@pytest.mark.parametrize("i", cases2())
+def test_oracle_rasterizer_matches_reference_kernels_tile16(i):
+  """raster2.npz (round 2): the reference's kernels at tile 16 / stride (2, 2) / statistics on with tile lists of
+  330 and ~600 entries (two and three groups, C mod 256 != 0: stale slots at the measured configuration), 34 feature
+  channels, and the antialiased pdf."""
+  d = load("raster2")
+  size, cfg = raster_case(d, i)
+  g = T(d[f"c{i}_gaussians"]).requires_grad_(True)
+  f = T(d[f"c{i}_features"]).requires_grad_(True)
+  out = oracle.rasterize_with_tiles(g, f, T(d[f"c{i}_overlap_to_point"]), T(d[f"c{i}_tile_ranges"]).view(-1, 2), size, cfg)
+  (out.image * T(d[f"c{i}_grad_image"])).sum().backward()
+  check_raster(d, i, out, g.grad, f.grad)
+
+
+def test_raster2_fixture_exercises_stale_tail_at_tile16():
+  d = load("raster2")
+  hit = 0
+  for i in cases2():
+    size, cfg = raster_case(d, i)
+    ranges = T(d[f"c{i}_tile_ranges"]).view(-1, 2)
+    counts = ranges[:, 1] - ranges[:, 0]
+    if not ((counts > 256) & (counts % 256 != 0)).any() or cfg.antialias:
+      continue
+    hit += 1
+    args = (T(d[f"c{i}_gaussians"]), T(d[f"c{i}_features"]), T(d[f"c{i}_overlap_to_point"]), ranges, size, cfg)
+    img_off, _, _ = oracle.raster_forward(*args, emulate_stale_tail=False)
+    assert rel_l2(img_off, T(d[f"c{i}_image"])) > 100 * IMAGE_REL_L2, "fixture does not exercise the stale slots"
+  assert hit >= 1
+
+
 def test_raster_fixture_exercises_stale_tail():
   """Case 1 has tile lists longer than a block (C > A, C mod A != 0): without the stale-slot emulation
    the oracle must NOT match the reference's kernels, with it it must."""
@@ -187,6 +222,22 @@ def test_gpu_tile_map_matches_reference_kernels(cuda_device, i):
 def test_gpu_rasterizer_matches_reference_kernels(cuda_device, i):
   from taichi_gaussian_rasterizer_b200 import rasterize_with_tiles
   d = load("raster")
+  size, cfg = raster_case(d, i)
+  g = T(d[f"c{i}_gaussians"]).to(cuda_device).requires_grad_(True)
+  f = T(d[f"c{i}_features"]).to(cuda_device).requires_grad_(True)
+  out = rasterize_with_tiles(g, f, T(d[f"c{i}_overlap_to_point"]).to(cuda_device),
+                             T(d[f"c{i}_tile_ranges"]).view(-1, 2).to(cuda_device), size, cfg)
+  (out.image * T(d[f"c{i}_grad_image"]).to(cuda_device)).sum().backward()
+  check_raster(d, i, out, g.grad, f.grad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", cases2())
+def test_gpu_fast_rasterizer_matches_reference_kernels_tile16(cuda_device, i):
+  """The measured (fast) kernels DIRECTLY against the reference's kernels: tile 16, lists longer than a group with
+  C mod 256 != 0 (the fast forward's re-walk of the stale slots), F = 34 (wide kernels), statistics on."""
+  from taichi_gaussian_rasterizer_b200 import rasterize_with_tiles
+  d = load("raster2")
   size, cfg = raster_case(d, i)
   g = T(d[f"c{i}_gaussians"]).to(cuda_device).requires_grad_(True)
   f = T(d[f"c{i}_features"]).to(cuda_device).requires_grad_(True)
