@@ -177,16 +177,20 @@ def run_ours(args):
   gaussians.requires_grad_(True)
   params = [gaussians.position, gaussians.log_scaling, gaussians.rotation, gaussians.alpha_logit, gaussians.feature]
   bucket = GradientBucket(params)
+  if world > 1 and args.reduce_early and args.background_ctas > 0:
+    from taichi_gaussian_rasterizer_b200.distributed import make_background_group
+    bucket.background_group = make_background_group(args.background_ctas)
   config = RasterConfig(tile_size=W["tile_size"])
 
   # per step inputs: camera (projection + pose) and the target image of every view, in pinned host memory
   torch.manual_seed(1234 + rank)
-  host_targets = [torch.rand(h, w, 3).pin_memory() for _ in range(views)]
+  # target images live on the host as a trainer holds them: 8 bit RGB (a dataset image), converted to float on the device
+  host_targets = [torch.randint(0, 256, (h, w, 3), dtype=torch.uint8).pin_memory() for _ in range(views)]
   host_proj = [c.projection.clone().pin_memory() for c in my_cameras]
   host_pose = [c.T_camera_world.clone().pin_memory() for c in my_cameras]
-  dev_targets = [t.to(device) for t in host_targets]
+  dev_targets = [t.to(device).to(torch.float32).mul_(1.0 / 255.0) for t in host_targets]
   dev_cams = [c.to(device=device) for c in my_cameras]
-  h2d_bytes = sum(t.numel() * 4 for t in host_targets) + sum(p.numel() * 4 for p in host_proj + host_pose)
+  h2d_bytes = sum(t.numel() for t in host_targets) + sum(p.numel() * 4 for p in host_proj + host_pose)
   # the step's result (its loss) is read on the host one step late, from the slot the previous step filled: the host
   # never drains the stream inside the timed region, every step still delivers its 4 bytes
   loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
@@ -199,13 +203,16 @@ def run_ours(args):
       return _step(from_host)
 
   copy_stream = torch.cuda.Stream(device=device)
-  staged = [dict(target=torch.empty(h, w, 3, device=device), proj=torch.empty(4, device=device),
+  staged = [dict(target=torch.empty(h, w, 3, dtype=torch.uint8, device=device), proj=torch.empty(4, device=device),
                  pose=torch.empty(4, 4, device=device), ready=torch.cuda.Event(), free=torch.cuda.Event())
             for _ in range(views)]
 
   poses_ready = torch.cuda.Event()
 
+  phase_events = []   # per timed device step: events around [reduce_early | last view | all_reduce]
+
   def _step(from_host: bool):
+    phase = phase_events if stats.get("record_phases") else None
     compute = torch.cuda.current_stream(device)
     if from_host:
       # this step's inputs (camera + target image of every view) go host -> device on a side stream: the (tiny) camera
@@ -238,11 +245,16 @@ def run_ours(args):
       if from_host:
         st = staged[i]
         compute.wait_event(st["ready"])
-        target = st["target"]
+        target = st["target"].to(torch.float32).mul_(1.0 / 255.0)   # two small elementwise kernels, inside the timed region
       else:
         target = dev_targets[i]
+      if i == views - 1 and phase is not None:
+        phase.append([torch.cuda.Event(enable_timing=True) for _ in range(4)])
+        phase[-1][0].record()
       if i == views - 1 and views > 1 and args.reduce_early:
         bucket.reduce_early()   # N > 1: the SH slices are all-reduced under the last view (distributed.py)
+      if i == views - 1 and phase is not None:
+        phase[-1][1].record()
       rendering = render_gaussians(gaussians, cam, config, use_sh=True, sh_colors=colors[i])
       loss = torch.nn.functional.l1_loss(rendering.image, target)   # mean |image - target|, one fused ATen op each way
       loss.backward()
@@ -250,7 +262,11 @@ def run_ours(args):
       if from_host:
         st["free"].record(compute)
       stats["V"] = rendering.points_in_view.shape[0]
+    if phase is not None:
+      phase[-1][2].record()
     bucket.all_reduce()
+    if phase is not None:
+      phase[-1][3].record()
     if from_host:
       k = stats["e2e_step"]
       slot = k & 1
@@ -299,8 +315,14 @@ def run_ours(args):
   if rank == 0:
     sampler.start()
   timer = _native.StageTimer()
+  stats["record_phases"] = True
   ms_dev = timed(lambda: step(False), args.steps, timer)
+  stats["record_phases"] = False
   stage = timer.summary()
+  # where the end of a step goes on this rank (device time, averaged over the timed steps): flushing + launching the
+  # early reduction, the last view (which shares the SMs with that reduction when N > 1), the closing all_reduce()
+  phase_ms = {name: sum(e[i].elapsed_time(e[i + 1]) for e in phase_events) / max(len(phase_events), 1)
+              for i, name in enumerate(("reduce_early_launch", "last_view", "all_reduce_tail"))}
   clocks = sampler.stop() if rank == 0 else None
   step(True)
   ms_e2e = timed(lambda: step(True), args.steps)
@@ -415,7 +437,7 @@ def run_ours(args):
     "e2e": {"value": e2e, "unit": "gaussian*pixel/s", "ms_per_step": ms_e2e / args.steps,
             "ms_per_frame": ms_e2e / args.steps / views,
             "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-            "note": "a training step: cameras + target images of the step's views go host -> device from pinned memory "
+            "note": "a training step: cameras + target images (8 bit RGB, as a dataset holds them; converted on the device) of the step's views go host -> device from pinned memory "
                     "inside the timed region, the step's loss comes back (read one step late, so the host never drains "
                     "the stream); the gaussians' parameters and their gradient bucket are RESIDENT on the device, as "
                     "they are for a trainer",
@@ -430,6 +452,7 @@ def run_ours(args):
                          "blend_evals_per_s is the informative figure",
                  "blend_evals_per_s": K * 256 / (bwd_avg_ms * 1e-3) if bwd_avg_ms > 0 else None,
                  "issue_roofline": issue},
+    "step_tail_ms": {k: round(v, 4) for k, v in phase_ms.items()},
     "stage_ms_per_frame": stage_ms,
     "hbm_stage_rooflines": hbm_stages,
     "clocks": clocks,
@@ -593,6 +616,8 @@ def main():
                   help="fixed batch split over the ranks (strong scaling), e.g. --workload c5 --total-views 64")
   ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration (c1..c5) timings at N = 1")
   ap.add_argument("--no-stock", action="store_true", help="skip the stock-API (no extensions) timing at N = 1")
+  ap.add_argument("--background-ctas", type=int, default=0,
+                  help="N > 1 with reduce_early: CTA limit of the communicator that runs under the last view (0 = default group)")
   ap.add_argument("--no-reduce-early", dest="reduce_early", action="store_false",
                   help="N > 1: one all-reduce of the whole bucket after the last view (round-1 behaviour)")
   args = ap.parse_args()

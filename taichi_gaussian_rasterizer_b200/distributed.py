@@ -31,6 +31,7 @@ class GradientBucket:
     sizes = [p.numel() for p in self.params]
     self.flat = torch.zeros((sum(sizes),), dtype=dtype, device=device)
     self._early = None            # state of reduce_early(): (split offset, deferred objects on hold, work handle)
+    self.background_group = None  # optional low-CTA communicator for the overlapped reduction (make_background_group)
     self._gather_buffers = {}     # all-gather targets of the last views' staged colour gradients, kept across steps
     off = 0
     for p, n in zip(self.params, sizes):
@@ -133,7 +134,9 @@ class GradientBucket:
     for d in deferred:
       d.flush()
       d.hold = True
-    work = dist.all_reduce(self.flat[split:], op=dist.ReduceOp.SUM, group=group, async_op=True)
+    # this collective runs UNDER the last view's kernels, which are issue bound and fill every SM: a communicator
+    # limited to a few CTAs (background_group) takes few SMs away from them and still has the whole view to finish
+    work = dist.all_reduce(self.flat[split:], op=dist.ReduceOp.SUM, group=self.background_group or group, async_op=True)
     self._early = (split, deferred, work)
 
   def _finish_early(self, group):
@@ -146,7 +149,7 @@ class GradientBucket:
       if not pending:
         continue
       # this rank's staged colour gradients (P, N, 3) and camera centres (P, 3) -> every rank's (world P, ...)
-      local = torch.stack([t for t, _ in pending])
+      local = pending[0][0].unsqueeze(0) if len(pending) == 1 else torch.stack([t for t, _ in pending])   # no copy for one view
       cams = torch.stack([c.reshape(3) for _, c in pending])
       key = (id(d), tuple(local.shape))
       buf = self._gather_buffers.get(key)
@@ -187,6 +190,21 @@ class GradientBucket:
     self.flush()
     dist.all_reduce(self.flat[split:], op=dist.ReduceOp.SUM, group=group)
     head.wait()
+    return None
+
+
+def make_background_group(max_ctas: int = 8):
+  """A second NCCL communicator over all ranks whose kernels use at most ``max_ctas`` CTAs: for collectives that are
+  meant to run underneath compute kernels (GradientBucket.reduce_early) without taking many SMs from them.  Returns
+  None when the backend has no such option (gloo) or no process group is initialised."""
+  if not (dist.is_available() and dist.is_initialized()) or dist.get_backend() != "nccl":
+    return None
+  try:
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.config.max_ctas = int(max_ctas)
+    opts.config.min_ctas = 1
+    return dist.new_group(ranks=list(range(dist.get_world_size())), backend="nccl", pg_options=opts)
+  except Exception:   # noqa: BLE001 - an older torch / NCCL without communicator configs: use the default group
     return None
 
 

@@ -298,7 +298,92 @@ def make_optim(out):
   out["num_steps"] = np.array(OPTIM_STEPS)
 
 
-MAKERS = {"tile_map": make_tile_map, "projection": make_projection, "sh": make_sh, "raster": make_raster,
+# ----------------------------------------------------------------------------------------------- ParameterClass + splits
+PCLASS_N, PCLASS_KEEP, PCLASS_NEW = 40, 27, 6
+
+
+def pclass_problem():
+  """Tensors, groups and the scripted sequence (steps, a filter, an append) shared by the generator and the tests."""
+  torch.manual_seed(77)
+  n = PCLASS_N
+  tensors = dict(position=torch.randn(n, 2), log_scaling=torch.randn(n, 2) * 0.3, feature=torch.rand(n, 3),
+                 z_depth=torch.rand(n, 1))
+  groups = dict(position=dict(lr=0.1, type="vector"), log_scaling=dict(lr=0.05, type="scalar"),
+                feature=dict(lr=0.02, type="vector"))
+  keep = torch.randperm(n)[:PCLASS_KEEP].sort().values
+  new = dict(position=torch.randn(PCLASS_NEW, 2), log_scaling=torch.randn(PCLASS_NEW, 2) * 0.3,
+             feature=torch.rand(PCLASS_NEW, 3), z_depth=torch.rand(PCLASS_NEW, 1))
+  sizes = [n, n, PCLASS_KEEP, PCLASS_KEEP + PCLASS_NEW]   # rows at each of the four optimizer steps
+  steps = []
+  for m in sizes:
+    idx = torch.nonzero(torch.rand(m) < 0.7).squeeze(1)
+    steps.append(dict(indexes=idx, grads={k: torch.randn(m, *tensors[k].shape[1:]) for k in groups}))
+  return tensors, groups, keep, new, steps
+
+
+def make_pclass(out):
+  """optim/parameter_class.py (ParameterClass: construction, step, boolean / index filtering with optimizer state,
+  append with zero state) driven by the reference's SparseAdam (optim/fractional.py + its Taichi step kernels under the
+  emulator), and the split operations of misc/renderer2d.py:60-132 with a seeded generator."""
+  from tensordict import TensorDict
+  from taichi_splatting.optim.parameter_class import ParameterClass
+  from taichi_splatting.optim.fractional import SparseAdam
+  import taichi_splatting.misc.renderer2d as r2
+  tensors, groups, keep, new, steps = pclass_problem()
+  for k, v in tensors.items():
+    out[f"init_{k}"] = np_(v)
+  for k, v in new.items():
+    out[f"new_{k}"] = np_(v)
+  out["keep"] = np_(keep)
+  pc = ParameterClass(TensorDict.from_dict({k: v.clone() for k, v in tensors.items()}, batch_dims=1), groups,
+                      optimizer=SparseAdam, betas=(0.9, 0.95), eps=1e-12, bias_correction=True)
+
+  def snapshot(tag, pc):
+    for k, v in pc.tensors.items():
+      out[f"{tag}_tensor_{k}"] = np_(v)
+    for k, st in pc.tensor_state.to_dict().items():
+      for sk, sv in st.items():
+        out[f"{tag}_state_{k}_{sk}"] = np_(sv)
+
+  def do_step(i, pc):
+    st = steps[i]
+    out[f"s{i}_indexes"] = np_(st["indexes"])
+    for k in groups:
+      out[f"s{i}_grad_{k}"] = np_(st["grads"][k])
+      pc.tensors[k].grad = st["grads"][k].clone()
+    pc.step(indexes=st["indexes"])
+    snapshot(f"after_step{i}", pc)
+
+  do_step(0, pc)
+  do_step(1, pc)
+  pc = pc[keep]                                     # filter: rows AND optimizer state follow
+  snapshot("after_filter", pc)
+  do_step(2, pc)
+  pc = pc.append_tensors(TensorDict.from_dict({k: v.clone() for k, v in new.items()}, batch_dims=1))   # zero state
+  snapshot("after_append", pc)
+  do_step(3, pc)
+  out["state_keys"] = np.array(sorted({k.split("_state_")[1] for k in out if "_state_" in k}))
+  print(f"pclass: rows {PCLASS_N} -> filter {PCLASS_KEEP} -> append {PCLASS_KEEP + PCLASS_NEW}; state entries "
+        f"{sorted({k.split('_state_')[1] for k in out if k.startswith('after_step3_state_')})}")
+
+  # split operations (misc/renderer2d.py): same generator seed before each call, outputs stored
+  torch.manual_seed(5)
+  g = random_2d_gaussians(25, (64, 48), num_channels=3, scale_factor=2.0)
+  for k in ("position", "z_depth", "log_scaling", "rotation", "alpha_logit", "feature"):
+    out[f"split_in_{k}"] = np_(getattr(g, k))
+  for name, fn in (("split2", lambda: r2.split_gaussians2d(g, n=2)), ("split3s", lambda: r2.split_gaussians2d(g, n=3, scaling=0.6)),
+                   ("uniform2", lambda: r2.uniform_split_gaussians2d(g, n=2)),
+                   ("uniform3r", lambda: r2.uniform_split_gaussians2d(g, n=3, random_axis=True, sep=0.5))):
+    torch.manual_seed(11)
+    res = fn()
+    for k in ("position", "z_depth", "log_scaling", "rotation", "alpha_logit", "feature"):
+      out[f"{name}_{k}"] = np_(getattr(res, k))
+  # (sample_gaussians cannot run in the reference: (N,2,2) @ (N,1,2) is a shape error, renderer2d.py:101-103)
+  out["point_basis"] = np_(r2.point_basis(g))
+  out["point_covariance"] = np_(r2.point_covariance(g))
+
+
+MAKERS = {"tile_map": make_tile_map, "pclass": make_pclass, "projection": make_projection, "sh": make_sh, "raster": make_raster,
           "optim": make_optim, "morton": lambda out: make_morton(out)}
 
 

@@ -875,10 +875,15 @@ def build_taichi_module():
 
 
 def _fake_tensordict():
+  """Stand-in for the part of ``tensordict`` the reference uses on the host side: ``@tensorclass`` containers
+  (constructed with a batch_size keyword, ``apply``) and a ``TensorDict`` with leading batch dimensions (string and
+  batch indexing, nesting, ``from_dict`` / ``to_dict``, ``new_zeros``, ``torch.cat``) - what optim/parameter_class.py and
+  misc/renderer2d.py need.  Written for the fixture generator only; the product package has its own
+  (taichi_gaussian_rasterizer_b200/tensor_dict.py), deliberately not imported here."""
   import dataclasses
+  import torch
 
   def tensorclass(cls):
-    """Plain dataclass with a batch_size keyword: enough for the reference's containers to be constructed."""
     fields = list(getattr(cls, "__annotations__", {}))
     dc = dataclasses.dataclass(cls)
     orig_init = dc.__init__
@@ -887,11 +892,108 @@ def _fake_tensordict():
       orig_init(self, *args, **kwargs)
       self.batch_size = tuple(batch_size) if batch_size is not None else ()
 
+    def apply(self, f, batch_size=None):
+      return type(self)(**{k: f(getattr(self, k)) for k in fields},
+                        batch_size=self.batch_size if batch_size is None else batch_size)
+
     dc.__init__ = __init__
     dc._fields = fields
+    if not hasattr(dc, "apply"):
+      dc.apply = apply
     return dc
 
-  return _module("tensordict", tensorclass=tensorclass, TensorDict=dict)
+  class TensorDict:
+    def __init__(self, data, batch_size):
+      self._d = dict(data)
+      self.batch_size = torch.Size(batch_size)
+
+    @classmethod
+    def from_dict(cls, d, batch_dims=None, batch_size=None):
+      def leaves(x):
+        for v in x.values():
+          if isinstance(v, (dict, TensorDict)):
+            yield from leaves(v if isinstance(v, dict) else v._d)
+          else:
+            yield v
+      if batch_size is None:
+        shapes = [tuple(t.shape) for t in leaves(d)]
+        common = 0
+        if shapes:
+          common = min(len(sh) for sh in shapes)
+          for i in range(common):
+            if len({sh[i] for sh in shapes}) != 1:
+              common = i
+              break
+        nd = common if batch_dims is None else min(batch_dims, common)
+        batch_size = shapes[0][:nd] if shapes else ()
+      data = {k: (cls.from_dict(v, batch_size=batch_size) if isinstance(v, dict) else v) for k, v in d.items()}
+      return cls(data, batch_size)
+
+    def to_dict(self):
+      return {k: (v.to_dict() if isinstance(v, TensorDict) else v) for k, v in self._d.items()}
+
+    def _map(self, f, batch_size=None):
+      return TensorDict({k: (v._map(f, batch_size) if isinstance(v, TensorDict) else f(v)) for k, v in self._d.items()},
+                        self.batch_size if batch_size is None else batch_size)
+
+    keys = lambda self: self._d.keys()        # noqa: E731
+    values = lambda self: self._d.values()    # noqa: E731
+    items = lambda self: self._d.items()      # noqa: E731
+    __contains__ = lambda self, k: k in self._d   # noqa: E731
+    __len__ = lambda self: self.batch_size[0] if len(self.batch_size) else 0   # noqa: E731
+
+    @property
+    def batch_dims(self):
+      return len(self.batch_size)
+
+    @property
+    def shape(self):
+      return self.batch_size
+
+    def __getitem__(self, idx):
+      if isinstance(idx, str):
+        return self._d[idx]
+      probe = torch.empty(self.batch_size)[idx]
+      return self._map(lambda t: t[idx], batch_size=probe.shape)
+
+    def __setitem__(self, k, v):
+      self._d[k] = v
+
+    def apply(self, f, batch_size=None):
+      return self._map(f, batch_size)
+
+    def detach(self):
+      return self._map(lambda t: t.detach())
+
+    def to(self, *a, **kw):
+      return self._map(lambda t: t.to(*a, **kw))
+
+    def replace(self, **kw):
+      return TensorDict({**self._d, **kw}, self.batch_size)
+
+    def new_zeros(self, *size):
+      size = tuple(size[0]) if len(size) == 1 and isinstance(size[0], (tuple, list)) else tuple(size)
+      nb = len(self.batch_size)
+      return self._map(lambda t: t.new_zeros((*size, *t.shape[nb:])), batch_size=size)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+      kwargs = kwargs or {}
+      if func is torch.cat:
+        tds = list(args[0])
+        dim = kwargs.get("dim", args[1] if len(args) > 1 else 0)
+
+        def cat(parts):
+          first = parts[0]
+          out = {k: (cat([p._d[k] for p in parts]) if isinstance(first._d[k], TensorDict)
+                     else torch.cat([p._d[k] for p in parts], dim=dim)) for k in first._d}
+          bs = list(first.batch_size)
+          bs[dim] = sum(p.batch_size[dim] for p in parts)
+          return TensorDict(out, bs)
+        return cat(tds)
+      return NotImplemented
+
+  return _module("tensordict", tensorclass=tensorclass, TensorDict=TensorDict)
 
 
 def _fake_cuda_lib():

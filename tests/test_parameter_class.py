@@ -211,3 +211,85 @@ def test_fit_loop_with_split_prune_on_the_cuda_path(cuda_device):
   assert state['position']['running_vis'].shape[0] == params.batch_size[0]
   for name, t in params.items():
     assert torch.isfinite(t).all(), name
+
+
+# ------------------------------------------------------------------------------- fixtures made from the reference itself
+# tests/golden/pclass.npz (make_golden.py --only pclass): the reference's ParameterClass driven by its own SparseAdam
+# (Taichi step kernels under the emulator, tensordict stand-in of ti_emu.py) through a scripted sequence — two steps, a
+# row filter, a step, an append with zero state, a step — and its split operations with a seeded generator.
+import numpy as np   # noqa: E402
+from pathlib import Path   # noqa: E402
+
+PCLASS = Path(__file__).resolve().parent / "golden" / "pclass.npz"
+FIELDS = ("position", "z_depth", "log_scaling", "rotation", "alpha_logit", "feature")
+
+
+def _T(a):
+  return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def _rel(a, b):
+  a, b = a.detach().double().cpu(), b.double()
+  return ((a - b).norm() / max(b.norm().item(), 1e-30)).item()
+
+
+def test_split_operations_match_reference():
+  """split_gaussians2d / uniform_split_gaussians2d / point_basis / point_covariance against the reference's functions
+  run on the same inputs with the same generator seed (misc/renderer2d.py:36-132)."""
+  d = np.load(PCLASS)
+  g = Gaussians2D(**{k: _T(d[f"split_in_{k}"]) for k in FIELDS}, batch_size=(d["split_in_position"].shape[0],))
+  cases = dict(split2=lambda: renderer2d.split_gaussians2d(g, n=2),
+               split3s=lambda: renderer2d.split_gaussians2d(g, n=3, scaling=0.6),
+               uniform2=lambda: renderer2d.uniform_split_gaussians2d(g, n=2),
+               uniform3r=lambda: renderer2d.uniform_split_gaussians2d(g, n=3, random_axis=True, sep=0.5))
+  for name, fn in cases.items():
+    torch.manual_seed(11)
+    res = fn()
+    for k in FIELDS:
+      ref = _T(d[f"{name}_{k}"])
+      assert getattr(res, k).shape == ref.shape, f"{name}.{k}"
+      assert torch.allclose(getattr(res, k), ref, rtol=1e-6, atol=1e-7), f"{name}.{k}: {_rel(getattr(res, k), ref)}"
+  assert torch.allclose(renderer2d.point_basis(g), _T(d["point_basis"]), rtol=1e-6, atol=1e-7)
+  assert torch.allclose(renderer2d.point_covariance(g), _T(d["point_covariance"]), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_parameter_class_sequence_matches_reference(cuda_device):
+  """Rows and optimizer state after every operation of the scripted sequence equal the reference's: construction,
+  step, filter (state follows the rows), append (new rows get zero state), step on the derived objects."""
+  from taichi_gaussian_rasterizer_b200.optim import SparseAdam
+  d = np.load(PCLASS)
+  names = ("position", "log_scaling", "feature", "z_depth")
+  groups = dict(position=dict(lr=0.1, type="vector"), log_scaling=dict(lr=0.05, type="scalar"),
+                feature=dict(lr=0.02, type="vector"))
+  tensors = {k: _T(d[f"init_{k}"]).to(cuda_device) for k in names}
+  pc = ParameterClass(TensorDict.from_dict(tensors, batch_dims=1), groups, optimizer=SparseAdam, betas=(0.9, 0.95),
+                      eps=1e-12, bias_correction=True)
+
+  def check(tag, pc):
+    for k in names:
+      ref = _T(d[f"{tag}_tensor_{k}"])
+      assert pc.tensors[k].shape == ref.shape and _rel(pc.tensors[k], ref) < 1e-5, f"{tag} tensor {k}"
+    state = pc.tensor_state.to_dict()
+    keys = {key[len(f"{tag}_state_"):] for key in d.files if key.startswith(f"{tag}_state_")}
+    ours = {f"{k}_{sk}" for k, st in state.items() for sk in st}
+    assert ours == keys, f"{tag}: state entries {ours} != {keys}"
+    for k, st in state.items():
+      for sk, sv in st.items():
+        ref = _T(d[f"{tag}_state_{k}_{sk}"])
+        assert sv.shape == ref.shape and _rel(sv, ref) < 1e-5, f"{tag} state {k}.{sk}: {_rel(sv, ref)}"
+
+  def step(i, pc):
+    for k in groups:
+      pc.tensors[k].grad = _T(d[f"s{i}_grad_{k}"]).to(cuda_device)
+    pc.step(indexes=_T(d[f"s{i}_indexes"]).to(cuda_device))
+    check(f"after_step{i}", pc)
+
+  step(0, pc)
+  step(1, pc)
+  pc = pc[_T(d["keep"]).to(cuda_device)]
+  check("after_filter", pc)
+  step(2, pc)
+  pc = pc.append_tensors(TensorDict.from_dict({k: _T(d[f"new_{k}"]).to(cuda_device) for k in names}, batch_dims=1))
+  check("after_append", pc)
+  step(3, pc)
