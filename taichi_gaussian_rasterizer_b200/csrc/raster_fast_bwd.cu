@@ -38,7 +38,10 @@ namespace gs {
 // PAIR: survivors are reduced two at a time — one transposed butterfly over 2 NV values (every exchange step halves
 // the live values, so 18 values cost 9 + 5 + 3 + 2 + 1 shuffles where two separate reductions of 9 cost 2 x 12) and
 // one red.global.add instruction with 2 NV owning lanes; an odd survivor left at the end of the tile is reduced alone.
-template <int F, int FP, bool HEUR, bool PAIR>
+// AA: antialiased pixel function (raster_math.cuh pdf_aa_grad with MUFU arithmetic): the records are the unscaled
+// {mean, axis}{1/sigma, alpha, index}, the seven gradient components are accumulated directly (the moment trick needs
+// a pure gaussian) and no moment pass follows.
+template <int F, int FP, bool HEUR, bool PAIR, bool AA = false>
 __global__ void __launch_bounds__(32, PAIR ? 32 : 1)
 raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
                        const float* __restrict__ featP, const int32_t* __restrict__ ranges,
@@ -48,7 +51,7 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
                        const unsigned char* __restrict__ cull_mask) {
   constexpr int NSUB = 4;
   constexpr int kBwdBatch = 64;   // staged tile-list entries per buffer (32 / 128 measured slower)
-  constexpr int NM = 6;  // moments: g, g u, g w, g u^2, g w^2, g u w
+  constexpr int NM = AA ? 7 : 6;  // moments: g, g u, g w, g u^2, g w^2, g u w; AA: d/d(mean, axis, sigma, alpha)
   constexpr int NV = NM + F + (HEUR ? 2 : 0);
   // one staged entry = {record (2 x float4), feature row (FP / 4 x float4)} in consecutive 16 B units: one address per
   // entry in the walk (all reads are warp-uniform, so the stride needs no padding)
@@ -128,49 +131,103 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
   // bm[i] bit jl = sub-block i can be reached at all (warp-uniform).
   auto evaluate = [&](const float4* ent, const unsigned (&bm)[NSUB], int jl, float* v) -> unsigned {
     const float4 r0 = ent[0], r1 = ent[1];
-    const float mx = r0.x, my = r0.y, a1x = r0.z, a1y = r0.w, a2x = r1.x, a2y = r1.y, l2a = r1.z;
     float f[F];
 #pragma unroll
     for (int c = 0; c < F; ++c) f[c] = reinterpret_cast<const float*>(ent + 2)[c];
-
-    float M0 = 0.f, Mu = 0.f, Mw = 0.f, Muu = 0.f, Mww = 0.f, Muw = 0.f, h0 = 0.f, h1 = 0.f;
     float gf[F];
 #pragma unroll
     for (int c = 0; c < F; ++c) gf[c] = 0.f;
-    const float dxb = px0 - mx, dyb = py0 - my;
+    float h0 = 0.f, h1 = 0.f;
+    const float dxb = px0 - r0.x, dyb = py0 - r0.y;
+    if constexpr (AA) {
+      const float ax = r0.z, ay = r0.w, isx = r1.x, isy = r1.y, a0 = r1.z;
+      const float sx = fast_rcp(isx), sy = fast_rcp(isy);
+      constexpr float tau = 6.283185307179586f;
+      float g[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < NSUB; ++i) {
-      if ((bm[i] >> jl) & 1u) {  // warp-uniform: this sub-block can be reached at all
-        const float dx = (i & 1) ? dxb + 8.f : dxb, dy = (i >> 1) ? dyb + 4.f * (i >> 1) : dyb;   // no x + 0.f
-        const float tx = fmaf(dy, a1y, dx * a1x), ty = fmaf(dy, a2y, dx * a2x);   // k x offset / sigma, own frame
-        const float araw = fast_ex2(fmaf(-ty, ty, fmaf(-tx, tx, l2a)));   // alpha0 p, as the forward forms it
-        if (araw > thr && W[i] < sat) {
-          const float alpha = fminf(araw, cmax);
-          const float Ti = 1.f - W[i];
-          const float w = alpha * Ti;
-          W[i] += w;
-          const float rinv = fast_rcp(1.f - alpha);
-          float fG = 0.f;
+      for (int i = 0; i < NSUB; ++i) {
+        if ((bm[i] >> jl) & 1u) {  // warp-uniform: this sub-block can be reached at all
+          const float dx = (i & 1) ? dxb + 8.f : dxb, dy = (i >> 1) ? dyb + 4.f * (i >> 1) : dyb;
+          const float tx = fmaf(dy, ay, dx * ax), ty = fmaf(dy, ax, -dx * ay);
+          const float zx1 = (tx + 0.5f) * isx, zx2 = (tx - 0.5f) * isx, zy1 = (ty + 0.5f) * isy, zy2 = (ty - 0.5f) * isy;
+          float dx1, dx2, dy1, dy2;   // dS/dz of the four edge terms
+          const float Sx = aa_sig_grad(zx1, dx1) - aa_sig_grad(zx2, dx2);
+          const float Sy = aa_sig_grad(zy1, dy1) - aa_sig_grad(zy2, dy2);
+          const float ix = sx * Sx, iy = sy * Sy;
+          const float pa = tau * ix * iy;
+          const float araw = a0 * pa;
+          if (araw > thr && W[i] < sat) {
+            const float alpha = fminf(araw, cmax);
+            const float Ti = 1.f - W[i];
+            const float w = alpha * Ti;
+            W[i] += w;
+            const float rinv = fast_rcp(1.f - alpha);
+            float fG = 0.f;
 #pragma unroll
-          for (int c = 0; c < F; ++c) {
-            fG = fmaf(f[c], Gd[i][c], fG);
-            gf[c] = fmaf(w, Gd[i][c], gf[c]);
-          }
-          RG[i] = fmaf(-fG, w, RG[i]);
-          const float ag = fmaf(fG, Ti, -RG[i] * rinv);   // dL/dalpha
-          const float gp = ag * araw;                     // alpha0 x the dL/dalpha0 share of this pixel
-          const float gu = gp * tx, gw = gp * ty;
-          M0 += gp; Mu += gu; Mw += gw;
-          Muu = fmaf(gu, tx, Muu); Mww = fmaf(gw, ty, Mww); Muw = fmaf(gu, ty, Muw);
-          if (HEUR) {
-            const float aag = fast_ex2(l2a) * ag;
-            h0 = fmaf(aag, aag, h0);   // |d/dmean| of this pixel: g (tx a1 + ty a2) / k^2
-            h1 += (fabsf(fmaf(gu, a1x, gw * a2x)) + fabsf(fmaf(gu, a1y, gw * a2y))) * (1.f / kHalfLog2e);
+            for (int c = 0; c < F; ++c) {
+              fG = fmaf(f[c], Gd[i][c], fG);
+              gf[c] = fmaf(w, Gd[i][c], gf[c]);
+            }
+            RG[i] = fmaf(-fG, w, RG[i]);
+            const float ag = fmaf(fG, Ti, -RG[i] * rinv);   // dL/dalpha
+            const float aag = a0 * ag * tau;
+            // d pdf_aa / d(mean, axis, sigma) (taichi_lib/generic.py:355-404): dS/dx = dS/dz / sigma, dS/dsigma = -z dS/dx
+            const float dSx = iy * (dx1 - dx2);            // iy sx (dSx1 - dSx2) / sx
+            const float dSy = ix * (dy1 - dy2);
+            const float gmx = aag * fmaf(dSy, ay, -dSx * ax), gmy = -aag * fmaf(dSx, ay, dSy * ax);
+            g[0] += gmx; g[1] += gmy;
+            g[2] = fmaf(aag, fmaf(dSx, dx, dSy * dy), g[2]);
+            g[3] = fmaf(aag, fmaf(dSx, dy, -dSy * dx), g[3]);
+            g[4] = fmaf(aag * iy, Sx - fmaf(zx1, dx1, -zx2 * dx2), g[4]);
+            g[5] = fmaf(aag * ix, Sy - fmaf(zy1, dy1, -zy2 * dy2), g[5]);
+            g[6] = fmaf(pa, ag, g[6]);
+            if (HEUR) {
+              const float q = a0 * ag;
+              h0 = fmaf(q, q, h0);
+              h1 += fabsf(gmx) + fabsf(gmy);
+            }
           }
         }
       }
+#pragma unroll
+      for (int k = 0; k < 7; ++k) v[k] = g[k];
+    } else {
+      const float a1x = r0.z, a1y = r0.w, a2x = r1.x, a2y = r1.y, l2a = r1.z;
+      float M0 = 0.f, Mu = 0.f, Mw = 0.f, Muu = 0.f, Mww = 0.f, Muw = 0.f;
+#pragma unroll
+      for (int i = 0; i < NSUB; ++i) {
+        if ((bm[i] >> jl) & 1u) {  // warp-uniform: this sub-block can be reached at all
+          const float dx = (i & 1) ? dxb + 8.f : dxb, dy = (i >> 1) ? dyb + 4.f * (i >> 1) : dyb;   // no x + 0.f
+          const float tx = fmaf(dy, a1y, dx * a1x), ty = fmaf(dy, a2y, dx * a2x);   // k x offset / sigma, own frame
+          const float araw = fast_ex2(fmaf(-ty, ty, fmaf(-tx, tx, l2a)));   // alpha0 p, as the forward forms it
+          if (araw > thr && W[i] < sat) {
+            const float alpha = fminf(araw, cmax);
+            const float Ti = 1.f - W[i];
+            const float w = alpha * Ti;
+            W[i] += w;
+            const float rinv = fast_rcp(1.f - alpha);
+            float fG = 0.f;
+#pragma unroll
+            for (int c = 0; c < F; ++c) {
+              fG = fmaf(f[c], Gd[i][c], fG);
+              gf[c] = fmaf(w, Gd[i][c], gf[c]);
+            }
+            RG[i] = fmaf(-fG, w, RG[i]);
+            const float ag = fmaf(fG, Ti, -RG[i] * rinv);   // dL/dalpha
+            const float gp = ag * araw;                     // alpha0 x the dL/dalpha0 share of this pixel
+            const float gu = gp * tx, gw = gp * ty;
+            M0 += gp; Mu += gu; Mw += gw;
+            Muu = fmaf(gu, tx, Muu); Mww = fmaf(gw, ty, Mww); Muw = fmaf(gu, ty, Muw);
+            if (HEUR) {
+              const float aag = fast_ex2(l2a) * ag;
+              h0 = fmaf(aag, aag, h0);   // |d/dmean| of this pixel: g (tx a1 + ty a2) / k^2
+              h1 += (fabsf(fmaf(gu, a1x, gw * a2x)) + fabsf(fmaf(gu, a1y, gw * a2y))) * (1.f / kHalfLog2e);
+            }
+          }
+        }
+      }
+      v[0] = M0; v[1] = Mu; v[2] = Mw; v[3] = Muu; v[4] = Mww; v[5] = Muw;
     }
-    v[0] = M0; v[1] = Mu; v[2] = Mw; v[3] = Muu; v[4] = Mww; v[5] = Muw;
 #pragma unroll
     for (int c = 0; c < F; ++c) v[NM + c] = gf[c];
     if (HEUR) { v[NM + F] = h0; v[NM + F + 1] = h1; }
@@ -292,15 +349,16 @@ static int launch_bwd_fast(const GsRasterParams& p, const RasterArgs& a, const f
   const unsigned char* cmask = (const unsigned char*)a.workspace + fast_layout(p).off_mask;
   // kernel_variant (benchmark A/B switch, 0 in production): bit 0 = reduce every survivor on its own
   const bool pair = (p.kernel_variant & 1) == 0;
-#define GS_BWD_LAUNCH(HEURV, PAIRV)                                                                              \
-  raster_bwd_fast_kernel<F, FP, HEURV, PAIRV><<<tiles * 2, 32, 0, st>>>(                                        \
+#define GS_BWD_LAUNCH(HEURV, PAIRV, AAV)                                                                         \
+  raster_bwd_fast_kernel<F, FP, HEURV, PAIRV, AAV><<<tiles * 2, 32, 0, st>>>(                                   \
       p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,   \
       (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr, cmask)
-  if (heur) { if (pair) GS_BWD_LAUNCH(true, true); else GS_BWD_LAUNCH(true, false); }
-  else { if (pair) GS_BWD_LAUNCH(false, true); else GS_BWD_LAUNCH(false, false); }
+  if (p.antialias) { if (heur) GS_BWD_LAUNCH(true, false, true); else GS_BWD_LAUNCH(false, false, true); }
+  else if (heur) { if (pair) GS_BWD_LAUNCH(true, true, false); else GS_BWD_LAUNCH(true, false, false); }
+  else { if (pair) GS_BWD_LAUNCH(false, true, false); else GS_BWD_LAUNCH(false, false, false); }
 #undef GS_BWD_LAUNCH
   GS_LAUNCH_CHECK();
-  if (p.points_requires_grad && a.grad_gaussians != nullptr && p.num_points > 0) {
+  if (!p.antialias && p.points_requires_grad && a.grad_gaussians != nullptr && p.num_points > 0) {
     raster_bwd_moments_kernel<<<(unsigned)ceil_div(p.num_points, 256), 256, 0, st>>>(
         p.num_points, (const float*)a.gaussians2d, (float*)a.grad_gaussians);
     GS_LAUNCH_CHECK();
@@ -324,7 +382,7 @@ int raster_bwd_fast(const GsRasterParams& p, const RasterArgs& a, cudaStream_t s
   const float* featP = (const float*)(ws + L.off_feat);
   if (p.num_features > 7)   // 8..64 channels: one pixel per lane, its own records
     return raster_bwd_wide(p, a, (const float4*)(ws + L.off_recB), featP, st);
-  const float4* rec = (const float4*)(ws + L.off_recF);   // the forward's records
+  const float4* rec = (const float4*)(ws + (p.antialias ? L.off_recB : L.off_recF));   // the forward's records
   switch (p.num_features) {
     case 1: return launch_bwd_fast<1, 4>(p, a, rec, featP, st);
     case 2: return launch_bwd_fast<2, 4>(p, a, rec, featP, st);

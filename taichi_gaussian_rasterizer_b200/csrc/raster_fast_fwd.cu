@@ -59,10 +59,12 @@ int raster_fast_pack(const GsRasterParams& p, const RasterArgs& a, bool forward,
   // the forward call also packs the backward records when a gradient will be asked for, so that the backward
   // call (workspace_holds_packed) launches no pack kernel at all
   // The narrow backward (F <= 7, raster_fast_bwd.cu) walks the forward's records; only the wide one has its own.
+  // Antialiased rendering (narrow features only) walks the unscaled records {mean, axis}{1/sigma, alpha, index} in
+  // both passes: its per pixel function needs the axis and the sigmas separately.
   const bool want_bwd = !forward || p.points_requires_grad || p.features_requires_grad;
   const bool narrow = p.num_features <= 7;
-  float4* recF = (forward || narrow) ? (float4*)(ws + L.off_recF) : nullptr;
-  float4* recB = (want_bwd && !narrow) ? (float4*)(ws + L.off_recB) : nullptr;
+  float4* recF = (!p.antialias && (forward || narrow)) ? (float4*)(ws + L.off_recF) : nullptr;
+  float4* recB = (p.antialias || (want_bwd && !narrow)) ? (float4*)(ws + L.off_recB) : nullptr;
   float* featP = features ? (float*)(ws + L.off_feat) : nullptr;
   const int64_t blocks = ceil_div(p.num_points, 256);
 #define GS_PACK(FPV)                                                                                          \
@@ -85,27 +87,40 @@ int raster_fast_pack(const GsRasterParams& p, const RasterArgs& a, bool forward,
 // alpha_threshold anywhere in the 8x4 pixel block w of the tile (w = 2 * block row + block column; exact minimum of
 // the ellipse's quadratic form over the block, with the slack of block_may_touch).  The forward (eight warps, one block
 // each) and the narrow backward (two warps, four blocks each) read the byte instead of repeating the test per warp.
+// AA: antialiased rendering evaluates the gaussian INTEGRATED over the pixel (raster_math.cuh pdf_aa: the pixel's unit
+// box in the gaussian's frame), which is bounded by the maximum of the point-sampled gaussian over that box: the same
+// test on the block grown by the box's half diagonal (0.75 px covers it) and with a factor two of slack on alpha for
+// the logistic approximation of the normal CDF is conservative.  Records there are {mean, axis}{1/sigma, alpha, index}.
+template <bool AA>
 __global__ void __launch_bounds__(128)
 raster_cull_mask_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
                         const int32_t* __restrict__ ranges, const int32_t* __restrict__ o2p,
                         unsigned char* __restrict__ mask) {
   const int tile = blockIdx.x;
   const int tw = (p.image_width + kFastTile - 1) / kFastTile;
-  const float x0 = (float)((tile % tw) * kFastTile) + 0.5f, y0 = (float)((tile / tw) * kFastTile) + 0.5f;
+  const float grow = AA ? 0.75f : 0.f;
+  const float x0 = (float)((tile % tw) * kFastTile) + 0.5f - grow, y0 = (float)((tile / tw) * kFastTile) + 0.5f - grow;
   const float l2thr = log2f((float)p.alpha_threshold);
   const int start = ranges[2 * tile], end = ranges[2 * tile + 1];
   for (int k = start + threadIdx.x; k < end; k += blockDim.x) {
     const int idx = o2p[k];
     const float4 r0 = rec[2 * (int64_t)idx], r1 = rec[2 * (int64_t)idx + 1];
-    const float a1x = r0.z, a1y = r0.w, a2x = r1.x, a2y = r1.y;
+    float a1x, a1y, a2x, a2y, l2a;
+    if (AA) {
+      const float cx = kSqrtHalfLog2e * r1.x, cy = kSqrtHalfLog2e * r1.y;
+      a1x = r0.z * cx; a1y = r0.w * cx; a2x = -r0.w * cy; a2y = r0.z * cy;
+      l2a = log2f(r1.z) + 1.0f;
+    } else {
+      a1x = r0.z; a1y = r0.w; a2x = r1.x; a2y = r1.y; l2a = r1.z;
+    }
     const float A00 = a1x * a1x + a2x * a2x, A01 = a1x * a1y + a2x * a2y, A11 = a1y * a1y + a2y * a2y;
     const float n01r11 = -A01 * fast_rcp(A11), n01r00 = -A01 * fast_rcp(A00);
-    const float qlim = (r1.z - l2thr) * 1.001f + 1e-3f;
+    const float qlim = (l2a - l2thr) * 1.001f + 1e-3f;
     unsigned bits = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-      const float dx0 = x0 + (float)((w & 1) * 8) - r0.x, dx1 = dx0 + 7.f;
-      const float dy0 = y0 + (float)((w >> 1) * 4) - r0.y, dy1 = dy0 + 3.f;
+      const float dx0 = x0 + (float)((w & 1) * 8) - r0.x, dx1 = dx0 + 7.f + 2.f * grow;
+      const float dy0 = y0 + (float)((w >> 1) * 4) - r0.y, dy1 = dy0 + 3.f + 2.f * grow;
       const float dxc = fminf(fmaxf(0.f, dx0), dx1), dyc = fminf(fmaxf(0.f, dy0), dy1);
       const float dyv = fminf(fmaxf(n01r11 * dxc, dy0), dy1);
       const float qv = A00 * dxc * dxc + 2.f * A01 * dxc * dyv + A11 * dyv * dyv;
@@ -122,8 +137,12 @@ int raster_cull_mask(const GsRasterParams& p, const RasterArgs& a, cudaStream_t 
   const FastLayout L = fast_layout(p);
   unsigned char* ws = (unsigned char*)a.workspace;
   const int tiles = tiles_wide(p) * tiles_high(p);
-  raster_cull_mask_kernel<<<tiles, 128, 0, st>>>(p, (const float4*)(ws + L.off_recF), a.tile_ranges, a.overlap_to_point,
-                                                 ws + L.off_mask);
+  if (p.antialias)
+    raster_cull_mask_kernel<true><<<tiles, 128, 0, st>>>(p, (const float4*)(ws + L.off_recB), a.tile_ranges,
+                                                         a.overlap_to_point, ws + L.off_mask);
+  else
+    raster_cull_mask_kernel<false><<<tiles, 128, 0, st>>>(p, (const float4*)(ws + L.off_recF), a.tile_ranges,
+                                                          a.overlap_to_point, ws + L.off_mask);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }
@@ -131,7 +150,7 @@ int raster_cull_mask(const GsRasterParams& p, const RasterArgs& a, cudaStream_t 
 // ------------------------------------------------------------------------------------------------ forward
 // BATCH = staged tile-list entries per buffer: 128 for narrow features, 64 for FP >= 16 (shared memory budget).
 // FOURTH: with FP = 4 the fourth accumulator is only needed when F = 4 (it is padding for F <= 3).
-template <int FP, bool VIS, int BATCH, bool FOURTH = true>
+template <int FP, bool VIS, int BATCH, bool FOURTH = true, bool AA = false>
 __global__ void __launch_bounds__(kFwdThreads)
 raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
                        const float* __restrict__ featP, const int32_t* __restrict__ ranges,
@@ -238,10 +257,18 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
           const float4* ent = s_e[buf][j];
           const float4 r0 = ent[0], r1 = ent[1];
           const float dx = pxf - r0.x, dy = pyf - r0.y;
-          const float tx = fmaf(dy, r0.w, dx * r0.z);
-          const float ty = fmaf(dy, r1.y, dx * r1.x);
-          const float ex = fmaf(-ty, ty, fmaf(-tx, tx, r1.z));
-          const float alpha = fminf(fast_ex2(ex), cmax);
+          float alpha;
+          if constexpr (AA) {   // gaussian integrated over the pixel: raster_math.cuh pdf_aa with MUFU ex2 / rcp
+            const float tx = fmaf(dy, r0.w, dx * r0.z), ty = fmaf(dy, r0.z, -dx * r0.w);
+            const float Sx = aa_sig(( tx + 0.5f) * r1.x) - aa_sig((tx - 0.5f) * r1.x);
+            const float Sy = aa_sig(( ty + 0.5f) * r1.y) - aa_sig((ty - 0.5f) * r1.y);
+            alpha = fminf(6.283185307179586f * r1.z * fast_rcp(r1.x * r1.y) * (Sx * Sy), cmax);
+          } else {
+            const float tx = fmaf(dy, r0.w, dx * r0.z);
+            const float ty = fmaf(dy, r1.y, dx * r1.x);
+            const float ex = fmaf(-ty, ty, fmaf(-tx, tx, r1.z));
+            alpha = fminf(fast_ex2(ex), cmax);
+          }
           // branch-free blend: a pixel below the threshold adds weight 0 (exactly nothing), which costs less than
           // the divergent branch did (the cull leaves few gaussians that miss every pixel of the block)
           const float weight = alpha > thr ? alpha * (1.f - W) : 0.f;
@@ -283,8 +310,8 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
 }
 
 bool raster_fast_supported(const GsRasterParams& p) {
-  return p.dtype == GS_F32 && p.tile_size == kFastTile && !p.antialias && p.use_alpha_blending &&
-         fast_feature_pad(p.num_features) != 0 && p.num_points < (1ll << 31);
+  return p.dtype == GS_F32 && p.tile_size == kFastTile && (!p.antialias || p.num_features <= 7) &&
+         p.use_alpha_blending && fast_feature_pad(p.num_features) != 0 && p.num_points < (1ll << 31);
 }
 
 size_t raster_fast_workspace_bytes(const GsRasterParams& p) { return fast_layout(p).total; }
@@ -297,10 +324,22 @@ int raster_fwd_fast(const GsRasterParams& p, const RasterArgs& a, cudaStream_t s
   const FastLayout L = fast_layout(p);
   unsigned char* ws = (unsigned char*)a.workspace;
   const unsigned char* cmask = ws + L.off_mask;
-  const float4* rec = (const float4*)(ws + L.off_recF);
+  const float4* rec = (const float4*)(ws + (p.antialias ? L.off_recB : L.off_recF));
   const float* featP = (const float*)(ws + L.off_feat);
   const int tiles = tiles_wide(p) * tiles_high(p);
   const bool vis = p.compute_visibility && a.visibility != nullptr;
+  if (p.antialias) {   // narrow features only (raster_fast_supported)
+#define GS_FWD_AA(FPV, VISV, FOURTHV)                                                                              \
+  raster_fwd_fast_kernel<FPV, VISV, 128, FOURTHV, true><<<tiles, kFwdThreads, 0, st>>>(                            \
+      p, rec, featP, a.tile_ranges, a.overlap_to_point, (float*)a.image, (float*)a.image_alpha,                    \
+      (float*)a.visibility, cmask)
+    if (L.FP == 4 && p.num_features < 4) { if (vis) GS_FWD_AA(4, true, false); else GS_FWD_AA(4, false, false); }
+    else if (L.FP == 4) { if (vis) GS_FWD_AA(4, true, true); else GS_FWD_AA(4, false, true); }
+    else { if (vis) GS_FWD_AA(8, true, true); else GS_FWD_AA(8, false, true); }
+#undef GS_FWD_AA
+    GS_LAUNCH_CHECK();
+    return GS_OK;
+  }
 #define GS_FWD_LAUNCH(FPV, VISV, BATCHV)                                                                           \
   do {                                                                                                             \
     if (FPV == 4 && p.num_features < 4)                                                                            \

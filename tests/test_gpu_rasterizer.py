@@ -109,6 +109,18 @@ def test_antialias_generic(cuda_device):
   compare_forward_backward(cuda_device, 40, 1500, (150, 100), cfg, scale=1.0)
 
 
+@pytest.mark.parametrize("seed,n,size,scale,channels", [(42, 3000, (200, 150), 1.0, 3), (43, 4000, (64, 64), 6.0, 3),
+                                                         (44, 20000, (1024, 1024), 0.5, 3), (45, 1500, (160, 112), 2.0, 5),
+                                                         (46, 2000, (100, 70), 0.3, 1)])
+def test_antialias_fast_path(cuda_device, seed, n, size, scale, channels):
+  """antialias=True at tile 16 with narrow features runs the measured (fast) kernels: the pixel-integrated gaussian
+  (taichi_lib/generic.py:340-404) with visibility and split / prune statistics — BASELINE.json config 1's setting
+  (examples/fit_image_gaussians.py:289-296); (43) has tiles with many hundred overlaps, (46) sub-pixel gaussians."""
+  cfg = RasterConfig(antialias=True, blur_cov=0.0, compute_visibility=True, compute_point_heuristic=True)
+  compare_forward_backward(cuda_device, seed, n, size, cfg, channels=channels, scale=scale,
+                           alpha_range=(0.5, 1.0) if seed == 44 else (0.1, 0.9))
+
+
 def test_quantile_mode_forward(cuda_device):
   cfg = RasterConfig(use_alpha_blending=False, saturate_threshold=0.5)
   size = (150, 100)
