@@ -57,6 +57,54 @@ def c1(dev):
     return {"V": 20_000, "K": K}
   with torch.no_grad():
     K = int(map_to_tiles(project_gaussians2d(g), g.z_depth.clamp(0, 1), size, cfg)[0].shape[0])
+  step.params = (g.position, g.log_scaling, g.rotation, g.alpha_logit, g.feature)
+  return step
+
+
+def c1_graph(dev):
+  """config 1 with the whole step (projection to 2D, tile mapping, rasterizer forward, loss, backward) replayed from ONE
+  CUDA graph: rasterize(..., overlap_capacity=) keeps the overlap total on the device, so nothing synchronises."""
+  torch.manual_seed(0)
+  size = (1024, 1024)
+  g = random_2d_gaussians(20_000, size, num_channels=3, scale_factor=0.5, alpha_range=(0.5, 1.0)).to(device=dev)
+  g.requires_grad_(True)
+  params = (g.position, g.log_scaling, g.rotation, g.alpha_logit, g.feature)
+  target = torch.rand(size[1], size[0], 3, device=dev)
+  cfg = RasterConfig(compute_point_heuristic=True, compute_visibility=True, tile_size=16, pixel_stride=(2, 2),
+                     antialias=True, blur_cov=0.0)
+  with torch.no_grad():
+    K = int(map_to_tiles(project_gaussians2d(g), g.z_depth.clamp(0, 1), size, cfg)[0].shape[0])
+  capacity = int(K * 1.5)
+  total = torch.zeros(1, dtype=torch.int32, device=dev)
+  out = {}
+
+  def body():
+    packed = project_gaussians2d(g)
+    r = rasterize(packed, g.z_depth.clamp(0, 1), g.feature, size, cfg, overlap_capacity=capacity,
+                  overlap_total_out=total)
+    loss = torch.nn.functional.mse_loss(torch.sigmoid(r.image), target)
+    loss.backward()
+    out["loss"] = loss.detach()
+
+  side = torch.cuda.Stream(device=dev)
+  side.wait_stream(torch.cuda.current_stream(dev))
+  with torch.cuda.stream(side):   # warm-up on a side stream, as graph capture requires
+    for _ in range(3):
+      for t in params:
+        t.grad = None
+      body()
+  torch.cuda.current_stream(dev).wait_stream(side)
+  for t in params:
+    t.grad = None
+  graph = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(graph):
+    body()
+
+  def step():
+    graph.replay()
+    return {"V": 20_000, "K": K, "capacity": capacity}
+  # everything the graph reads must outlive it: the replay dereferences the captured addresses
+  step.graph_state = dict(params=params, out=out, total=total, keep_alive=(g, target, graph, body))
   return step
 
 
@@ -116,6 +164,7 @@ def c5(dev):
 
 
 CONFIGS = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5}
+EXTRA = {"c1_graph": c1_graph}   # not part of the default list: python benchmarks/configs.py --only c1,c1_graph
 
 
 def main():
@@ -126,9 +175,10 @@ def main():
   dev = torch.device("cuda:0")
   for name in args.only.split(","):
     try:
-      step = CONFIGS[name](dev)
+      maker = CONFIGS.get(name) or EXTRA[name]
+      step = maker(dev)
       ms, stages, info = timed(step, args.steps)
-      print(json.dumps({"config": name, "what": CONFIGS[name].__doc__.strip(), "ms_per_frame_fwd_bwd": round(ms, 3),
+      print(json.dumps({"config": name, "what": " ".join(maker.__doc__.split()), "ms_per_frame_fwd_bwd": round(ms, 3),
                         "stage_ms": stages, **info, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2)}),
             flush=True)
     except Exception as e:   # noqa: BLE001 - report and continue with the next configuration

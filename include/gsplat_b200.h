@@ -219,6 +219,16 @@ int gs_tile_emit_tiles(const GsTileParams* p, const float* gaussians, const int3
                        const uint64_t* tile_masks, uint32_t* tile_ids, int32_t* values, void* stream);
 int gs_find_ranges_tiles(const GsTileParams* p, int64_t num_overlaps, const uint32_t* sorted_tile_ids,
                          int32_t* tile_ranges, void* stream);
+/* Capacity-bounded tail of the tile mapping: the overlap total K stays on the device (the int32 behind the scan's
+ * total_out), tile_ids / values have `capacity` rows.  No host read-back anywhere in map_to_tiles, so a whole
+ * forward + backward step can be captured in a CUDA graph (the reference synchronises the device twice here,
+ * cuda_lib/full_cumsum.cu:45, radix_sort_pairs.cu:27).  Overlaps that would land at or beyond `capacity` are dropped
+ * (the caller compares K with the capacity after the fact); gs_radix_sort_pairs_counted sorts min(K, capacity) rows. */
+int gs_tile_emit_tiles_capped(const GsTileParams* p, const float* gaussians, const int32_t* perm, const int32_t* cum,
+                              const uint64_t* tile_masks, int64_t capacity, uint32_t* tile_ids, int32_t* values,
+                              void* stream);
+int gs_find_ranges_tiles_counted(const GsTileParams* p, int64_t capacity, const int32_t* num_overlaps_dev,
+                                 const uint32_t* sorted_tile_ids, int32_t* tile_ranges, void* stream);
 
 /* ------------------------------------------------------------------ rasterizer
  * replaces _forward_kernel (rasterizer/forward.py:24-137) and _backward_kernel

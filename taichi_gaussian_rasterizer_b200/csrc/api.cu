@@ -19,7 +19,7 @@ void set_error(const char* fmt, ...) {
 
 extern "C" {
 
-int gs_abi_version(void) { return 3; }
+int gs_abi_version(void) { return 4; }
 
 const char* gs_last_error_string(void) { return gs::g_error; }
 

@@ -159,7 +159,10 @@ __global__ void __launch_bounds__(kTileBlock)
 tile_query_kernel(const __grid_constant__ GsTileParams p, int img_w, int img_h, const float* __restrict__ g,
                   const float* __restrict__ depth, const int32_t* __restrict__ perm, const int32_t* __restrict__ cum,
                   int32_t* __restrict__ counts, KeyT* __restrict__ keys, int32_t* __restrict__ values,
-                  uint2* __restrict__ masks, const int32_t* __restrict__ n_dev = nullptr) {
+                  uint2* __restrict__ masks, const int32_t* __restrict__ n_dev = nullptr,
+                  long long limit = 0x7fffffffffffffffll) {
+  // limit: capacity of keys / values (emit passes): entries that would land at or beyond it are dropped, so a
+  // capacity-sized buffer (no host read-back of the overlap total, CUDA-graph friendly) cannot be overrun
   constexpr bool EMIT = MODE != 0;
   const int64_t slot = (int64_t)blockIdx.x * kTileBlock + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -191,8 +194,10 @@ tile_query_kernel(const __grid_constant__ GsTileParams p, int img_w, int img_h, 
           const int b = __ffs(bits) - 1;
           bits &= bits - 1;
           const int tu = (int)(((float)b + 0.5f) * inv_span), tv = b - tu * span_y;
-          keys[base + c] = (KeyT)((tu + min_x) + (tv + min_y) * tiles_wide);
-          values[base + c] = (int32_t)i;
+          if (base + c < limit) {
+            keys[base + c] = (KeyT)((tu + min_x) + (tv + min_y) * tiles_wide);
+            values[base + c] = (int32_t)i;
+          }
           ++c;
         }
       }
@@ -211,7 +216,7 @@ tile_query_kernel(const __grid_constant__ GsTileParams p, int img_w, int img_h, 
     for (int tu = 0; tu < qy.span_x; ++tu)
       for (int tv = 0; tv < qy.span_y; ++tv)
         if (test_tile(qy, tu, tv, ts)) {
-          if (EMIT) {
+          if (EMIT && base + count < limit) {
             int tile_id = (tu + qy.min_x) + (tv + qy.min_y) * tiles_wide;
             keys[base + count] = MODE == 2 ? (KeyT)tile_id
                                  : sizeof(KeyT) == 8 ? (KeyT)make_key64(d, tile_id) : (KeyT)make_key32(d, tile_id);
@@ -248,7 +253,7 @@ tile_query_kernel(const __grid_constant__ GsTileParams p, int img_w, int img_h, 
         hit = test_tile(q, tu, tv, ts);
       }
       const unsigned hm = __ballot_sync(kFull, hit);
-      if (EMIT && hit) {
+      if (EMIT && hit && bq + running + __popc(hm & ((1u << lane) - 1u)) < limit) {
         const int r = running + __popc(hm & ((1u << lane) - 1u));
         int tile_id = (tu + q.min_x) + (tv + q.min_y) * tiles_wide;
         keys[bq + r] = MODE == 2 ? (KeyT)tile_id
@@ -266,8 +271,10 @@ tile_query_kernel(const __grid_constant__ GsTileParams p, int img_w, int img_h, 
 // Tile ranges from sorted keys.  ranges[t] = [first, last+1); tiles without overlaps stay [0,0].
 // ------------------------------------------------------------------------------------------------
 template <typename KeyT, int SHIFT>
-__global__ void find_ranges_kernel(int64_t n, const KeyT* __restrict__ keys, int32_t* __restrict__ ranges) {
+__global__ void find_ranges_kernel(int64_t n, const KeyT* __restrict__ keys, int32_t* __restrict__ ranges,
+                                   const int32_t* __restrict__ n_dev = nullptr) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = min(n, (int64_t)*n_dev);   // counted variant: n is the capacity
   if (i >= n) return;
   const int max_tile = 65535;
   const int tile = (int)(keys[i] >> SHIFT);
@@ -513,6 +520,39 @@ int gs_tile_emit_tiles(const GsTileParams* p, const float* gaussians, const int3
   int img_w = (int)ceil_div(p->image_width, ts) * ts, img_h = (int)ceil_div(p->image_height, ts) * ts;
   tile_query_kernel<2, uint32_t><<<(unsigned)ceil_div(p->num_points, kTileBlock), kTileBlock, 0, (cudaStream_t)stream>>>(
       *p, img_w, img_h, gaussians, nullptr, perm, cum, nullptr, tile_ids, values, (uint2*)tile_masks);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+int gs_tile_emit_tiles_capped(const GsTileParams* p, const float* gaussians, const int32_t* perm, const int32_t* cum,
+                              const uint64_t* tile_masks, int64_t capacity, uint32_t* tile_ids, int32_t* values,
+                              void* stream) {
+  int rc = check_tile_params(p, "gs_tile_emit_tiles_capped");
+  if (rc != GS_OK) return rc;
+  if (p->num_points == 0 || capacity <= 0) return GS_OK;
+  GS_CHECK_ARG(gaussians && perm && cum && tile_ids && values, "gs_tile_emit_tiles_capped: null tensor");
+  int ts = p->tile_size;
+  int img_w = (int)ceil_div(p->image_width, ts) * ts, img_h = (int)ceil_div(p->image_height, ts) * ts;
+  tile_query_kernel<2, uint32_t><<<(unsigned)ceil_div(p->num_points, kTileBlock), kTileBlock, 0, (cudaStream_t)stream>>>(
+      *p, img_w, img_h, gaussians, nullptr, perm, cum, nullptr, tile_ids, values, (uint2*)tile_masks, nullptr,
+      (long long)capacity);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+int gs_find_ranges_tiles_counted(const GsTileParams* p, int64_t capacity, const int32_t* num_overlaps_dev,
+                                 const uint32_t* sorted_tile_ids, int32_t* tile_ranges, void* stream) {
+  int rc = check_tile_params(p, "gs_find_ranges_tiles_counted");
+  if (rc != GS_OK) return rc;
+  GS_CHECK_ARG(tile_ranges != nullptr && capacity >= 0 && num_overlaps_dev != nullptr,
+               "gs_find_ranges_tiles_counted: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t tiles = ceil_div(p->image_width, p->tile_size) * ceil_div(p->image_height, p->tile_size);
+  GS_CUDA(cudaMemsetAsync(tile_ranges, 0, (size_t)tiles * 2 * sizeof(int32_t), st));
+  if (capacity == 0) return GS_OK;
+  GS_CHECK_ARG(sorted_tile_ids != nullptr, "gs_find_ranges_tiles_counted: null keys");
+  find_ranges_kernel<uint32_t, 0><<<(unsigned)ceil_div(capacity, 256), 256, 0, st>>>(capacity, sorted_tile_ids, tile_ranges,
+                                                                                  num_overlaps_dev);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }

@@ -23,7 +23,7 @@ from numbers import Integral
 
 import torch
 from beartype import beartype
-from beartype.typing import Tuple
+from beartype.typing import Optional, Tuple
 
 from .. import _native as N
 from ..cuda_lib import full_cumsum_device, radix_sort_pairs, radix_sort_pairs_counted
@@ -69,7 +69,9 @@ def _check_inputs(gaussians, depth, image_size, config):
 def map_to_tiles(gaussians: torch.Tensor, depth: torch.Tensor,
                  image_size: Tuple[Integral, Integral],
                  config: RasterConfig,
-                 use_depth16: bool = False
+                 use_depth16: bool = False,
+                 overlap_capacity: Optional[int] = None,
+                 overlap_total_out: Optional[torch.Tensor] = None
                  ) -> Tuple[torch.Tensor, torch.Tensor]:
   """ maps gaussians to tiles, sorted by depth (front to back):
     Parameters:
@@ -81,8 +83,57 @@ def map_to_tiles(gaussians: torch.Tensor, depth: torch.Tensor,
     Returns:
      overlap_to_point: (K, ) int32, maps overlap index to point index
      tile_ranges: (TH, TW, 2) int32, maps tile index to its [start, end) range of overlap indices
+
+    ``overlap_capacity`` (extension): bound on the number of overlaps K.  ``overlap_to_point`` then has exactly that
+    many rows (those past K are undefined), K never travels to the host — no synchronisation at all, so a training step
+    can be captured in a CUDA graph — and overlaps beyond the capacity are DROPPED: pass a 1-element int32 CUDA tensor
+    as ``overlap_total_out`` to receive K and compare it with the capacity now and then.
   """
+  if overlap_capacity is not None:
+    return _map_to_tiles_capped(gaussians, depth, image_size, config, use_depth16, int(overlap_capacity),
+                                overlap_total_out)
   return _map_to_tiles(gaussians, depth, image_size, config, use_depth16, ndc_range=None)
+
+
+def _map_to_tiles_capped(gaussians, depth, image_size, config, use_depth16, capacity, total_out=None):
+  """The depth-first mapping with capacity-sized key buffers and the overlap total left on the device."""
+  shape = _check_inputs(gaussians, depth, image_size, config)
+  assert capacity >= 0
+  with torch.no_grad():
+    device = gaussians.device
+    g = gaussians.detach().to(torch.float32).contiguous()
+    d = depth.detach().to(torch.float32).contiguous()
+    n = g.shape[0]
+    stream = N.stream_ptr(device)
+    p = _tile_params(n, image_size, config, use_depth16)
+    tile_ranges = torch.empty((*shape, 2), dtype=torch.int32, device=device)
+    overlap_to_point = torch.empty((capacity,), dtype=torch.int32, device=device)
+    if n == 0 or capacity == 0:
+      tile_ranges.zero_()
+      if total_out is not None:
+        total_out.zero_()
+      return overlap_to_point, tile_ranges
+    depth_keys = torch.empty((n,), dtype=torch.int32, device=device)
+    iota = torch.empty((n,), dtype=torch.int32, device=device)
+    N.call("gs_depth_keys", ctypes.byref(p), N.ptr(d), ctypes.c_double(0.0), ctypes.c_double(0.0), N.ptr(depth_keys),
+           N.ptr(iota), stream)
+    _, perm = radix_sort_pairs(depth_keys, iota, 0, 16 if use_depth16 else 32)
+    counts = torch.empty((n,), dtype=torch.int32, device=device)
+    masks = torch.empty((n,), dtype=torch.int64, device=device)
+    N.call("gs_tile_count_perm", ctypes.byref(p), N.ptr(g), N.ptr(perm), N.ptr(counts), N.ptr(masks), stream)
+    cum = full_cumsum_device(counts)
+    total_dev = cum[n:]                      # K, on the device
+    if total_out is not None:
+      total_out.copy_(total_dev.reshape(total_out.shape))
+    tile_ids = torch.empty((capacity,), dtype=torch.int32, device=device)
+    values = torch.empty((capacity,), dtype=torch.int32, device=device)
+    N.call("gs_tile_emit_tiles_capped", ctypes.byref(p), N.ptr(g), N.ptr(perm), N.ptr(cum), N.ptr(masks),
+           ctypes.c_int64(capacity), N.ptr(tile_ids), N.ptr(values), stream)
+    tile_bits = max(1, (shape[0] * shape[1] - 1).bit_length())
+    tile_ids, overlap_to_point = radix_sort_pairs_counted(tile_ids, values, total_dev, 0, tile_bits)
+    N.call("gs_find_ranges_tiles_counted", ctypes.byref(p), ctypes.c_int64(capacity), N.ptr(total_dev), N.ptr(tile_ids),
+           N.ptr(tile_ranges), stream)
+    return overlap_to_point, tile_ranges
 
 
 def launch_depth_order_counted(depth_capacity, count_device, image_size, config, use_depth16=False, ndc_range=None):

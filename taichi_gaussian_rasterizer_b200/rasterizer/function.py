@@ -153,7 +153,9 @@ def rasterize_with_tiles(gaussians2d: torch.Tensor, features: torch.Tensor,
 
 def rasterize(gaussians2d: torch.Tensor, depth: torch.Tensor,
               features: torch.Tensor, image_size: Tuple[Integral, Integral],
-              config: RasterConfig, use_depth16: bool = False) -> RasterOut:
+              config: RasterConfig, use_depth16: bool = False,
+              overlap_capacity: Optional[int] = None,
+              overlap_total_out: Optional[torch.Tensor] = None) -> RasterOut:
   """
   Rasterize an image given 2d gaussians, depths and features (tile mapping + rasterization).
 
@@ -163,12 +165,15 @@ def rasterize(gaussians2d: torch.Tensor, depth: torch.Tensor,
       features: (N, F)   features
       image_size: (2, ) tuple of ints, (width, height)
       config: RasterConfig
+      overlap_capacity, overlap_total_out: (extension) see map_to_tiles — bound the overlap count so that nothing
+        is read back to the host and the call can sit inside a CUDA graph (examples/fit_image_gaussians.py --graph)
   """
   assert gaussians2d.shape[0] == depth.shape[0] == features.shape[0], \
     f"Size mismatch: got {gaussians2d.shape}, {depth.shape}, {features.shape}"
 
   overlap_to_point, tile_overlap_ranges = map_to_tiles(
-    gaussians2d, depth, image_size=image_size, config=config, use_depth16=use_depth16)
+    gaussians2d, depth, image_size=image_size, config=config, use_depth16=use_depth16,
+    overlap_capacity=overlap_capacity, overlap_total_out=overlap_total_out)
 
   return rasterize_with_tiles(
     gaussians2d, features,

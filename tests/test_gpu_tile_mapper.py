@@ -6,7 +6,7 @@ import torch
 import oracle
 from taichi_gaussian_rasterizer_b200 import RasterConfig, map_to_tiles
 from taichi_gaussian_rasterizer_b200.mapper.tile_mapper import map_to_tiles_staged
-from util import scene2d
+from util import rel_l2, scene2d
 
 pytestmark = pytest.mark.gpu
 
@@ -112,3 +112,49 @@ def test_fused_ndc_sort_depth_is_bit_identical(cuda_device):
     a16, _ = map_to_tiles(gd, ndc_depth(linear, near, far), size, cfg, use_depth16=True)
     b16, _ = _map_to_tiles(gd, linear, size, cfg, use_depth16=True, ndc_range=(near, far))
     assert torch.equal(a16, b16)
+
+
+def test_capacity_bounded_mapping_matches_and_reports_overflow(cuda_device):
+  """map_to_tiles(overlap_capacity=): same lists and ranges without any host read-back; beyond the capacity overlaps
+  are dropped and the reported total says so."""
+  cfg = RasterConfig()
+  size = (200, 150)
+  g, depth, _ = scene2d(3, 3000, size, scale_factor=2.0)
+  gd, dd = g.to(cuda_device), depth.to(cuda_device)
+  o2p, ranges = map_to_tiles(gd, dd, size, cfg)
+  K = o2p.shape[0]
+  total = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+  o2p_c, ranges_c = map_to_tiles(gd, dd, size, cfg, overlap_capacity=K + 1000, overlap_total_out=total)
+  assert o2p_c.shape == (K + 1000,) and int(total.item()) == K
+  assert torch.equal(o2p_c[:K], o2p) and torch.equal(ranges_c, ranges)
+  o2p_s, ranges_s = map_to_tiles(gd, dd, size, cfg, overlap_capacity=K // 2, overlap_total_out=total)
+  assert o2p_s.shape == (K // 2,) and int(total.item()) == K            # the caller sees K > capacity
+  assert int(ranges_s.max()) <= K // 2                                  # nothing points past the buffer
+  e, r = map_to_tiles(gd[:0], dd[:0], size, cfg, overlap_capacity=16, overlap_total_out=total)
+  assert int(total.item()) == 0 and int(r.abs().sum()) == 0
+
+
+def test_whole_step_in_a_cuda_graph(cuda_device):
+  """The 2D fit step of BASELINE config 1 replayed from one CUDA graph (benchmarks/configs.py c1_graph) gives the
+  gradients of the eager step."""
+  import sys
+  from pathlib import Path
+  sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "benchmarks"))
+  import configs
+  step = configs.c1_graph(cuda_device)
+  step()
+  torch.cuda.synchronize()
+  st = step.graph_state
+  graph_grads = [t.grad.clone() for t in st["params"]]
+  graph_loss = float(st["out"]["loss"])
+  assert int(st["total"].item()) > 0
+  eager = configs.c1(cuda_device)       # same seed, same scene, eager launches with the read-back of K
+  eager()
+  torch.cuda.synchronize()
+  for a, b in zip(graph_grads, [t.grad for t in eager.params]):   # the graph computes what the eager step computes
+    assert rel_l2(a, b) < 1e-5
+  step()                                 # a second replay gives the same numbers again
+  torch.cuda.synchronize()
+  assert abs(float(st["out"]["loss"]) - graph_loss) < 1e-7
+  for a, b in zip(graph_grads, [t.grad for t in st["params"]]):
+    assert rel_l2(a, b) < 1e-5
