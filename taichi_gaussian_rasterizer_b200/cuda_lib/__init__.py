@@ -95,9 +95,47 @@ def radix_argsort(keys: torch.Tensor):
   return idx
 
 
-def segmented_sort_pairs(*args, **kwargs):
-  raise NotImplementedError("segmented_sort_pairs is exported by the reference's cuda_lib but not used by the "
-                            "render path (SURVEY.md K12); it is out of scope here")
+def segmented_sort_pairs(keys: torch.Tensor, values: torch.Tensor, start_offset: torch.Tensor, end_offset: torch.Tensor):
+  """Sort (key, value) pairs by ascending signed key inside every segment [start_offset[i], end_offset[i])
+  (cuda_lib/segmented_sort_pairs.cu:9-73: cub::DeviceSegmentedSort::SortPairs; int32 or int16 keys, int32 values, int64
+  offsets; segments must not overlap).  Rows outside every segment are copied through.  Not on the render path
+  (SURVEY.md K12): composed from the onesweep sort — a stable sort of all rows by key, then a stable sort by segment
+  number, then a scatter of every segment to its own offsets — rather than a dedicated kernel."""
+  check_cuda("keys", keys)
+  check_cuda("values", values)
+  assert keys.dim() == 1 and values.dim() == 1 and keys.shape == values.shape, "keys and values must be 1D and equal in size"
+  assert start_offset.dim() == 1 and start_offset.shape == end_offset.shape, "offsets must be 1D and equal in size"
+  assert start_offset.dtype == torch.int64 and end_offset.dtype == torch.int64, "start_offset/end_offset must be int64"
+  assert keys.dtype in (torch.int32, torch.int16) and values.dtype == torch.int32, "Not yet implemented for data type."
+  n, nseg = keys.shape[0], start_offset.shape[0]
+  keys_out, values_out = keys.clone(), values.clone()
+  if n == 0 or nseg == 0:
+    return keys_out, values_out
+  dev = keys.device
+  lengths = (end_offset - start_offset).clamp_min(0)
+  # segment number of every row (nseg = outside): +1 / -1 marks at the segment borders, prefix sum
+  marks = torch.zeros((n + 1,), dtype=torch.int64, device=dev)
+  ids = torch.arange(1, nseg + 1, device=dev)
+  live = lengths > 0
+  marks.index_add_(0, start_offset[live], ids[live])
+  marks.index_add_(0, end_offset[live], -ids[live])
+  seg = torch.cumsum(marks[:n], 0) - 1
+  seg = torch.where(seg < 0, torch.full_like(seg, nseg), seg).to(torch.int32)
+  # pass 1: all rows by key (sign bit flipped: signed order on an unsigned radix sort); pass 2: stable by segment
+  flipped = (keys.to(torch.int32) ^ torch.tensor(-2 ** 31, dtype=torch.int32, device=dev)).contiguous()
+  rows = torch.arange(n, dtype=torch.int32, device=dev)
+  _, order = radix_sort_pairs(flipped, rows, 0, 32)
+  seg_sorted = seg[order.long()].contiguous()
+  _, order = radix_sort_pairs(seg_sorted, order.contiguous(), 0, max(1, int(nseg).bit_length()))
+  order = order.long()
+  # grouped row j of segment i goes to start_offset[i] + (j - first grouped row of segment i)
+  first = torch.cumsum(lengths, 0) - lengths
+  inside = int(lengths.sum().item())
+  seg_of = seg[order[:inside]].long()
+  dest = start_offset[seg_of] + (torch.arange(inside, device=dev) - first[seg_of])
+  keys_out[dest] = keys[order[:inside]]
+  values_out[dest] = values[order[:inside]]
+  return keys_out, values_out
 
 
 __all__ = ["full_cumsum", "full_cumsum_device", "radix_sort_pairs", "radix_sort_pairs_counted", "radix_argsort",

@@ -166,7 +166,7 @@ def rasterize(gaussians2d: torch.Tensor, depth: torch.Tensor,
       image_size: (2, ) tuple of ints, (width, height)
       config: RasterConfig
       overlap_capacity, overlap_total_out: (extension) see map_to_tiles — bound the overlap count so that nothing
-        is read back to the host and the call can sit inside a CUDA graph (examples/fit_image_gaussians.py --graph)
+        is read back to the host and the call can sit inside a CUDA graph (benchmarks/configs.py c1_graph)
   """
   assert gaussians2d.shape[0] == depth.shape[0] == features.shape[0], \
     f"Size mismatch: got {gaussians2d.shape}, {depth.shape}, {features.shape}"

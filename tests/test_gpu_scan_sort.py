@@ -59,3 +59,34 @@ def test_sort_preserves_inputs_and_runs_on_current_stream(cuda_device):
   s.synchronize()
   assert torch.equal(keys, k0) and torch.equal(values, v0)
   assert torch.equal(k_out & ((1 << 48) - 1), torch.sort(k0 & ((1 << 48) - 1), stable=True).values)
+
+
+@pytest.mark.parametrize("key_dtype", [torch.int32, torch.int16])
+def test_segmented_sort_pairs(cuda_device, key_dtype):
+  """cuda_lib.segmented_sort_pairs (cuda_lib/segmented_sort_pairs.cu:9-73, the demo of cuda_lib/__init__.py:47-60):
+  ascending signed keys inside every segment, rows outside the segments untouched, values follow their keys."""
+  from taichi_gaussian_rasterizer_b200.cuda_lib import segmented_sort_pairs
+  torch.manual_seed(4)
+  n = 5000
+  hi = 2 ** 15 if key_dtype == torch.int16 else 2 ** 31
+  keys = torch.randint(-hi, hi, (n,), dtype=torch.int64).to(key_dtype)
+  values = torch.arange(n, dtype=torch.int32)
+  cuts = torch.sort(torch.randperm(n - 1)[:40] + 1).values
+  bounds = torch.cat([torch.tensor([0]), cuts, torch.tensor([n])])
+  start, end = bounds[:-1].clone(), bounds[1:].clone()
+  start, end = torch.cat([start[:10], start[12:]]), torch.cat([end[:10], end[12:]])   # a gap: two segments left out
+  end[3] = start[3]                                                                  # and an empty segment
+  ko, vo = segmented_sort_pairs(keys.to(cuda_device), values.to(cuda_device), start.to(cuda_device), end.to(cuda_device))
+  ko, vo = ko.cpu(), vo.cpu()
+  covered = torch.zeros(n, dtype=torch.bool)
+  for s, e in zip(start.tolist(), end.tolist()):
+    if e > s:
+      covered[s:e] = True
+      ref = torch.sort(keys[s:e].long()).values
+      assert torch.equal(ko[s:e].long(), ref)
+      assert torch.equal(keys[vo[s:e].long()], ko[s:e])                 # values follow their keys
+      assert torch.equal(torch.sort(vo[s:e]).values, values[s:e])       # and stay inside their segment
+  assert torch.equal(ko[~covered], keys[~covered]) and torch.equal(vo[~covered], values[~covered])
+  e0, e1 = segmented_sort_pairs(keys[:0].to(cuda_device), values[:0].to(cuda_device), start[:0].to(cuda_device),
+                                end[:0].to(cuda_device))
+  assert e0.shape == (0,) and e1.shape == (0,)
