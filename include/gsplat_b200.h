@@ -248,8 +248,11 @@ typedef struct GsRasterParams {
   int32_t workspace_holds_packed;    /* bwd: the workspace is untouched since a gs_raster_fwd call made with the same
                                         gaussians / features AND a requires_grad flag set (fwd then packs the
                                         backward records too); 0 = repack */
-  int32_t kernel_variant;            /* 0 = the shipped kernels; other values select alternative instantiations for
-                                        A/B timing (benchmarks/variants.py); every value gives the same results */
+  int32_t kernel_variant;            /* 0 = the shipped kernels; bits select alternative instantiations kept for A/B
+                                        timing (benchmarks/variants.py), all tested to the same tolerances
+                                        (tests/test_gpu_rasterizer.py test_kernel_variants_agree): bit 0 = narrow backward
+                                        reduces every survivor alone (default: pairs), bit 1 = wide backward reduces the
+                                        feature gradient with warp butterflies (default: mma.sync product) */
   int64_t num_points;                /* V */
   int64_t num_overlaps;              /* K */
   double clamp_max_alpha, alpha_threshold, saturate_threshold;

@@ -191,7 +191,7 @@ raster_bwd_wide_kernel(const __grid_constant__ GsRasterParams p, const float4* _
 // on the tensor cores (mma.sync m16n8k8, tf32 inputs, f32 accumulate): the lanes park their blend weights in a
 // per-warp shared-memory tile during the replay (one 8 B store per survivor), G sits in shared memory once per tile.
 // tf32 alone (11 bit significands) would leave ~2e-4 relative error, above the 1e-4 gradient tolerance, so both
-// operands are split x = hi + lo with hi = x & 0xffffe000 (exactly representable) and three products are accumulated
+// operands are split x = hi + lo (both rounded to nearest tf32, residual 2^-24) and three products are accumulated
 // (hi hi + lo hi + hi lo; the dropped lo lo term is 2^-22): measured error against the oracle as for the f32 path.
 // Why mma.sync and not tcgen05: the product is per WARP (its own 16 survivors, its own 32 pixels), 16 x 32 x 40, issued
 // from inside a SIMT replay loop whose A operand is produced by the lanes a few instructions earlier; a CTA-level
@@ -207,7 +207,12 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-constexpr unsigned kTf32Mask = 0xffffe000u;
+// x = hi + lo, both rounded to nearest tf32: residual 2^-24 |x| (see raster_fast_fwd_wide.cu)
+__device__ __forceinline__ unsigned tf32_rna(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
 
 template <int FP>
 struct WideMmaLayout {
@@ -297,8 +302,8 @@ raster_bwd_wide_mma_kernel(const __grid_constant__ GsRasterParams p, const float
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float b0 = s_G[(tig + 8 * k) * L::GS + gid + 8 * n], b1 = s_G[(tig + 4 + 8 * k) * L::GS + gid + 8 * n];
-          const unsigned b0h = __float_as_uint(b0) & kTf32Mask, b1h = __float_as_uint(b1) & kTf32Mask;
-          const unsigned b0l = __float_as_uint(b0 - __uint_as_float(b0h)), b1l = __float_as_uint(b1 - __uint_as_float(b1h));
+          const unsigned b0h = tf32_rna(b0), b1h = tf32_rna(b1);
+          const unsigned b0l = tf32_rna(b0 - __uint_as_float(b0h)), b1l = tf32_rna(b1 - __uint_as_float(b1h));
           mma_tf32_16x8x8(c, ahi[k], b0h, b1h);
           mma_tf32_16x8x8(c, alo[k], b0h, b1h);
           mma_tf32_16x8x8(c, ahi[k], b0l, b1l);
@@ -416,8 +421,8 @@ raster_bwd_wide_mma_kernel(const __grid_constant__ GsRasterParams p, const float
           else if (HEUR) atomicAdd(heuristic + idx * 2 + (own_g - 7), vg[0]);
         }
         if (fg) {   // park the blend weights of this survivor: row ns of the warp's weight tile
-          const float whi = __uint_as_float(__float_as_uint(wl) & kTf32Mask);
-          s_W[ns * L::WS + lane] = make_float2(whi, wl - whi);
+          const float whi = __uint_as_float(tf32_rna(wl));
+          s_W[ns * L::WS + lane] = make_float2(whi, __uint_as_float(tf32_rna(wl - whi)));
           if (lane == 0) s_idx[ns] = (int)idx;
           if (++ns == kMmaGroup) flush_group();
         }

@@ -258,3 +258,17 @@ def test_visibility(cuda_device):
     r32 = rasterize(g.float().to(cuda_device), depth.to(cuda_device), f32, image_size, config)
     r32.image.sum().backward()
     assert rel_l2(f32.grad[:, 0], r32.visibility) < GRAD_REL_L2
+
+
+@pytest.mark.parametrize("variant,channels", [(1, 3), (2, 34), (2, 12)])
+def test_kernel_variants_agree(cuda_device, variant, channels):
+  """GsRasterParams.kernel_variant selects alternative instantiations kept for A/B timing (benchmarks/variants.py):
+  bit 0 = the narrow backward reduces every survivor on its own (default: in pairs), bit 1 = the wide backward reduces
+  the feature gradient with warp butterflies (default: tensor-core product).  Every variant must pass the same parity
+  check as the default."""
+  cfg = RasterConfig(compute_visibility=True, compute_point_heuristic=True)
+  set_raster_options(kernel_variant=variant)
+  try:
+    compare_forward_backward(cuda_device, 60 + channels, 1500, (160, 112), cfg, channels=channels, scale=2.0)
+  finally:
+    set_raster_options(kernel_variant=0)
