@@ -9,9 +9,9 @@ OUT=gpurun_out
 mkdir -p $OUT
 python bench.py > $OUT/bench_$TAG.log 2>&1; echo "bench rc=$?"; tail -1 $OUT/bench_$TAG.log | cut -c1-400
 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref_$TAG.log 2>&1; echo "reference arm rc=$?"; tail -1 $OUT/bench_ref_$TAG.log | cut -c1-300
-python benchmarks/configs.py > $OUT/configs_$TAG.log 2>&1; echo "configs rc=$?"
+python benchmarks/configs.py --only c1,c1_graph,c2,c3,c4,c5 > $OUT/configs_$TAG.log 2>&1; echo "configs rc=$?"
 python benchmarks/timeline.py > $OUT/timeline_$TAG.log 2>&1; echo "timeline rc=$?"
-SMALL="python bench.py --no-cpu-baseline --steps 2 --warmup 1 --views-per-rank 2"
+SMALL="python bench.py --no-cpu-baseline --no-configs --no-stock --steps 2 --warmup 1 --views-per-rank 2"
 $SMALL > $OUT/plain_$TAG.log 2>&1; echo "plain rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches_$TAG.csv $SMALL > $OUT/ncu_launches_$TAG.log 2>&1; echo "launch list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'raster_.wd_fast' -s 6 -c 2 -f -o $OUT/prof_raster_$TAG $SMALL > $OUT/ncu_raster_$TAG.log 2>&1; echo "raster capture rc=$?"

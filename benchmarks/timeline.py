@@ -24,12 +24,12 @@ from taichi_gaussian_rasterizer_b200 import RasterConfig, evaluate_sh_views, ren
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--views", type=int, default=4)
-  ap.add_argument("--num-gaussians", type=int, default=bench.WORKLOAD["num_gaussians"])
+  ap.add_argument("--num-gaussians", type=int, default=0)
   args = ap.parse_args()
-  W = dict(bench.WORKLOAD, num_gaussians=args.num_gaussians)
+  from taichi_gaussian_rasterizer_b200.synthetic import BASELINE_SCENES
+  W = dict(bench.WORKLOADS["bench"], image_size=BASELINE_SCENES["bench"]["image_size"])
   dev = torch.device("cuda:0")
-  g_cpu, cams = bench.build_scene(W["num_gaussians"], W["image_size"], W["sh_degree"], W["scale_factor"],
-                                  W["alpha_range"], W["seed"], num_views=args.views)
+  g_cpu, cams, _ = bench.build_scene(W["scene"], W["seed"], args.views, args.num_gaussians or None)
   g = g_cpu.to(device=dev)
   g.requires_grad_(True)
   cams = [c.to(device=dev) for c in cams]
