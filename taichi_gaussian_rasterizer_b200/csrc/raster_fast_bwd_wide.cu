@@ -198,7 +198,7 @@ raster_bwd_wide_kernel(const __grid_constant__ GsRasterParams p, const float4* _
 // tcgen05 tile (M >= 64, operands in descriptor-addressed shared memory, accumulator in TMEM behind an mbarrier) would
 // need a block-diagonal [gaussians x 256 pixels] operand of mostly zeros and two extra copies for the split.  The tensor
 // work is ~1 % of the kernel's issue slots either way; what it removes is the shuffle work.
-constexpr int kMmaGroup = 16;
+constexpr int kMmaGroup = 16;   // survivors per product (M of the mma)
 constexpr int kMmaBatch = 32;   // staged tile-list entries per buffer (64: 8.6 ms instead of 6.9 at config 4, the warps of a CTA drift further apart between barriers)
 
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
@@ -228,7 +228,7 @@ struct WideMmaLayout {
 };
 
 template <int FP, bool HEUR>
-__global__ void __launch_bounds__(kWideThreads, 2)
+__global__ void __launch_bounds__(kWideThreads, 2)   // 118 registers; an 80-register cap (three CTAs) spills: 8.0 vs 6.8 ms
 raster_bwd_wide_mma_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
                            const float* __restrict__ featP, const int32_t* __restrict__ ranges,
                            const int32_t* __restrict__ o2p, const float* __restrict__ image,
