@@ -150,7 +150,7 @@ def workload_name(W):
 def run_ours(args):
   import torch.distributed as dist
   from taichi_gaussian_rasterizer_b200 import RasterConfig, _native, evaluate_sh_views, render_gaussians
-  from taichi_gaussian_rasterizer_b200.distributed import GradientBucket
+  from taichi_gaussian_rasterizer_b200.distributed import GradientBucket, run_views
   from taichi_gaussian_rasterizer_b200.perspective import CameraParams
 
   world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,11 +208,12 @@ def run_ours(args):
             for _ in range(views)]
 
   poses_ready = torch.cuda.Event()
+  view_streams = [torch.cuda.Stream(device=device) for _ in range(args.streams)] if args.streams > 1 else []
 
   phase_events = []   # per timed device step: events around [reduce_early | last view | all_reduce]
 
   def _step(from_host: bool):
-    phase = phase_events if stats.get("record_phases") else None
+    phase = phase_events if (stats.get("record_phases") and world > 1) else None   # the markers join the view streams
     compute = torch.cuda.current_stream(device)
     if from_host:
       # this step's inputs (camera + target image of every view) go host -> device on a side stream: the (tiny) camera
@@ -236,32 +237,37 @@ def run_ours(args):
     else:
       cams = dev_cams
     bucket.zero_()
-    total = torch.zeros((), device=device)
     # the batch's cameras are known up front: the SH coefficients are read once for all views of the step
     colors = (evaluate_sh_views(gaussians.feature, gaussians.position, [c.camera_position for c in cams])
               if args.batched_sh else [None] * views)
-    for i in range(views):
-      cam = cams[i]
+    # Views are independent until their gradients meet in the bucket: distributed.run_views issues them round robin
+    # on `--streams` CUDA streams (the backward of one view runs under the read-backs of the next view's forward)
+    def before_last():
+      if phase is not None:
+        phase.append([torch.cuda.Event(enable_timing=True) for _ in range(4)])
+        phase[-1][0].record()
+      if views > 1 and args.reduce_early:
+        bucket.reduce_early()   # N > 1: the SH slices are all-reduced under the last view (distributed.py)
+      if phase is not None:
+        phase[-1][1].record()
+
+    def one_view(i):
       if from_host:
         st = staged[i]
-        compute.wait_event(st["ready"])
+        torch.cuda.current_stream(device).wait_event(st["ready"])
         target = st["target"].to(torch.float32).mul_(1.0 / 255.0)   # two small elementwise kernels, inside the timed region
       else:
         target = dev_targets[i]
-      if i == views - 1 and phase is not None:
-        phase.append([torch.cuda.Event(enable_timing=True) for _ in range(4)])
-        phase[-1][0].record()
-      if i == views - 1 and views > 1 and args.reduce_early:
-        bucket.reduce_early()   # N > 1: the SH slices are all-reduced under the last view (distributed.py)
-      if i == views - 1 and phase is not None:
-        phase[-1][1].record()
-      rendering = render_gaussians(gaussians, cam, config, use_sh=True, sh_colors=colors[i])
+      rendering = render_gaussians(gaussians, cams[i], config, use_sh=True, sh_colors=colors[i])
       loss = torch.nn.functional.l1_loss(rendering.image, target)   # mean |image - target|, one fused ATen op each way
       loss.backward()
-      total += loss.detach()
       if from_host:
-        st["free"].record(compute)
+        st["free"].record(torch.cuda.current_stream(device))
       stats["V"] = rendering.points_in_view.shape[0]
+      return loss.detach()
+
+    need_hook = phase is not None or (world > 1 and views > 1 and args.reduce_early)
+    total = run_views(views, one_view, view_streams, before_last if need_hook else None)
     if phase is not None:
       phase[-1][2].record()
     bucket.all_reduce()
@@ -314,10 +320,20 @@ def run_ours(args):
   sampler = ClockSampler(local_rank)
   if rank == 0:
     sampler.start()
-  timer = _native.StageTimer()
   stats["record_phases"] = True
-  ms_dev = timed(lambda: step(False), args.steps, timer)
+  ms_dev = timed(lambda: step(False), args.steps)
   stats["record_phases"] = False
+  # per entry point device times (CUDA events on the launching stream) come from a SECOND pass with the views issued one
+  # after another on one stream: with two view streams a kernel shares the SMs with the other view's kernels and its
+  # event-to-event time is not the kernel's own (the roofline wants the kernel timed alone)
+  timer = _native.StageTimer()
+  saved_streams = list(view_streams)
+  view_streams.clear()
+  stage_steps = max(2, args.steps // 2)
+  for _ in range(2):   # the current stream's allocator pool has to grow first (the view streams own the cached blocks)
+    step(False)
+  ms_single = timed(lambda: step(False), stage_steps, timer)
+  view_streams.extend(saved_streams)
   stage = timer.summary()
   # where the end of a step goes on this rank (device time, averaged over the timed steps): flushing + launching the
   # early reduction, the last view (which shares the SMs with that reduction when N > 1), the closing all_reduce()
@@ -377,14 +393,14 @@ def run_ours(args):
     ach_ips = warp_inst / (bwd_avg_ms * 1e-3)
     issue = {"warp_inst_per_launch": warp_inst, "achieved_warp_inst_per_s": ach_ips, "peak_warp_inst_per_s": peak_ips,
              "frac": ach_ips / peak_ips, "source": traffic_src}
-  stage_ms = {k: round(v[1] / args.steps / views, 4) for k, v in sorted(stage.items())}
+  stage_ms = {k: round(v[1] / stage_steps / views, 4) for k, v in sorted(stage.items())}
   launches = sum(KERNELS_PER_CALL.get(k, 0) * v[0] for k, v in stage.items())
   # two sorts per frame, each = histogram + one kernel per digit pass: the depth keys (32 bits, enqueued with
   # the count still on the device: gs_radix_sort_pairs_counted) and the tile ids (tile_bits)
   tile_bits = max(1, (int(ranges.shape[0] * ranges.shape[1]) - 1).bit_length())
   launches += stage.get("gs_radix_sort_pairs_counted", (0, 0.0))[0] * (1 + 4)
   launches += stage.get("gs_radix_sort_pairs", (0, 0.0))[0] * (1 + -(-tile_bits // 8))
-  launches = launches // max(args.steps, 1)
+  launches = launches // max(stage_steps, 1)
 
   # HBM rooflines of the bandwidth-bound stages: SURVEY.md §8(d) algorithmic bytes per launch over the live CUDA-event
   # time of the entry point (the sort figure covers both sorts of a frame: V depth keys in 4 passes, K tile ids in 2)
@@ -424,7 +440,7 @@ def run_ours(args):
     "ms_per_step": ms_dev / args.steps, "ms_per_frame": ms_dev / args.steps / views,
     "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
     "config": {"workload": workload_name(W),
-               "views_per_rank": views, "parallelism": f"view-parallel x{world}, replicated gaussians, "
+               "views_per_rank": views, "view_streams": max(args.streams, 1), "parallelism": f"view-parallel x{world}, replicated gaussians, "
                                                        "one gradient all-reduce per step"
                                                        + (" (SH slices reduced under the last view, its staged colour "
                                                           "gradients all-gathered)" if world > 1 and args.reduce_early else ""),
@@ -453,6 +469,8 @@ def run_ours(args):
                  "blend_evals_per_s": K * 256 / (bwd_avg_ms * 1e-3) if bwd_avg_ms > 0 else None,
                  "issue_roofline": issue},
     "step_tail_ms": {k: round(v, 4) for k, v in phase_ms.items()},
+    "single_stream_ms_per_frame": ms_single / stage_steps / views,
+    "stage_ms_note": "entry point times and the roofline come from a second pass with one view stream (kernels timed alone)",
     "stage_ms_per_frame": stage_ms,
     "hbm_stage_rooflines": hbm_stages,
     "clocks": clocks,
@@ -617,6 +635,8 @@ def main():
                   help="fixed batch split over the ranks (strong scaling), e.g. --workload c5 --total-views 64")
   ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration (c1..c5) timings at N = 1")
   ap.add_argument("--no-stock", action="store_true", help="skip the stock-API (no extensions) timing at N = 1")
+  ap.add_argument("--streams", type=int, default=2,
+                  help="CUDA streams the views of a step are issued on, round robin (1 = one after another)")
   ap.add_argument("--background-ctas", type=int, default=0,
                   help="N > 1 with reduce_early: CTA limit of the communicator that runs under the last view (0 = default group)")
   ap.add_argument("--no-reduce-early", dest="reduce_early", action="store_false",

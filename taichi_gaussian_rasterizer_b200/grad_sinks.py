@@ -53,6 +53,7 @@ class DeferredSH:
     self.points = None     # (N,3) positions shared by the pending views
     self.overwrite_next = False   # the sink holds nothing yet (mark_clean): the next flush writes instead of adding
     self.hold = False
+    self._last_flush = None
 
   def mark_clean(self):
     """The caller declares the sink's content void (start of a batch): pending views are dropped and the next flush
@@ -67,13 +68,19 @@ class DeferredSH:
       assert not self.hold, "positions changed while the SH sink is held by an all-reduce"
       self.flush()
     self.points = points
-    self.pending.append((staged, camera_pos))
+    # views of a batch may be issued on different CUDA streams (bench.py --streams): remember where this one was staged
+    ready = None
+    if staged.is_cuda:
+      ready = torch.cuda.Event()
+      ready.record(torch.cuda.current_stream(staged.device))
+    self.pending.append((staged, camera_pos, ready))
     if len(self.pending) >= self.MAX_VIEWS and not self.hold:
       self.flush()
 
   def take_pending(self):
     """Hand the pending views to the caller (who will flush them itself) and release the hold."""
-    pending, points = self.pending, self.points
+    self._order_after_producers()
+    pending, points = [(p[0], p[1]) for p in self.pending], self.points
     self.pending, self.points, self.hold = [], None, False
     return pending, points
 
@@ -81,15 +88,31 @@ class DeferredSH:
     if not self.pending and not self.overwrite_next:
       self.points = None
       return
+    self._order_after_producers()
     if len(self.pending) == 0:   # clean sink, nothing staged: the rows become zeros
       self.sink.zero_()
-      self.overwrite_next = False
-      return
-    flush_sh_views(self.sink, self.points, [t for t, _ in self.pending], [c for _, c in self.pending],
-                   self.overwrite_next)
+    else:
+      flush_sh_views(self.sink, self.points, [p[0] for p in self.pending], [p[1] for p in self.pending],
+                     self.overwrite_next)
+    if self.sink.is_cuda:
+      self._last_flush = torch.cuda.Event()
+      self._last_flush.record(torch.cuda.current_stream(self.sink.device))
     self.overwrite_next = False
     self.pending = []
     self.points = None
+
+  def _order_after_producers(self):
+    """The flushing stream waits for every stream a pending view was staged on and for the previous flush (two
+    flushes read-modify-write the same rows)."""
+    if not self.sink.is_cuda:
+      return
+    cur = torch.cuda.current_stream(self.sink.device)
+    for p in self.pending:
+      if p[2] is not None:
+        cur.wait_event(p[2])
+        p[0].record_stream(cur)   # staged on another stream's pool, read here: the allocator must not recycle it early
+    if self._last_flush is not None:
+      cur.wait_event(self._last_flush)
 
 
 _deferred = {}

@@ -274,3 +274,43 @@ def test_render_gaussians_equals_stagewise_composition(cuda_device, n, size, mar
   assert torch.equal(out.gaussians2d, g2d)
   assert torch.equal(out.image, ref.image)
   assert torch.equal(out.image_weight, ref.image_weight)
+
+
+def test_views_on_two_streams_accumulate_the_same_gradients(cuda_device):
+  """distributed.run_views: the views of a batch issued round robin on two CUDA streams (their gradients meet in the
+  flat bucket through atomic adds and the deferred SH flush) give the sums of the one-after-another loop."""
+  from taichi_gaussian_rasterizer_b200 import evaluate_sh_views
+  from taichi_gaussian_rasterizer_b200.distributed import GradientBucket, run_views
+  from taichi_gaussian_rasterizer_b200.torch_lib.projection import join_rt, quat_to_mat
+  g, cam = scene3d(11, 40_000, image_size=(400, 300), scale_factor=0.8, sh_degree=3)
+  cams = [cam]
+  for k in range(5):
+    q = torch.tensor([0.01 * (k + 1), -0.02 + 0.004 * k, 0.005, 1.0])
+    cams.append(cam.transformed(join_rt(quat_to_mat(q / q.norm()), torch.tensor([0.02, 0.002 * k, -0.01]))))
+  cams = [c.to(device=cuda_device) for c in cams]
+  cfg = RasterConfig()
+  targets = [torch.rand(300, 400, 3, device=cuda_device) for _ in cams]
+
+  def batch(streams):
+    gd = g.to(device=cuda_device).requires_grad_(True)
+    bucket = GradientBucket([gd.position, gd.log_scaling, gd.rotation, gd.alpha_logit, gd.feature])
+    with bucket.fused_accumulation():
+      bucket.zero_()
+      colors = evaluate_sh_views(gd.feature, gd.position, [c.camera_position for c in cams])
+
+      def one(i):
+        loss = torch.nn.functional.l1_loss(render_gaussians(gd, cams[i], cfg, use_sh=True, sh_colors=colors[i]).image,
+                                           targets[i])
+        loss.backward()
+        return loss.detach()
+      total = run_views(len(cams), one, streams)
+      bucket.all_reduce()
+    torch.cuda.synchronize()
+    return float(total), bucket.flat.clone()
+
+  loss1, flat1 = batch([])
+  loss2, flat2 = batch([torch.cuda.Stream(device=cuda_device) for _ in range(2)])
+  loss3, flat3 = batch([torch.cuda.Stream(device=cuda_device) for _ in range(3)])
+  assert abs(loss1 - loss2) < 1e-6 and abs(loss1 - loss3) < 1e-6
+  assert float(flat1.abs().sum()) > 0
+  assert rel_l2(flat2, flat1) < 1e-5 and rel_l2(flat3, flat1) < 1e-5
