@@ -186,8 +186,10 @@ def run_ours(args):
   torch.manual_seed(1234 + rank)
   # target images live on the host as a trainer holds them: 8 bit RGB (a dataset image), converted to float on the device
   host_targets = [torch.randint(0, 256, (h, w, 3), dtype=torch.uint8).pin_memory() for _ in range(views)]
-  host_proj = [c.projection.clone().pin_memory() for c in my_cameras]
-  host_pose = [c.T_camera_world.clone().pin_memory() for c in my_cameras]
+  # f32, contiguous, pinned: a copy that converts or gathers on the way goes through an unpinned temporary (and cannot
+  # be captured in a CUDA graph)
+  host_proj = [c.projection.detach().to(torch.float32).contiguous().clone().pin_memory() for c in my_cameras]
+  host_pose = [c.T_camera_world.detach().to(torch.float32).contiguous().clone().pin_memory() for c in my_cameras]
   dev_targets = [t.to(device).to(torch.float32).mul_(1.0 / 255.0) for t in host_targets]
   dev_cams = [c.to(device=device) for c in my_cameras]
   h2d_bytes = sum(t.numel() for t in host_targets) + sum(p.numel() * 4 for p in host_proj + host_pose)
@@ -198,9 +200,11 @@ def run_ours(args):
   losses_read = []
   stats = {"e2e_step": 0}
 
-  def step(from_host: bool):
+  graph_state = {"capacity": None, "totals": None, "graphs": {}, "error": None, "capturing": False}
+
+  def step(from_host: bool, static: bool = False, collective: bool = True):
     with bucket.fused_accumulation():
-      return _step(from_host)
+      return _step(from_host, static, collective)
 
   copy_stream = torch.cuda.Stream(device=device)
   staged = [dict(target=torch.empty(h, w, 3, dtype=torch.uint8, device=device), proj=torch.empty(4, device=device),
@@ -212,17 +216,24 @@ def run_ours(args):
 
   phase_events = []   # per timed device step: events around [reduce_early | last view | all_reduce]
 
-  def _step(from_host: bool):
-    phase = phase_events if (stats.get("record_phases") and world > 1) else None   # the markers join the view streams
+  def _step(from_host: bool, static: bool = False, collective: bool = True):
+    """static: every view through render_gaussians(..., overlap_capacity=) — nothing is read back, the step can be
+    captured in a CUDA graph; collective=False: stop after the flush of the deferred SH gradient (the all-reduce is
+    issued by the caller, outside the graph)."""
+    phase = phase_events if (stats.get("record_phases") and world > 1 and not static) else None   # the markers join the view streams
     compute = torch.cuda.current_stream(device)
+    capturing = graph_state["capturing"]
     if from_host:
       # this step's inputs (camera + target image of every view) go host -> device on a side stream: the (tiny) camera
       # blocks of all views first, then the target images, so the copy of view i+1's image overlaps the rendering of
       # view i; the compute stream waits on each event before using what it guards
+      if capturing:
+        copy_stream.wait_stream(compute)          # the copy stream joins the capture; replays are ordered on `compute`
       with torch.cuda.stream(copy_stream):
         for i in range(views):
           st = staged[i]
-          copy_stream.wait_event(st["free"])      # the previous step has finished reading this slot
+          if not capturing:
+            copy_stream.wait_event(st["free"])    # the previous step has finished reading this slot
           st["proj"].copy_(host_proj[i], non_blocking=True)
           st["pose"].copy_(host_pose[i], non_blocking=True)
         poses_ready.record(copy_stream)
@@ -258,22 +269,26 @@ def run_ours(args):
         target = st["target"].to(torch.float32).mul_(1.0 / 255.0)   # two small elementwise kernels, inside the timed region
       else:
         target = dev_targets[i]
-      rendering = render_gaussians(gaussians, cams[i], config, use_sh=True, sh_colors=colors[i])
+      extra = dict(overlap_capacity=graph_state["capacity"], overlap_total_out=graph_state["totals"][i]) if static else {}
+      rendering = render_gaussians(gaussians, cams[i], config, use_sh=True, sh_colors=colors[i], **extra)
       loss = torch.nn.functional.l1_loss(rendering.image, target)   # mean |image - target|, one fused ATen op each way
       loss.backward()
-      if from_host:
+      if from_host and not capturing:
         st["free"].record(torch.cuda.current_stream(device))
       stats["V"] = rendering.points_in_view.shape[0]
       return loss.detach()
 
-    need_hook = phase is not None or (world > 1 and views > 1 and args.reduce_early)
+    need_hook = (phase is not None or (world > 1 and views > 1 and args.reduce_early)) and not static
     total = run_views(views, one_view, view_streams, before_last if need_hook else None)
     if phase is not None:
       phase[-1][2].record()
-    bucket.all_reduce()
+    if collective:
+      bucket.all_reduce()
+    else:
+      bucket.flush()
     if phase is not None:
       phase[-1][3].record()
-    if from_host:
+    if from_host and not capturing:
       k = stats["e2e_step"]
       slot = k & 1
       loss_host[slot].copy_(total.reshape(1), non_blocking=True)
@@ -315,14 +330,93 @@ def run_ours(args):
       ms = float(t.item())
     return ms
 
+  # ---- the step as ONE CUDA graph (default): every view runs through render_gaussians(..., overlap_capacity=), which
+  # reads nothing back, so the ~370 launches of a step (two view streams as parallel branches, H2D copies included in
+  # the end-to-end variant) are replayed by one cudaGraphLaunch; the gradient all-reduce (N > 1) follows the replay.
+  def overlap_capacity():
+    from taichi_gaussian_rasterizer_b200 import map_to_tiles
+    from taichi_gaussian_rasterizer_b200.perspective.projection import project_to_image
+    from taichi_gaussian_rasterizer_b200.torch_lib.projection import ndc_depth
+    worst = 0
+    with torch.no_grad():
+      for c in dev_cams:
+        g2d, depths, _ = project_to_image(gaussians, c, config)
+        worst = max(worst, int(map_to_tiles(g2d, ndc_depth(depths, c.near_plane, c.far_plane), c.image_size,
+                                            config)[0].shape[0]))
+    return int(worst * 1.25) + 4096
+
+  def capture(from_host: bool):
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):   # warm-up on a side stream, as graph capture requires
+      for _ in range(2):
+        step(from_host, static=True, collective=False)
+    torch.cuda.current_stream(device).wait_stream(side)
+    torch.cuda.synchronize()
+    holder = {}
+    g = torch.cuda.CUDAGraph()
+    graph_state["capturing"] = True
+    try:
+      with torch.cuda.graph(g):
+        holder["total"] = step(from_host, static=True, collective=False)
+    finally:
+      graph_state["capturing"] = False
+    return g, holder
+
+  def graph_step(from_host: bool):
+    g, holder = graph_state["graphs"][from_host]
+    g.replay()
+    if world > 1:
+      bucket.all_reduce()   # nothing pending: one all-reduce of the flat bucket
+    if from_host:
+      k = stats["e2e_step"]
+      slot = k & 1
+      loss_host[slot].copy_(holder["total"].reshape(1), non_blocking=True)
+      loss_ready[slot].record(torch.cuda.current_stream(device))
+      if k > 0:
+        loss_ready[slot ^ 1].synchronize()
+        losses_read.append(float(loss_host[slot ^ 1].item()))
+      stats["e2e_step"] = k + 1
+    return holder["total"]
+
+  use_graph, graph_check = False, None
+  if args.graph:
+    try:
+      graph_state["capacity"] = overlap_capacity()
+      graph_state["totals"] = [torch.zeros(1, dtype=torch.int32, device=device) for _ in range(views)]
+      step(False)
+      eager_flat = bucket.flat.clone()
+      graph_state["graphs"][False] = capture(False)
+      graph_state["graphs"][True] = capture(True)
+      graph_step(False)
+      torch.cuda.synchronize()
+      # the replayed step against the eager default path (same kernels; sums differ by the order of the atomic adds)
+      graph_check = float(((bucket.flat.double() - eager_flat.double()).norm() / eager_flat.double().norm()).item())
+      del eager_flat
+      use_graph = True
+    except Exception as e:   # noqa: BLE001 - report and fall back to the eager step
+      import traceback
+      traceback.print_exc(file=sys.stderr)
+      graph_state["error"] = f"{type(e).__name__}: {e}"[:300]
+      graph_state["graphs"].clear()
+      graph_state["capturing"] = False
+      torch.cuda.synchronize()
+  run_dev = (lambda: graph_step(False)) if use_graph else (lambda: step(False))
+  run_e2e = (lambda: graph_step(True)) if use_graph else (lambda: step(True))
+
   for _ in range(args.warmup):
-    step(False)
+    run_dev()
   sampler = ClockSampler(local_rank)
   if rank == 0:
     sampler.start()
   stats["record_phases"] = True
-  ms_dev = timed(lambda: step(False), args.steps)
+  ms_dev = timed(run_dev, args.steps)
   stats["record_phases"] = False
+  ms_eager = None
+  if use_graph and world == 1:   # the same step issued eagerly (round 2a's headline), for the record
+    for _ in range(2):
+      step(False)
+    ms_eager = timed(lambda: step(False), max(2, args.steps // 2)) / max(2, args.steps // 2)
   # per entry point device times (CUDA events on the launching stream) come from a SECOND pass with the views issued one
   # after another on one stream: with two view streams a kernel shares the SMs with the other view's kernels and its
   # event-to-event time is not the kernel's own (the roofline wants the kernel timed alone)
@@ -340,8 +434,12 @@ def run_ours(args):
   phase_ms = {name: sum(e[i].elapsed_time(e[i + 1]) for e in phase_events) / max(len(phase_events), 1)
               for i, name in enumerate(("reduce_early_launch", "last_view", "all_reduce_tail"))}
   clocks = sampler.stop() if rank == 0 else None
-  step(True)
-  ms_e2e = timed(lambda: step(True), args.steps)
+  run_e2e()
+  ms_e2e = timed(run_e2e, args.steps)
+  overlap_total_max = None
+  if use_graph:
+    overlap_total_max = max(int(t.item()) for t in graph_state["totals"])
+    assert overlap_total_max <= graph_state["capacity"], "overlap capacity exceeded: the timed images dropped gaussians"
   stock_ms = None
   if world == 1 and not args.no_stock:
     saved = [p.grad for p in params]
@@ -448,6 +546,9 @@ def run_ours(args):
                "K_per_tile_max": int(counts.max()), "scale_factor": W["scale_factor"],
                "l2_policy": "inputs larger than L2 (708 MB of gaussians per view)", "gaussian_order": "morton" if args.morton else "as generated (random)",
                "emulate_stale_tail": True, "forward_exit_transmittance": 0.0,
+               "cuda_graph": use_graph, "cuda_graph_error": graph_state["error"],
+               "overlap_capacity": graph_state["capacity"] if use_graph else None, "overlap_total_max": overlap_total_max,
+               "graph_vs_eager_grad_rel_l2": graph_check,
                "sh": "colours of all views of a step evaluated in one pass over the coefficients, coefficient gradient "
                      "formed once per step" if args.batched_sh else "evaluated per view, coefficient gradient formed once per step"},
     "e2e": {"value": e2e, "unit": "gaussian*pixel/s", "ms_per_step": ms_e2e / args.steps,
@@ -470,6 +571,7 @@ def run_ours(args):
                  "issue_roofline": issue},
     "step_tail_ms": {k: round(v, 4) for k, v in phase_ms.items()},
     "single_stream_ms_per_frame": ms_single / stage_steps / views,
+    "eager_ms_per_frame": (ms_eager / views) if ms_eager is not None else None,
     "stage_ms_note": "entry point times and the roofline come from a second pass with one view stream (kernels timed alone)",
     "stage_ms_per_frame": stage_ms,
     "hbm_stage_rooflines": hbm_stages,
@@ -639,6 +741,9 @@ def main():
                   help="CUDA streams the views of a step are issued on, round robin (1 = one after another)")
   ap.add_argument("--background-ctas", type=int, default=0,
                   help="N > 1 with reduce_early: CTA limit of the communicator that runs under the last view (0 = default group)")
+  ap.add_argument("--no-graph", dest="graph", action="store_false",
+                  help="issue every step eagerly (kernel launches + two host read-backs per view) instead of replaying it "
+                       "from one CUDA graph")
   ap.add_argument("--no-reduce-early", dest="reduce_early", action="store_false",
                   help="N > 1: one all-reduce of the whole bucket after the last view (round-1 behaviour)")
   args = ap.parse_args()

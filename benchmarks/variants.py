@@ -27,12 +27,13 @@ def main():
   ap.add_argument("--variants", default="0,1")
   ap.add_argument("--scene", default="bench")
   ap.add_argument("--stats", action="store_true")
+  ap.add_argument("--no-stats", action="store_true", help="visibility / heuristics off even if the scene asks for them")
   ap.add_argument("--iters", type=int, default=10)
   ap.add_argument("--rounds", type=int, default=7)
   args = ap.parse_args()
   dev = torch.device("cuda:0")
   g, cam, spec = baseline_scene(args.scene)
-  stats = args.stats or bool(spec.get("stats"))
+  stats = (args.stats or bool(spec.get("stats"))) and not args.no_stats
   cfg = RasterConfig(compute_visibility=stats, compute_point_heuristic=stats)
   g, cam = g.to(device=dev), cam.to(device=dev)
   with torch.no_grad():

@@ -77,6 +77,15 @@ int gs_project_bwd(const GsProjectParams* p, int64_t num_visible, const void* po
                    const void* grad_points, const void* grad_depth, void* grad_position,
                    void* grad_log_scaling, void* grad_rotation, void* grad_alpha_logit,
                    void* grad_T_camera_world, void* grad_projection, void* stream);
+/* Same with the visible count still on the device: grad_points / grad_depth / indexes have `capacity` rows, the first
+ * *count_dev of them are used (the capacity-sized outputs of gs_project_fwd, handed on without reading num_visible
+ * back: the reference reads it with torch.nonzero, projection.py:146-149 — a device synchronisation per view). */
+int gs_project_bwd_counted(const GsProjectParams* p, int64_t capacity, const int32_t* count_dev, const void* position,
+                           const void* log_scaling, const void* rotation, const void* alpha_logit,
+                           const void* T_camera_world, const void* projection, const int64_t* indexes,
+                           const void* grad_points, const void* grad_depth, void* grad_position,
+                           void* grad_log_scaling, void* grad_rotation, void* grad_alpha_logit,
+                           void* grad_T_camera_world, void* grad_projection, void* stream);
 
 /* ------------------------------------------------------------------ spherical harmonics
  * replaces evaluate_sh_at_kernel and its .grad (spherical_harmonics.py:118-134, :154-161). */
@@ -129,6 +138,10 @@ int gs_sh_bwd(const GsSHParams* p, const void* params, const void* positions,
 #define GS_SH_MAX_DEFERRED_VIEWS 16
 int gs_sh_bwd_stage(const GsSHParams* p, const void* forward_out, const int64_t* indexes, const void* grad_out,
                     void* staged, void* stream);
+/* gs_sh_bwd_stage with the number of indexes still on the device (p->num_indexes = capacity of indexes / forward_out /
+ * grad_out; `staged` is always cleared first). */
+int gs_sh_bwd_stage_counted(const GsSHParams* p, const void* forward_out, const int64_t* indexes, const void* grad_out,
+                            const int32_t* count_dev, void* staged, void* stream);
 int gs_sh_bwd_flush(const GsSHParams* p, int32_t num_views, const void* const* staged,
                     const void* const* camera_positions, const void* positions, void* grad_params, void* stream);
 
@@ -227,6 +240,12 @@ int gs_find_ranges_tiles(const GsTileParams* p, int64_t num_overlaps, const uint
 int gs_tile_emit_tiles_capped(const GsTileParams* p, const float* gaussians, const int32_t* perm, const int32_t* cum,
                               const uint64_t* tile_masks, int64_t capacity, uint32_t* tile_ids, int32_t* values,
                               void* stream);
+/* ... and with the number of gaussians still on the device as well (p->num_points = capacity of perm / cum /
+ * tile_masks, as left by gs_tile_count_perm_counted + gs_full_cumsum_counted): with this, gs_project_bwd_counted and
+ * gs_sh_bwd_stage_counted a whole 3D view (render_gaussians forward + backward) runs without a host read-back. */
+int gs_tile_emit_tiles_capped_counted(const GsTileParams* p, const float* gaussians, const int32_t* perm,
+                                      const int32_t* cum, const uint64_t* tile_masks, const int32_t* count_dev,
+                                      int64_t capacity, uint32_t* tile_ids, int32_t* values, void* stream);
 int gs_find_ranges_tiles_counted(const GsTileParams* p, int64_t capacity, const int32_t* num_overlaps_dev,
                                  const uint32_t* sorted_tile_ids, int32_t* tile_ranges, void* stream);
 

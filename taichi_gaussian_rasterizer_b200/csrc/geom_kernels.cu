@@ -524,9 +524,9 @@ int gs_tile_emit_tiles(const GsTileParams* p, const float* gaussians, const int3
   return GS_OK;
 }
 
-int gs_tile_emit_tiles_capped(const GsTileParams* p, const float* gaussians, const int32_t* perm, const int32_t* cum,
-                              const uint64_t* tile_masks, int64_t capacity, uint32_t* tile_ids, int32_t* values,
-                              void* stream) {
+static int tile_emit_tiles_capped_entry(const GsTileParams* p, const float* gaussians, const int32_t* perm,
+                                        const int32_t* cum, const uint64_t* tile_masks, const int32_t* count_dev,
+                                        int64_t capacity, uint32_t* tile_ids, int32_t* values, void* stream) {
   int rc = check_tile_params(p, "gs_tile_emit_tiles_capped");
   if (rc != GS_OK) return rc;
   if (p->num_points == 0 || capacity <= 0) return GS_OK;
@@ -534,10 +534,23 @@ int gs_tile_emit_tiles_capped(const GsTileParams* p, const float* gaussians, con
   int ts = p->tile_size;
   int img_w = (int)ceil_div(p->image_width, ts) * ts, img_h = (int)ceil_div(p->image_height, ts) * ts;
   tile_query_kernel<2, uint32_t><<<(unsigned)ceil_div(p->num_points, kTileBlock), kTileBlock, 0, (cudaStream_t)stream>>>(
-      *p, img_w, img_h, gaussians, nullptr, perm, cum, nullptr, tile_ids, values, (uint2*)tile_masks, nullptr,
+      *p, img_w, img_h, gaussians, nullptr, perm, cum, nullptr, tile_ids, values, (uint2*)tile_masks, count_dev,
       (long long)capacity);
   GS_LAUNCH_CHECK();
   return GS_OK;
+}
+
+int gs_tile_emit_tiles_capped(const GsTileParams* p, const float* gaussians, const int32_t* perm, const int32_t* cum,
+                              const uint64_t* tile_masks, int64_t capacity, uint32_t* tile_ids, int32_t* values,
+                              void* stream) {
+  return tile_emit_tiles_capped_entry(p, gaussians, perm, cum, tile_masks, nullptr, capacity, tile_ids, values, stream);
+}
+
+int gs_tile_emit_tiles_capped_counted(const GsTileParams* p, const float* gaussians, const int32_t* perm,
+                                      const int32_t* cum, const uint64_t* tile_masks, const int32_t* count_dev,
+                                      int64_t capacity, uint32_t* tile_ids, int32_t* values, void* stream) {
+  GS_CHECK_ARG(count_dev != nullptr, "gs_tile_emit_tiles_capped_counted: null count");
+  return tile_emit_tiles_capped_entry(p, gaussians, perm, cum, tile_masks, count_dev, capacity, tile_ids, values, stream);
 }
 
 int gs_find_ranges_tiles_counted(const GsTileParams* p, int64_t capacity, const int32_t* num_overlaps_dev,

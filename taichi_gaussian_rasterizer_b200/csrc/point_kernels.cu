@@ -329,8 +329,10 @@ sh_bwd_dense_kernel(const __grid_constant__ GsSHParams p, const float* __restric
 template <int K>
 __global__ void __launch_bounds__(256)
 sh_bwd_stage_kernel(int64_t nv, const float* __restrict__ out_fwd, const int64_t* __restrict__ indexes,
-                    const float* __restrict__ grad_out, float* __restrict__ staged) {
+                    const float* __restrict__ grad_out, float* __restrict__ staged,
+                    const int32_t* __restrict__ count_dev = nullptr) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (count_dev) nv = min(nv, (int64_t)*count_dev);   // counted variant: nv is the capacity
   if (j >= nv) return;
   const int64_t idx = indexes[j];
 #pragma unroll
@@ -466,8 +468,9 @@ project_bwd_kernel(const __grid_constant__ GsProjectParams p, int64_t num_visibl
                    const int64_t* __restrict__ indexes, const T* __restrict__ grad_points,
                    const T* __restrict__ grad_depth, T* __restrict__ g_position, T* __restrict__ g_log_scaling,
                    T* __restrict__ g_rotation, T* __restrict__ g_alpha_logit, T* __restrict__ g_Tcw,
-                   T* __restrict__ g_proj) {
+                   T* __restrict__ g_proj, const int32_t* __restrict__ count_dev) {
   const int64_t i = (int64_t)blockIdx.x * kPBwdBlock + threadIdx.x;
+  if (count_dev) num_visible = min(num_visible, (int64_t)*count_dev);   // counted variant: the capacity was passed
   CameraConst<T> C;
 #pragma unroll
   for (int k = 0; k < 12; ++k) C.Tcw[k] = Tcw[k];
@@ -763,8 +766,8 @@ int gs_sh_bwd(const GsSHParams* p, const void* params, const void* positions, co
                                                   grad_params, grad_positions, grad_camera_pos, st);
 }
 
-int gs_sh_bwd_stage(const GsSHParams* p, const void* forward_out, const int64_t* indexes, const void* grad_out,
-                    void* staged, void* stream) {
+static int sh_bwd_stage_entry(const GsSHParams* p, const void* forward_out, const int64_t* indexes, const void* grad_out,
+                             const int32_t* count_dev, void* staged, void* stream) {
   int rc = check_sh(p, "gs_sh_bwd_stage");
   if (rc != GS_OK) return rc;
   if (p->dtype != GS_F32 || p->num_channels != 3) {
@@ -773,14 +776,25 @@ int gs_sh_bwd_stage(const GsSHParams* p, const void* forward_out, const int64_t*
   }
   GS_CHECK_ARG(staged != nullptr, "gs_sh_bwd_stage: null staging buffer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->num_indexes < p->num_points)   // culled gaussians stage zeros
+  if (count_dev != nullptr || p->num_indexes < p->num_points)   // culled gaussians stage zeros
     GS_CUDA(cudaMemsetAsync(staged, 0, (size_t)p->num_points * 3 * sizeof(float), st));
   if (p->num_indexes == 0) return GS_OK;
   GS_CHECK_ARG(forward_out && indexes && grad_out, "gs_sh_bwd_stage: null tensor");
   sh_bwd_stage_kernel<3><<<(unsigned)ceil_div(p->num_indexes, 256), 256, 0, st>>>(
-      p->num_indexes, (const float*)forward_out, indexes, (const float*)grad_out, (float*)staged);
+      p->num_indexes, (const float*)forward_out, indexes, (const float*)grad_out, (float*)staged, count_dev);
   GS_LAUNCH_CHECK();
   return GS_OK;
+}
+
+int gs_sh_bwd_stage(const GsSHParams* p, const void* forward_out, const int64_t* indexes, const void* grad_out,
+                    void* staged, void* stream) {
+  return sh_bwd_stage_entry(p, forward_out, indexes, grad_out, nullptr, staged, stream);
+}
+
+int gs_sh_bwd_stage_counted(const GsSHParams* p, const void* forward_out, const int64_t* indexes, const void* grad_out,
+                            const int32_t* count_dev, void* staged, void* stream) {
+  GS_CHECK_ARG(count_dev != nullptr, "gs_sh_bwd_stage_counted: null count");
+  return sh_bwd_stage_entry(p, forward_out, indexes, grad_out, count_dev, staged, stream);
 }
 
 int gs_sh_bwd_flush(const GsSHParams* p, int32_t num_views, const void* const* staged,
@@ -862,7 +876,8 @@ int gs_gather_rows_counted(int64_t capacity, int32_t row_floats, const void* src
   return GS_OK;
 }
 
-int gs_project_bwd(const GsProjectParams* p, int64_t num_visible, const void* position, const void* log_scaling,
+static int project_bwd_entry(const GsProjectParams* p, int64_t num_visible, const int32_t* count_dev,
+                             const void* position, const void* log_scaling,
                    const void* rotation, const void* alpha_logit, const void* T_camera_world, const void* projection,
                    const int64_t* indexes, const void* grad_points, const void* grad_depth, void* grad_position,
                    void* grad_log_scaling, void* grad_rotation, void* grad_alpha_logit, void* grad_T_camera_world,
@@ -891,12 +906,34 @@ int gs_project_bwd(const GsProjectParams* p, int64_t num_visible, const void* po
       *p, num_visible, (const TT*)position, (const TT*)log_scaling, (const TT*)rotation, (const TT*)alpha_logit,    \
       (const TT*)T_camera_world, (const TT*)projection, indexes, (const TT*)grad_points, (const TT*)grad_depth,     \
       (TT*)grad_position, (TT*)grad_log_scaling, (TT*)grad_rotation, (TT*)grad_alpha_logit,                         \
-      (TT*)grad_T_camera_world, (TT*)grad_projection)
+      (TT*)grad_T_camera_world, (TT*)grad_projection, count_dev)
   if (p->dtype == GS_F32) { if (acc) GS_PBWD_LAUNCH(float, true); else GS_PBWD_LAUNCH(float, false); }
   else { if (acc) GS_PBWD_LAUNCH(double, true); else GS_PBWD_LAUNCH(double, false); }
 #undef GS_PBWD_LAUNCH
   GS_LAUNCH_CHECK();
   return GS_OK;
+}
+
+int gs_project_bwd(const GsProjectParams* p, int64_t num_visible, const void* position, const void* log_scaling,
+                   const void* rotation, const void* alpha_logit, const void* T_camera_world, const void* projection,
+                   const int64_t* indexes, const void* grad_points, const void* grad_depth, void* grad_position,
+                   void* grad_log_scaling, void* grad_rotation, void* grad_alpha_logit, void* grad_T_camera_world,
+                   void* grad_projection, void* stream) {
+  return project_bwd_entry(p, num_visible, nullptr, position, log_scaling, rotation, alpha_logit, T_camera_world,
+                           projection, indexes, grad_points, grad_depth, grad_position, grad_log_scaling, grad_rotation,
+                           grad_alpha_logit, grad_T_camera_world, grad_projection, stream);
+}
+
+int gs_project_bwd_counted(const GsProjectParams* p, int64_t capacity, const int32_t* count_dev, const void* position,
+                           const void* log_scaling, const void* rotation, const void* alpha_logit,
+                           const void* T_camera_world, const void* projection, const int64_t* indexes,
+                           const void* grad_points, const void* grad_depth, void* grad_position,
+                           void* grad_log_scaling, void* grad_rotation, void* grad_alpha_logit,
+                           void* grad_T_camera_world, void* grad_projection, void* stream) {
+  GS_CHECK_ARG(count_dev != nullptr, "gs_project_bwd_counted: null count");
+  return project_bwd_entry(p, capacity, count_dev, position, log_scaling, rotation, alpha_logit, T_camera_world,
+                           projection, indexes, grad_points, grad_depth, grad_position, grad_log_scaling, grad_rotation,
+                           grad_alpha_logit, grad_T_camera_world, grad_projection, stream);
 }
 
 }  // extern "C"

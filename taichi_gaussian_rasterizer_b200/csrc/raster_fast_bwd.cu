@@ -48,7 +48,7 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
                        const int32_t* __restrict__ o2p, const float* __restrict__ image,
                        const float* __restrict__ grad_image, float* __restrict__ grad_pts,
                        float* __restrict__ grad_feat, float* __restrict__ heuristic,
-                       const unsigned char* __restrict__ cull_mask) {
+                       const unsigned char* __restrict__ cull_mask, const float3 kf) {
   constexpr int NSUB = 4;
   constexpr int kBwdBatch = 64;   // staged tile-list entries per buffer (32 / 128 measured slower)
   constexpr int NM = AA ? 7 : 6;  // moments: g, g u, g w, g u^2, g w^2, g u w; AA: d/d(mean, axis, sigma, alpha)
@@ -65,7 +65,11 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
   const int ox = (tile % tw) * kFastTile, oy = (tile / tw) * kFastTile + warp * (NSUB * 2);
   const int x0 = ox + (lane & 7), y0 = oy + (lane >> 3);
   const float px0 = (float)x0 + 0.5f, py0 = (float)y0 + 0.5f;
-  const float thr = (float)p.alpha_threshold, cmax = (float)p.clamp_max_alpha, sat = (float)p.saturate_threshold;
+  // {alpha_threshold, clamp_max_alpha, saturate_threshold} converted to f32 on the host: as kernel parameters they are
+  // constant-bank operands of the compares.  Converted here from the doubles of GsRasterParams, the 64-register cap of
+  // the paired variant made the compiler re-issue the F2F.F32.F64 conversions inside the walk (26 of them in the SASS,
+  // 3.4 % of the executed instructions, on the MUFU pipe).
+  const float thr = kf.x, cmax = kf.y, sat = kf.z;
 
   // which reduced value this lane commits, and where: value `own` of a single reduction; in a paired reduction values
   // 0 .. NV-1 belong to the first gaussian of the pair and NV .. 2 NV-1 to the second
@@ -349,10 +353,11 @@ static int launch_bwd_fast(const GsRasterParams& p, const RasterArgs& a, const f
   const unsigned char* cmask = (const unsigned char*)a.workspace + fast_layout(p).off_mask;
   // kernel_variant (benchmark A/B switch, 0 in production): bit 0 = reduce every survivor on its own
   const bool pair = (p.kernel_variant & 1) == 0;
+  const float3 kf = make_float3((float)p.alpha_threshold, (float)p.clamp_max_alpha, (float)p.saturate_threshold);
 #define GS_BWD_LAUNCH(HEURV, PAIRV, AAV)                                                                         \
   raster_bwd_fast_kernel<F, FP, HEURV, PAIRV, AAV><<<tiles * 2, 32, 0, st>>>(                                   \
       p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,   \
-      (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr, cmask)
+      (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr, cmask, kf)
   if (p.antialias) { if (heur) GS_BWD_LAUNCH(true, false, true); else GS_BWD_LAUNCH(false, false, true); }
   else if (heur) { if (pair) GS_BWD_LAUNCH(true, true, false); else GS_BWD_LAUNCH(true, false, false); }
   else { if (pair) GS_BWD_LAUNCH(false, true, false); else GS_BWD_LAUNCH(false, false, false); }

@@ -162,6 +162,10 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
   constexpr int U = (2 + FP / 4) | 1;
   __shared__ __align__(16) float4 s_e[2][kFwdBatch][U];
   __shared__ unsigned char s_mask[2][kFwdBatch];   // cull bytes of the staged entries (raster_cull_mask_kernel)
+  // VIS: the tile's visibility sum of every staged entry (23 bit fixed point: 256 pixels stay below 2^31), merged over the eight warps in shared
+  // memory and committed with ONE global atomic per entry and tile after the batch, as the reference's kernel does
+  // (rasterizer/forward.py:116-128) — round 1 issued one global atomic per surviving (warp, entry) pair
+  __shared__ unsigned s_vis[VIS ? 2 : 1][VIS ? kFwdBatch : 1];
 
   const int tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int tw = (p.image_width + kFastTile - 1) / kFastTile;
@@ -233,6 +237,9 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
     cp_async_commit();
   };
 
+  if constexpr (VIS) {   // ordered before the first shared atomic by the barrier of the first batch
+    if (t < 2 * kFwdBatch) (&s_vis[0][0])[t] = 0u;
+  }
   bool warp_done = __all_sync(kFull, (1.f - W) <= exit_T);
   if (nb > 0) issue_load(0);
   for (int b = 0; b < nb; ++b) {
@@ -282,20 +289,32 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
             if (FP > 4 || FOURTH) acc[4 * c4 + 3] = fmaf(f4.w, weight, acc[4 * c4 + 3]);
           }
           if constexpr (VIS) {
-            // visibility[g] += sum over the warp's pixels of the blend weight.  The weights are in [0, 1): summed as
-            // 24 bit fixed point with ONE redux.sync (integer warp reduction) instead of five float shuffles; the
-            // quantisation (2^-25 per pixel) is far below the f32 rounding of the running sums.  Stale re-reads (Q1,
-            // vbase + j >= C) do not count, as in the reference, whose write-back skips those slots.
-            const unsigned wq = (vbase + j < C) ? __float2uint_rn(weight * 16777216.f) : 0u;
-            const unsigned total_q = __reduce_add_sync(kFull, wq);
-            if (lane == 0 && total_q != 0u)
-              atomicAdd(visibility + __float_as_int(r1.w), (float)total_q * (1.f / 16777216.f));
+            // visibility[g] += sum over the tile's pixels of the blend weight.  The weights are in [0, 0.99]: summed as
+            // 23 bit fixed point with ONE redux.sync (integer warp reduction) instead of five float shuffles, then one
+            // shared-memory atomic per warp.  The fixed-point value is the mantissa of 1 + weight (one FADD rounds the
+            // weight to a multiple of 2^-23; no multiply, no float -> integer conversion on the MUFU pipe): the 32
+            // exponent fields add up to 32 * 0x3f800000 = 0xf0000000 mod 2^32, taken off after the reduction.  The
+            // quantisation (2^-24 per pixel) is far below the f32 rounding of the running sums.  Stale re-reads (Q1,
+            // vbase + j >= C: warp-uniform) do not count, as in the reference, whose write-back skips those slots.
+            const unsigned wq = __float_as_uint(1.0f + weight);
+            const unsigned total_q = (vbase + j < C) ? __reduce_add_sync(kFull, wq) - 0xf0000000u : 0u;
+            if (lane == 0 && total_q != 0u) atomicAdd(&s_vis[buf][j], total_q);
           }
         }
       }
       warp_done = __all_sync(kFull, (1.f - W) <= exit_T);
     }
     const bool all_done = __syncthreads_and(warp_done);
+    if constexpr (VIS) {
+      // the thread that staged slot t (and will stage it again two batches on) commits and clears the slot's sum
+      if (t < kFwdBatch) {
+        const unsigned q = s_vis[buf][t];
+        if (q != 0u) {
+          s_vis[buf][t] = 0u;
+          atomicAdd(visibility + __float_as_int(s_e[buf][t][1].w), (float)q * (1.f / 8388608.f));
+        }
+      }
+    }
     if (all_done) break;
   }
   cp_async_wait<0>();

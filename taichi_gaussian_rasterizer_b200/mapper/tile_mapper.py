@@ -159,11 +159,11 @@ def launch_depth_order_counted(depth_capacity, count_device, image_size, config,
 class MapperFront:
   """What launch_mapper_front_counted leaves on the device (capacity-sized buffers, valid in their first V rows) and
   the pending read-back of the overlap total."""
-  __slots__ = ("perm", "counts", "masks", "cum", "host_total", "total_ready")
+  __slots__ = ("perm", "counts", "masks", "cum", "host_total", "total_ready", "total_dev")
 
 
 def launch_mapper_front_counted(points_capacity, depth_capacity, count_device, image_size, config, use_depth16=False,
-                                ndc_range=None) -> MapperFront:
+                                ndc_range=None, read_back=True) -> MapperFront:
   """Everything of the depth-first mapping that does not need the overlap total, for a visible set whose SIZE is still
   on the device: depth keys + their sort, the overlap count in depth order, its scan, and the asynchronous copy of the
   total K into a pinned word.  render_gaussians enqueues this right behind the projection kernel: about 0.3 ms of GPU
@@ -186,11 +186,51 @@ def launch_mapper_front_counted(points_capacity, depth_capacity, count_device, i
   ws = N.workspace(lib.gs_full_cumsum_workspace_bytes(cap, 4), device)
   N.call("gs_full_cumsum_counted", ctypes.c_int64(cap), ctypes.c_int32(4), N.ptr(count_device), N.ptr(f.counts),
          N.ptr(f.cum), N.ptr(total_dev), N.ptr(ws), ctypes.c_size_t(ws.numel()), stream)
-  f.host_total = _pinned_total(device)
-  f.host_total.copy_(total_dev, non_blocking=True)
-  f.total_ready = torch.cuda.Event()
-  f.total_ready.record(torch.cuda.current_stream(device))
+  f.total_dev = total_dev
+  f.host_total = f.total_ready = None
+  if read_back:   # not for map_front_to_tiles_capped: the total never leaves the device there
+    f.host_total = _pinned_total(device)
+    f.host_total.copy_(total_dev, non_blocking=True)
+    f.total_ready = torch.cuda.Event()
+    f.total_ready.record(torch.cuda.current_stream(device))
   return f
+
+
+def map_front_to_tiles_capped(gaussians_capacity, count_device, front: MapperFront, image_size, config, capacity,
+                              total_out=None):
+  """The back half of the depth-first mapping for a visible set whose size AND overlap total both stay on the device
+  (render_gaussians(..., overlap_capacity=)): ``gaussians_capacity`` (N, 7) holds the packed gaussians in its first
+  ``count_device[0]`` rows, ``front`` is their MapperFront (launch_mapper_front_counted(..., read_back=False)).
+  Returns (overlap_to_point (capacity,), tile_ranges (TH, TW, 2)); overlaps beyond the capacity are dropped, K goes to
+  ``total_out`` (1-element int32 CUDA tensor) when given."""
+  capacity = int(capacity)
+  assert capacity >= 0
+  shape = tile_shape(image_size, config.tile_size)
+  assert shape[0] * shape[1] < MAX_TILE, \
+    f"tile dimensions {shape} for image size {image_size} exceed maximum tile count (16 bit id), try increasing tile_size"
+  with torch.no_grad():
+    device = gaussians_capacity.device
+    g = gaussians_capacity.detach()
+    assert g.dtype == torch.float32 and g.is_contiguous()
+    n = g.shape[0]
+    stream = N.stream_ptr(device)
+    p = _tile_params(n, image_size, config, False)
+    tile_ranges = torch.empty((*shape, 2), dtype=torch.int32, device=device)
+    overlap_to_point = torch.empty((capacity,), dtype=torch.int32, device=device)
+    if total_out is not None:
+      total_out.copy_(front.total_dev.reshape(total_out.shape))
+    if n == 0 or capacity == 0:
+      tile_ranges.zero_()
+      return overlap_to_point, tile_ranges
+    tile_ids = torch.empty((capacity,), dtype=torch.int32, device=device)
+    values = torch.empty((capacity,), dtype=torch.int32, device=device)
+    N.call("gs_tile_emit_tiles_capped_counted", ctypes.byref(p), N.ptr(g), N.ptr(front.perm), N.ptr(front.cum),
+           N.ptr(front.masks), N.ptr(count_device), ctypes.c_int64(capacity), N.ptr(tile_ids), N.ptr(values), stream)
+    tile_bits = max(1, (shape[0] * shape[1] - 1).bit_length())
+    tile_ids, overlap_to_point = radix_sort_pairs_counted(tile_ids, values, front.total_dev, 0, tile_bits)
+    N.call("gs_find_ranges_tiles_counted", ctypes.byref(p), ctypes.c_int64(capacity), N.ptr(front.total_dev),
+           N.ptr(tile_ids), N.ptr(tile_ranges), stream)
+    return overlap_to_point, tile_ranges
 
 
 def _map_to_tiles(gaussians, depth, image_size, config, use_depth16=False, ndc_range=None, depth_order=None,

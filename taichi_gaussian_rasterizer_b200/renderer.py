@@ -12,12 +12,14 @@ import torch
 from beartype import beartype
 
 from .data_types import Gaussians3D, RasterConfig
-from .mapper.tile_mapper import _map_to_tiles, launch_mapper_front_counted, map_to_tiles
+from .mapper.tile_mapper import (_map_to_tiles, launch_mapper_front_counted, map_front_to_tiles_capped,
+                                 map_to_tiles)
 from .perspective import CameraParams
-from .perspective.projection import project_to_image
+from .perspective.projection import project_to_image, project_to_image_static
 from .rasterizer.function import rasterize_with_tiles
 from .rendering import Rendering
-from .spherical_harmonics import evaluate_sh_at, launch_gather_into, launch_sh_forward_into
+from .spherical_harmonics import (evaluate_sh_at, launch_gather_counted, launch_gather_into, launch_sh_forward_counted,
+                                  launch_sh_forward_into)
 from .torch_lib.projection import ndc_depth
 
 
@@ -30,7 +32,9 @@ def render_gaussians(
   render_depth: bool = False,
   use_depth16: bool = False,
   render_median_depth: bool = False,
-  sh_colors: Optional[torch.Tensor] = None
+  sh_colors: Optional[torch.Tensor] = None,
+  overlap_capacity: Optional[int] = None,
+  overlap_total_out: Optional[torch.Tensor] = None
 ) -> Rendering:
   """
   A complete renderer for 3D gaussians.
@@ -45,10 +49,20 @@ def render_gaussians(
     sh_colors: (extension) with use_sh, this view's dense (N, 3) colours from ``evaluate_sh_views`` (one pass over the
       SH coefficients for the whole batch of views): the visible rows are gathered instead of evaluated; autograd
       still reaches ``gaussians.feature``
+    overlap_capacity: (extension) bound on the number of tile overlaps K.  The call then reads NOTHING back to the
+      host (the reference synchronises the device four times per view: torch.nonzero, two cudaDeviceSynchronize in
+      cuda_lib, and the size of the key buffers): the visible count V and K stay on the device, the point space
+      tensors of the result keep N rows (``points_in_view_count`` holds V), overlaps beyond the capacity are dropped
+      (pass a (1,) int32 CUDA tensor as ``overlap_total_out`` to receive K and compare it with the capacity now and
+      then).  Same kernels and the same values as the default path; forward + backward of any number of views can be
+      captured in ONE CUDA graph (bench.py).  f32 gaussians only.
 
   Returns:
     Rendering - rendered image, with optional depth / depth variance and per point statistics
   """
+  if overlap_capacity is not None:
+    return _render_gaussians_static(gaussians, camera_params, config, use_sh, render_depth, use_depth16,
+                                    render_median_depth, sh_colors, int(overlap_capacity), overlap_total_out)
   # issued before the projection so that these few tiny launches overlap with it instead of sitting behind the
   # host read-back of the visible count
   camera_position = camera_params.camera_position if use_sh else None
@@ -96,6 +110,76 @@ def render_gaussians(
                           render_depth=render_depth, use_depth16=use_depth16,
                           render_median_depth=render_median_depth, mapper_front=early.get("front"),
                           before_total_sync=fill_features)
+
+
+def _render_gaussians_static(gaussians, camera_params, config, use_sh, render_depth, use_depth16, render_median_depth,
+                             sh_colors, overlap_capacity, overlap_total_out):
+  """render_gaussians without a single host read-back (see its ``overlap_capacity``): projection with the visible
+  count left on the device, the ``*_counted`` tile mapper front, the capacity-bounded back half, the rasterizer over
+  the capacity-sized buffers (rows past the count are never referenced by a tile list)."""
+  assert gaussians.position.dtype == torch.float32, "overlap_capacity: float32 gaussians only"
+  size = camera_params.image_size
+  ndc_range = (camera_params.near_plane, camera_params.far_plane)
+  camera_position = camera_params.camera_position if use_sh else None
+  gaussians2d, depths, indexes, count = project_to_image_static(gaussians, camera_params, config)
+  front = launch_mapper_front_counted(gaussians2d.detach(), depths.detach(), count, size, config, use_depth16,
+                                      ndc_range, read_back=False)
+  if use_sh:
+    feature, position = gaussians.feature, gaussians.position
+    assert feature.is_contiguous() and position.is_contiguous() and feature.dtype == torch.float32, \
+      "overlap_capacity with use_sh: contiguous float32 SH coefficients and positions"
+    if sh_colors is not None:
+      assert sh_colors.shape == (feature.shape[0], feature.shape[1]) and sh_colors.is_contiguous()
+      pre = launch_gather_counted(sh_colors, indexes, count)
+    else:
+      pre = launch_sh_forward_counted(feature.detach(), position.detach(), indexes, count,
+                                      camera_position.detach().to(feature.dtype).contiguous())
+    features = evaluate_sh_at(feature, position.detach(), indexes, camera_position, indexes_sorted_unique=True,
+                              precomputed=pre, count=count)
+  else:
+    assert sh_colors is None
+    assert len(gaussians.feature.shape) == 2, f"Features must be (N, C) if use_sh=False, got {gaussians.feature.shape}"
+    features = _GatherCounted.apply(gaussians.feature, indexes, count)
+  if render_depth:
+    features = torch.cat([depths, depths ** 2, features], dim=1)
+  overlap_to_point, tile_ranges = map_front_to_tiles_capped(gaussians2d, count, front, size, config, overlap_capacity,
+                                                            overlap_total_out)
+  ranges = tile_ranges.view(-1, 2)
+  raster = rasterize_with_tiles(gaussians2d, features, tile_overlap_ranges=ranges, overlap_to_point=overlap_to_point,
+                                image_size=size, config=config)
+  image, depth_image, depth_var = raster.image, None, None
+  if render_depth:
+    depth_image, depth_var = compute_depth_variance(image[..., :2], raster.image_weight)
+    image = image[..., 2:]
+  return Rendering(
+    image=image, image_weight=raster.image_weight, depth=depth_image, depth_var=depth_var,
+    median_depth=(_median_depth(gaussians2d, depths, overlap_to_point, ranges, camera_params, config)
+                  if render_median_depth else None),
+    points_in_view=indexes, point_depth=depths, gaussians2d=gaussians2d,
+    point_visibility=raster.visibility if config.compute_visibility else None,
+    point_heuristic=raster.point_heuristic if config.compute_point_heuristic else None,
+    camera=camera_params, config=config, points_in_view_count=count)
+
+
+class _GatherCounted(torch.autograd.Function):
+  """features[indexes[:count]] into a capacity-sized buffer (rows past the count: zeros), count on the device; the
+  backward scatters the first count gradient rows back (indexes are unique).  Plain torch indexing with a
+  device-side row limit: the rows past the count are masked instead of sliced off."""
+
+  @staticmethod
+  def forward(ctx, features, indexes, count):
+    valid = torch.arange(indexes.shape[0], device=indexes.device) < count
+    safe = torch.where(valid, indexes, torch.zeros_like(indexes))
+    ctx.save_for_backward(safe, valid)
+    ctx.rows = features.shape[0]
+    return features[safe] * valid.unsqueeze(1).to(features.dtype)
+
+  @staticmethod
+  def backward(ctx, grad):
+    safe, valid = ctx.saved_tensors
+    out = grad.new_zeros((ctx.rows, grad.shape[1]))
+    out.index_add_(0, safe, grad * valid.unsqueeze(1).to(grad.dtype))
+    return out, None, None
 
 
 def compute_depth_variance(depth_depthsq, weight, eps=1e-6):

@@ -41,6 +41,9 @@ class Rendering:
   gaussians2d: torch.Tensor                        # (V, 7) mean, axis, sigma, alpha
   point_visibility: Optional[torch.Tensor] = None  # (V,) summed blend weight
   point_heuristic: Optional[torch.Tensor] = None   # (V, 2) prune cost, split score
+  # (extension) render_gaussians(..., overlap_capacity=): the point space tensors keep N rows, the first
+  # points_in_view_count[0] of them valid — V stays on the device ((1,) int32) so that nothing synchronises
+  points_in_view_count: Optional[torch.Tensor] = None
 
   camera: CameraParams
   config: RasterConfig

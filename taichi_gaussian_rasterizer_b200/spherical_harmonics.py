@@ -27,10 +27,14 @@ def check_sh_degree(sh_features):
 class _SHFunction(torch.autograd.Function):
 
   @staticmethod
-  def forward(ctx, params, points, indexes, camera_pos, sorted_unique=False, precomputed=None):
+  def forward(ctx, params, points, indexes, camera_pos, sorted_unique=False, precomputed=None, count=None):
     m, k, d = params.shape
     v = indexes.shape[0]
     p = N.GsSHParams(N.dtype_code(params.dtype), k, d, int(bool(sorted_unique)), m, v, 0, 0)
+    ctx.count = count   # (1,) int32 on the device: only the first count[0] rows of indexes / out are valid
+    if count is not None:
+      assert precomputed is not None and sorted_unique and params.dtype == torch.float32 and k == 3 and d in (4, 16), \
+        "counted SH evaluation: precomputed f32 colours of the ascending visible set, 3 channels, degree 1 or 3"
     if precomputed is not None:     # evaluated ahead of time on the capacity buffers (launch_sh_forward_counted)
       assert precomputed.shape == (v, k)
       out = precomputed
@@ -56,6 +60,26 @@ class _SHFunction(torch.autograd.Function):
     from_out = int(dense and need[0] and not need[1] and not need[3])
     coeffs = out if from_out else params
     deferred = deferred_sh(params) if (sink is not None and dense and from_out) else None
+    if ctx.count is not None:
+      # the visible count never reached the host (render_gaussians(..., overlap_capacity=)): the masked colour gradient
+      # is staged for the first count rows (gs_sh_bwd_stage_counted) and either joins the batch's deferred flush, or is
+      # turned into coefficient rows right here by a one-view flush (added to the sink, or a fresh dense gradient)
+      assert need[0] and not need[1] and not need[3], "counted SH backward: coefficient gradient only"
+      staged = torch.empty((params.shape[0], params.shape[1]), dtype=params.dtype, device=params.device)
+      p = N.GsSHParams(ctx.p.dtype, ctx.p.num_channels, ctx.p.num_coeffs, 1, ctx.p.num_points, ctx.p.num_indexes, 1, 1)
+      N.call("gs_sh_bwd_stage_counted", ctypes.byref(p), N.ptr(out), N.ptr(indexes), N.ptr(doutput.contiguous()),
+             N.ptr(ctx.count), N.ptr(staged), N.stream_ptr(params.device))
+      cam = camera_pos.detach().contiguous()
+      if deferred is not None:
+        deferred.add(staged, cam, points.detach())
+        return None, None, None, None, None, None, None
+      from .grad_sinks import flush_sh_views
+      if sink is not None:
+        flush_sh_views(sink, points.detach(), [staged], [cam], overwrite=False)
+        return None, None, None, None, None, None, None
+      g_params = torch.empty_like(params)
+      flush_sh_views(g_params, points.detach(), [staged], [cam], overwrite=True)
+      return g_params, None, None, None, None, None, None
     if deferred is not None:
       # deferred accumulation (grad_sinks.DeferredSH): this view only stages its masked colour gradient, the batch's
       # flush forms the coefficient rows once
@@ -64,7 +88,7 @@ class _SHFunction(torch.autograd.Function):
       N.call("gs_sh_bwd_stage", ctypes.byref(p), N.ptr(out), N.ptr(indexes), N.ptr(doutput.contiguous()), N.ptr(staged),
              N.stream_ptr(params.device))
       deferred.add(staged, camera_pos.detach().contiguous(), points.detach())
-      return None, None, None, None, None, None
+      return None, None, None, None, None, None, None
     if sink is not None and dense:
       # fused accumulation: the kernel adds into the sink, autograd gets no gradient for `params`
       p = N.GsSHParams(ctx.p.dtype, ctx.p.num_channels, ctx.p.num_coeffs, 1, ctx.p.num_points, ctx.p.num_indexes, 1,
@@ -73,7 +97,7 @@ class _SHFunction(torch.autograd.Function):
       g_cam = torch.empty_like(camera_pos) if need[3] else None
       N.call("gs_sh_bwd", ctypes.byref(p), N.ptr(coeffs), N.ptr(points), N.ptr(indexes), N.ptr(camera_pos),
              N.ptr(doutput.contiguous()), N.ptr(sink), N.ptr(g_points), N.ptr(g_cam), N.stream_ptr(params.device))
-      return None, g_points, None, g_cam, None, None
+      return None, g_points, None, g_cam, None, None, None
     g_params = torch.empty_like(params) if need[0] else None
     g_points = torch.empty_like(points) if need[1] else None
     g_cam = torch.empty_like(camera_pos) if need[3] else None
@@ -82,7 +106,7 @@ class _SHFunction(torch.autograd.Function):
     N.call("gs_sh_bwd", ctypes.byref(p), N.ptr(coeffs), N.ptr(points), N.ptr(indexes),
                               N.ptr(camera_pos), N.ptr(doutput.contiguous()), N.ptr(g_params), N.ptr(g_points),
                               N.ptr(g_cam), N.stream_ptr(params.device))
-    return g_params, g_points, None, g_cam, None, None
+    return g_params, g_points, None, g_cam, None, None, None
 
 
 def launch_sh_forward_counted(sh_params, positions, indexes_capacity, count_device, camera_pos) -> torch.Tensor:
@@ -156,16 +180,19 @@ def evaluate_sh_at(sh_params: torch.Tensor,   # M, K, (degree + 1)^2  (usually K
                    indexes: torch.Tensor,     # V   (int64 indexes into the M gaussians)
                    camera_pos: torch.Tensor,  # 3
                    indexes_sorted_unique: bool = False,
-                   precomputed: Optional[torch.Tensor] = None
+                   precomputed: Optional[torch.Tensor] = None,
+                   count: Optional[torch.Tensor] = None
                    ) -> torch.Tensor:         # V, K
   """``indexes_sorted_unique`` (extension, not in the reference signature): promise that ``indexes`` is strictly
   ascending, as the visible set returned by project_to_image is; the backward then writes dense gradient rows
   without atomics or a memset (csrc/point_kernels.cu sh_bwd_dense_kernel).  Results are identical.
   ``precomputed``: the forward values already evaluated by launch_sh_forward_counted for exactly these inputs; the
-  call then only builds the autograd node."""
+  call then only builds the autograd node.  ``count`` (with ``precomputed``): a (1,) int32 CUDA tensor — ``indexes`` and
+  ``precomputed`` are capacity-sized and only their first ``count[0]`` rows are valid (project_to_image_static); the
+  backward then reads the count on the device as well."""
   check_sh_degree(sh_params)
   N.require_cuda(sh_params, positions, indexes, camera_pos)
   dtype = sh_params.dtype
   return _SHFunction.apply(sh_params.contiguous(), positions.to(dtype).contiguous(),
                            indexes.to(torch.int64).contiguous(), camera_pos.to(dtype).contiguous(),
-                           indexes_sorted_unique, precomputed)
+                           indexes_sorted_unique, precomputed, count)
