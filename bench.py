@@ -176,7 +176,11 @@ def run_ours(args):
     gaussians = gaussians.apply(lambda t: t[order].contiguous(), batch_size=gaussians.batch_size)
   gaussians.requires_grad_(True)
   params = [gaussians.position, gaussians.log_scaling, gaussians.rotation, gaussians.alpha_logit, gaussians.feature]
-  bucket = GradientBucket(params)
+  # N > 1: the bucket lives in symmetric memory with an NVSwitch multicast mapping and is summed by our own kernel
+  # (csrc/multimem_reduce.cu) on the step's streams, inside the step's CUDA graph; --nccl-bucket = ncclAllReduce
+  # Measured (gpurun_out/s8_*): 8 GPUs 21.22 ms per step against 21.37 with NCCL; 2 GPUs 21.30 against 20.59 — through
+  # the switch (1 + 1/N) x the bucket crosses each link, a two-GPU exchange moves 1 x: used from four ranks up.
+  bucket = GradientBucket(params, symmetric=(world >= 4 and args.symmetric))
   if world > 1 and args.reduce_early and args.background_ctas > 0:
     from taichi_gaussian_rasterizer_b200.distributed import make_background_group
     bucket.background_group = make_background_group(args.background_ctas)
@@ -212,7 +216,14 @@ def run_ours(args):
             for _ in range(views)]
 
   poses_ready = torch.cuda.Event()
-  view_streams = [torch.cuda.Stream(device=device) for _ in range(args.streams)] if args.streams > 1 else []
+  # high-priority view streams: the library launches the two big rasterizer kernels at the LOWEST priority whatever the
+  # stream's (csrc/common.cuh launch_background), so every other kernel of a view gets SM room first and runs under the
+  # other views' rasterizers
+  view_streams = ([torch.cuda.Stream(device=device, priority=args.stream_priority) for _ in range(args.streams)]
+                  if args.streams > 1 else [])
+  if args.kernel_variant:
+    from taichi_gaussian_rasterizer_b200 import set_raster_options
+    set_raster_options(kernel_variant=args.kernel_variant)
 
   phase_events = []   # per timed device step: events around [reduce_early | last view | all_reduce]
 
@@ -278,7 +289,8 @@ def run_ours(args):
       stats["V"] = rendering.points_in_view.shape[0]
       return loss.detach()
 
-    need_hook = (phase is not None or (world > 1 and views > 1 and args.reduce_early)) and not static
+    need_hook = (phase is not None or (world > 1 and views > 1 and args.reduce_early)) and \
+      (not static or bucket.reducer is not None)
     total = run_views(views, one_view, view_streams, before_last if need_hook else None)
     if phase is not None:
       phase[-1][2].record()
@@ -350,7 +362,7 @@ def run_ours(args):
     side.wait_stream(torch.cuda.current_stream(device))
     with torch.cuda.stream(side):   # warm-up on a side stream, as graph capture requires
       for _ in range(2):
-        step(from_host, static=True, collective=False)
+        step(from_host, static=True, collective=in_graph_collective)
     torch.cuda.current_stream(device).wait_stream(side)
     torch.cuda.synchronize()
     holder = {}
@@ -358,7 +370,7 @@ def run_ours(args):
     graph_state["capturing"] = True
     try:
       with torch.cuda.graph(g):
-        holder["total"] = step(from_host, static=True, collective=False)
+        holder["total"] = step(from_host, static=True, collective=in_graph_collective)
     finally:
       graph_state["capturing"] = False
     return g, holder
@@ -366,7 +378,7 @@ def run_ours(args):
   def graph_step(from_host: bool):
     g, holder = graph_state["graphs"][from_host]
     g.replay()
-    if world > 1:
+    if world > 1 and not in_graph_collective:
       bucket.all_reduce()   # nothing pending: one all-reduce of the flat bucket
     if from_host:
       k = stats["e2e_step"]
@@ -379,6 +391,8 @@ def run_ours(args):
       stats["e2e_step"] = k + 1
     return holder["total"]
 
+  # our multimem reduction is a kernel on the step's streams: it is captured with the step; NCCL's follows the replay
+  in_graph_collective = bucket.reducer is not None
   use_graph, graph_check = False, None
   if args.graph:
     try:
@@ -538,7 +552,7 @@ def run_ours(args):
     "ms_per_step": ms_dev / args.steps, "ms_per_frame": ms_dev / args.steps / views,
     "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
     "config": {"workload": workload_name(W),
-               "views_per_rank": views, "view_streams": max(args.streams, 1), "parallelism": f"view-parallel x{world}, replicated gaussians, "
+               "views_per_rank": views, "view_streams": max(args.streams, 1), "view_stream_priority": args.stream_priority, "parallelism": f"view-parallel x{world}, replicated gaussians, "
                                                        "one gradient all-reduce per step"
                                                        + (" (SH slices reduced under the last view, its staged colour "
                                                           "gradients all-gathered)" if world > 1 and args.reduce_early else ""),
@@ -547,6 +561,9 @@ def run_ours(args):
                "l2_policy": "inputs larger than L2 (708 MB of gaussians per view)", "gaussian_order": "morton" if args.morton else "as generated (random)",
                "emulate_stale_tail": True, "forward_exit_transmittance": 0.0,
                "cuda_graph": use_graph, "cuda_graph_error": graph_state["error"],
+               "gradient_sum": ("in-switch reduction through a multicast mapping of the bucket (gs_multimem_all_reduce), "
+                                "inside the step's graph" if bucket.reducer is not None else
+                                ("ncclAllReduce" if world > 1 else None)),
                "overlap_capacity": graph_state["capacity"] if use_graph else None, "overlap_total_max": overlap_total_max,
                "graph_vs_eager_grad_rel_l2": graph_check,
                "sh": "colours of all views of a step evaluated in one pass over the coefficients, coefficient gradient "
@@ -741,11 +758,20 @@ def main():
                   help="CUDA streams the views of a step are issued on, round robin (1 = one after another)")
   ap.add_argument("--background-ctas", type=int, default=0,
                   help="N > 1 with reduce_early: CTA limit of the communicator that runs under the last view (0 = default group)")
+  ap.add_argument("--stream-priority", type=int, default=-1,
+                  help="CUDA priority of the view streams (-1 = high: the rasterizer kernels still launch at the lowest)")
+  ap.add_argument("--kernel-variant", type=int, default=0, help="set_raster_options(kernel_variant=): A/B switches")
+  ap.add_argument("--nccl-bucket", dest="symmetric", action="store_false",
+                  help="N > 1: sum the gradient bucket with ncclAllReduce instead of the multimem kernel")
   ap.add_argument("--no-graph", dest="graph", action="store_false",
                   help="issue every step eagerly (kernel launches + two host read-backs per view) instead of replaying it "
                        "from one CUDA graph")
+  ap.add_argument("--reduce-early", dest="reduce_early", action="store_true",
+                  help="N > 1: reduce the SH slices of the bucket under the last view (measured: the reduction's traffic "
+                       "slows that view's rasterizer by what it hides, 21.42 vs 21.22 ms per step on 8 GPUs)")
   ap.add_argument("--no-reduce-early", dest="reduce_early", action="store_false",
-                  help="N > 1: one all-reduce of the whole bucket after the last view (round-1 behaviour)")
+                  help="N > 1: one all-reduce of the whole bucket after the last view (the default)")
+  ap.set_defaults(reduce_early=False)
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)

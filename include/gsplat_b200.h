@@ -352,6 +352,24 @@ int gs_morton_codes(int64_t n, const float* points, const float* lower, const fl
  * workspace, nothing read back.  dtype GS_F32 / GS_F64. */
 int gs_camera_position(int32_t dtype, const void* T_camera_world, void* position, void* stream);
 
+/* ------------------------------------------------------------------ multi-GPU: the step's gradient sum
+ * The reference is single process (no collective call site); the view-parallel step of this package sums one flat f32
+ * bucket over the ranks once per step (distributed.GradientBucket.all_reduce).  gs_multimem_all_reduce does that in
+ * place through an NVSwitch MULTICAST mapping of the bucket (multicast_ptr: the address that stands for the same
+ * offset on every GPU; the caller sets the mapping up — torch.distributed._symmetric_memory in this package): rank r
+ * fetches the switch-reduced r-th slice with multimem.ld_reduce and writes it to all replicas with multimem.st.
+ * flags_dev: DEVICE array of `world` pointers, entry q = rank q's flag words in peer-accessible memory,
+ * gs_multimem_all_reduce_flag_words(world, num_blocks, num_channels) zero-initialised uint32 each; every rank must
+ * launch with the same num_blocks (all of them resident: <= SMs of the device) and channel; reductions that can be in
+ * flight at the same time use different channels.  Enqueued on `stream`; captured by CUDA graphs.
+ * gs_cross_rank_barrier: the ranks meet on the stream (one CTA; the barrier of channel `channel` must not be shared
+ * with a reduction in flight) — what every rank enqueued before it is complete and visible to its peers afterwards. */
+int gs_multimem_all_reduce_flag_words(int32_t world, int32_t num_blocks, int32_t num_channels);
+int gs_multimem_all_reduce(float* multicast_ptr, int64_t num_floats, int32_t rank, int32_t world,
+                           uint32_t* const* flags_dev, int32_t num_blocks, int32_t channel, void* stream);
+int gs_cross_rank_barrier(int32_t rank, int32_t world, uint32_t* const* flags_dev, int32_t num_blocks, int32_t channel,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

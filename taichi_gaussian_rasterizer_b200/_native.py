@@ -25,6 +25,7 @@ EXPORTS = [
   "gs_raster_workspace_bytes", "gs_raster_fwd", "gs_raster_bwd",
   "gs_opt_update_visibility", "gs_opt_accumulate_weight", "gs_opt_step",
   "gs_morton_codes", "gs_camera_position",
+  "gs_multimem_all_reduce_flag_words", "gs_multimem_all_reduce", "gs_cross_rank_barrier",
 ]
 
 

@@ -354,10 +354,21 @@ static int launch_bwd_fast(const GsRasterParams& p, const RasterArgs& a, const f
   // kernel_variant (benchmark A/B switch, 0 in production): bit 0 = reduce every survivor on its own
   const bool pair = (p.kernel_variant & 1) == 0;
   const float3 kf = make_float3((float)p.alpha_threshold, (float)p.clamp_max_alpha, (float)p.saturate_threshold);
+  // kernel_variant bit 2 (A/B): launch at the stream's own priority instead of the lowest one (launch_background)
+  const bool background = (p.kernel_variant & 4) == 0;
 #define GS_BWD_LAUNCH(HEURV, PAIRV, AAV)                                                                         \
-  raster_bwd_fast_kernel<F, FP, HEURV, PAIRV, AAV><<<tiles * 2, 32, 0, st>>>(                                   \
-      p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,   \
-      (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr, cmask, kf)
+  do {                                                                                                           \
+    if (background)                                                                                              \
+      GS_CUDA(launch_background(raster_bwd_fast_kernel<F, FP, HEURV, PAIRV, AAV>, dim3(tiles * 2), dim3(32), 0,  \
+                                st, p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in,  \
+                                (const float*)a.grad_image, (float*)a.grad_gaussians, (float*)a.grad_features,   \
+                                heur ? (float*)a.point_heuristic : nullptr, cmask, kf));                         \
+    else                                                                                                         \
+      raster_bwd_fast_kernel<F, FP, HEURV, PAIRV, AAV><<<tiles * 2, 32, 0, st>>>(                                \
+          p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,\
+          (float*)a.grad_gaussians, (float*)a.grad_features, heur ? (float*)a.point_heuristic : nullptr, cmask,  \
+          kf);                                                                                                   \
+  } while (0)
   if (p.antialias) { if (heur) GS_BWD_LAUNCH(true, false, true); else GS_BWD_LAUNCH(false, false, true); }
   else if (heur) { if (pair) GS_BWD_LAUNCH(true, true, false); else GS_BWD_LAUNCH(true, false, false); }
   else { if (pair) GS_BWD_LAUNCH(false, true, false); else GS_BWD_LAUNCH(false, false, false); }

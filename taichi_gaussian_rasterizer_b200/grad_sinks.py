@@ -53,7 +53,15 @@ class DeferredSH:
     self.points = None     # (N,3) positions shared by the pending views
     self.overwrite_next = False   # the sink holds nothing yet (mark_clean): the next flush writes instead of adding
     self.hold = False
+    self.staging = None    # while held: where the next view stages its colour gradient (peer readable memory)
+    self.last_points = None
     self._last_flush = None
+
+  def staging_buffer(self):
+    """The buffer the next view should stage into, if the holder asked for a particular one (first held view only)."""
+    if self.hold and self.staging is not None and not self.pending:
+      return self.staging
+    return None
 
   def mark_clean(self):
     """The caller declares the sink's content void (start of a batch): pending views are dropped and the next flush
@@ -62,12 +70,14 @@ class DeferredSH:
     self.points = None
     self.overwrite_next = True
     self.hold = False
+    self.staging = None
 
   def add(self, staged: torch.Tensor, camera_pos: torch.Tensor, points: torch.Tensor):
     if self.points is not None and (self.points.data_ptr() != points.data_ptr() or self.points.shape != points.shape):
       assert not self.hold, "positions changed while the SH sink is held by an all-reduce"
       self.flush()
     self.points = points
+    self.last_points = points
     # views of a batch may be issued on different CUDA streams (bench.py --streams): remember where this one was staged
     ready = None
     if staged.is_cuda:

@@ -65,7 +65,9 @@ class _SHFunction(torch.autograd.Function):
       # is staged for the first count rows (gs_sh_bwd_stage_counted) and either joins the batch's deferred flush, or is
       # turned into coefficient rows right here by a one-view flush (added to the sink, or a fresh dense gradient)
       assert need[0] and not need[1] and not need[3], "counted SH backward: coefficient gradient only"
-      staged = torch.empty((params.shape[0], params.shape[1]), dtype=params.dtype, device=params.device)
+      staged = deferred.staging_buffer() if deferred is not None else None
+      if staged is None:
+        staged = torch.empty((params.shape[0], params.shape[1]), dtype=params.dtype, device=params.device)
       p = N.GsSHParams(ctx.p.dtype, ctx.p.num_channels, ctx.p.num_coeffs, 1, ctx.p.num_points, ctx.p.num_indexes, 1, 1)
       N.call("gs_sh_bwd_stage_counted", ctypes.byref(p), N.ptr(out), N.ptr(indexes), N.ptr(doutput.contiguous()),
              N.ptr(ctx.count), N.ptr(staged), N.stream_ptr(params.device))
@@ -83,7 +85,9 @@ class _SHFunction(torch.autograd.Function):
     if deferred is not None:
       # deferred accumulation (grad_sinks.DeferredSH): this view only stages its masked colour gradient, the batch's
       # flush forms the coefficient rows once
-      staged = torch.empty((params.shape[0], params.shape[1]), dtype=params.dtype, device=params.device)
+      staged = deferred.staging_buffer()
+      if staged is None:
+        staged = torch.empty((params.shape[0], params.shape[1]), dtype=params.dtype, device=params.device)
       p = N.GsSHParams(ctx.p.dtype, ctx.p.num_channels, ctx.p.num_coeffs, 1, ctx.p.num_points, ctx.p.num_indexes, 1, 1)
       N.call("gs_sh_bwd_stage", ctypes.byref(p), N.ptr(out), N.ptr(indexes), N.ptr(doutput.contiguous()), N.ptr(staged),
              N.stream_ptr(params.device))

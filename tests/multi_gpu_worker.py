@@ -39,10 +39,12 @@ def main():
   cams = [c.to(device=dev) for c in cams]
   cfg = RasterConfig()
 
-  def grads(view_ids, fused, early=False):
+  def grads(view_ids, fused, early=False, symmetric=False):
     g = g_cpu.to(device=dev)
     g.requires_grad_(True)
-    bucket = GradientBucket([g.position, g.log_scaling, g.rotation, g.alpha_logit, g.feature])
+    bucket = GradientBucket([g.position, g.log_scaling, g.rotation, g.alpha_logit, g.feature], symmetric=symmetric)
+    if symmetric and bucket.reducer is None:
+      return None   # no multicast mapping on this box
     if fused:
       with bucket.fused_accumulation():
         bucket.zero_()
@@ -59,7 +61,14 @@ def main():
     return bucket.flat.clone()
 
   mine = partition_views(views, rank, world)
-  reduced = {"all-reduce at the end": grads(mine, fused=True), "reduce_early + gather": grads(mine, fused=True, early=True)}
+  reduced = {"all-reduce at the end": grads(mine, fused=True), "reduce_early + gather": grads(mine, fused=True, early=True),
+             # the bucket in symmetric memory, summed inside the NVSwitch by gs_multimem_all_reduce; with reduce_early the
+             # last view's staged colour gradients are read from the peers' memory by the flush kernel itself
+             "multimem all-reduce at the end": grads(mine, fused=True, symmetric=True),
+             "multimem reduce_early + peer flush": grads(mine, fused=True, early=True, symmetric=True)}
+  reduced = {k: v for k, v in reduced.items() if v is not None}
+  if rank == 0:
+    print(f"world {world}: variants {sorted(reduced)}")
   ok = True
   if rank == 0:
     ref = grads(list(range(views)), fused=False)
