@@ -198,6 +198,7 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
     } else {
       const float a1x = r0.z, a1y = r0.w, a2x = r1.x, a2y = r1.y, l2a = r1.z;
       float M0 = 0.f, Mu = 0.f, Mw = 0.f, Muu = 0.f, Mww = 0.f, Muw = 0.f;
+      const float a0h = HEUR ? fast_ex2(l2a) : 0.f;   // alpha0, once per gaussian (was one MUFU per hit)
 #pragma unroll
       for (int i = 0; i < NSUB; ++i) {
         if ((bm[i] >> jl) & 1u) {  // warp-uniform: this sub-block can be reached at all
@@ -223,9 +224,9 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
             M0 += gp; Mu += gu; Mw += gw;
             Muu = fmaf(gu, tx, Muu); Mww = fmaf(gw, ty, Mww); Muw = fmaf(gu, ty, Muw);
             if (HEUR) {
-              const float aag = fast_ex2(l2a) * ag;
-              h0 = fmaf(aag, aag, h0);   // |d/dmean| of this pixel: g (tx a1 + ty a2) / k^2
-              h1 += (fabsf(fmaf(gu, a1x, gw * a2x)) + fabsf(fmaf(gu, a1y, gw * a2y))) * (1.f / kHalfLog2e);
+              const float aag = a0h * ag;
+              h0 = fmaf(aag, aag, h0);   // |d/dmean| of this pixel: g (tx a1 + ty a2) / k^2 (the 1 / k^2 once, below)
+              h1 += fabsf(fmaf(gu, a1x, gw * a2x)) + fabsf(fmaf(gu, a1y, gw * a2y));
             }
           }
         }
@@ -234,7 +235,7 @@ raster_bwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
     }
 #pragma unroll
     for (int c = 0; c < F; ++c) v[NM + c] = gf[c];
-    if (HEUR) { v[NM + F] = h0; v[NM + F + 1] = h1; }
+    if (HEUR) { v[NM + F] = h0; v[NM + F + 1] = AA ? h1 : h1 * (1.f / kHalfLog2e); }
     return (unsigned)__float_as_int(r1.w);
   };
 

@@ -162,10 +162,11 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
   constexpr int U = (2 + FP / 4) | 1;
   __shared__ __align__(16) float4 s_e[2][kFwdBatch][U];
   __shared__ unsigned char s_mask[2][kFwdBatch];   // cull bytes of the staged entries (raster_cull_mask_kernel)
-  // VIS: the tile's visibility sum of every staged entry (23 bit fixed point: 256 pixels stay below 2^31), merged over the eight warps in shared
-  // memory and committed with ONE global atomic per entry and tile after the batch, as the reference's kernel does
-  // (rasterizer/forward.py:116-128) — round 1 issued one global atomic per surviving (warp, entry) pair
-  __shared__ unsigned s_vis[VIS ? 2 : 1][VIS ? kFwdBatch : 1];
+  // VIS: the visibility sums of every staged entry, one word per warp (23 bit fixed point: 32 pixels stay below 2^28),
+  // merged over the eight warps after the batch and committed with ONE global atomic per entry and tile, as the
+  // reference's kernel does (rasterizer/forward.py:116-128) — round 1 issued one global atomic per surviving (warp,
+  // entry) pair.  Plain stores, no shared-memory atomics: the merging thread clears the words it has read.
+  __shared__ __align__(16) unsigned s_vis[VIS ? 2 : 1][VIS ? kFwdBatch : 1][8];
 
   const int tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int tw = (p.image_width + kFastTile - 1) / kFastTile;
@@ -238,7 +239,7 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
   };
 
   if constexpr (VIS) {   // ordered before the first shared atomic by the barrier of the first batch
-    if (t < 2 * kFwdBatch) (&s_vis[0][0])[t] = 0u;
+    for (int q = t; q < 2 * kFwdBatch * 8; q += kFwdThreads) (&s_vis[0][0][0])[q] = 0u;
   }
   bool warp_done = __all_sync(kFull, (1.f - W) <= exit_T);
   if (nb > 0) issue_load(0);
@@ -296,9 +297,11 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
             // exponent fields add up to 32 * 0x3f800000 = 0xf0000000 mod 2^32, taken off after the reduction.  The
             // quantisation (2^-24 per pixel) is far below the f32 rounding of the running sums.  Stale re-reads (Q1,
             // vbase + j >= C: warp-uniform) do not count, as in the reference, whose write-back skips those slots.
-            const unsigned wq = __float_as_uint(1.0f + weight);
-            const unsigned total_q = (vbase + j < C) ? __reduce_add_sync(kFull, wq) - 0xf0000000u : 0u;
-            if (lane == 0 && total_q != 0u) atomicAdd(&s_vis[buf][j], total_q);
+            // One predicated store of the warp's sum into the warp's own word: an atomic on a warp-uniform shared address
+            // makes ptxas emit its warp-aggregation sequence (vote, leader election, popc, multiply: 9 more instructions
+            // per survivor) although a single lane enters.
+            const unsigned total_q = __reduce_add_sync(kFull, __float_as_uint(1.0f + weight)) - 0xf0000000u;
+            if (lane == 0 && vbase + j < C) s_vis[buf][j][warp] = total_q;
           }
         }
       }
@@ -308,9 +311,12 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
     if constexpr (VIS) {
       // the thread that staged slot t (and will stage it again two batches on) commits and clears the slot's sum
       if (t < kFwdBatch) {
-        const unsigned q = s_vis[buf][t];
+        uint4* w4 = reinterpret_cast<uint4*>(&s_vis[buf][t][0]);
+        const uint4 a = w4[0], b = w4[1];
+        const unsigned q = (a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w);
         if (q != 0u) {
-          s_vis[buf][t] = 0u;
+          w4[0] = make_uint4(0u, 0u, 0u, 0u);
+          w4[1] = make_uint4(0u, 0u, 0u, 0u);
           atomicAdd(visibility + __float_as_int(s_e[buf][t][1].w), (float)q * (1.f / 8388608.f));
         }
       }
