@@ -274,14 +274,14 @@ def run_ours(args):
         phase[-1][1].record()
 
     def one_view(i):
-      if from_host:
+      extra = dict(overlap_capacity=graph_state["capacity"], overlap_total_out=graph_state["totals"][i]) if static else {}
+      rendering = render_gaussians(gaussians, cams[i], config, use_sh=True, sh_colors=colors[i], **extra)
+      if from_host:   # the target image is only needed by the loss: its copy runs under the view's forward pass
         st = staged[i]
         torch.cuda.current_stream(device).wait_event(st["ready"])
         target = st["target"].to(torch.float32).mul_(1.0 / 255.0)   # two small elementwise kernels, inside the timed region
       else:
         target = dev_targets[i]
-      extra = dict(overlap_capacity=graph_state["capacity"], overlap_total_out=graph_state["totals"][i]) if static else {}
-      rendering = render_gaussians(gaussians, cams[i], config, use_sh=True, sh_colors=colors[i], **extra)
       loss = torch.nn.functional.l1_loss(rendering.image, target)   # mean |image - target|, one fused ATen op each way
       loss.backward()
       if from_host and not capturing:

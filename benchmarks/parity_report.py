@@ -87,6 +87,9 @@ def main():
                "the conditioned gaussians) and save 0.033 ms per frame (stand-alone calls with plain gradient writes: 0.146 "
                "against 0.179 ms); the large unconditioned numbers are the same with and without the flag — they are f32 "
                "cancellation in the eigen decomposition, not the approximations.  The flag stays.\n")
+  extra = ROOT / "benchmarks" / "parity_extra.md"   # sections measured by other tests (static path, multi-GPU sums)
+  if extra.exists():
+    out.append("\n" + extra.read_text().rstrip("\n"))
   print("\n".join(out))
 
 

@@ -103,6 +103,18 @@ def test_bucket_all_reduce_is_noop_without_process_group():
   assert torch.equal(b.flat, torch.full((12,), 2.0)) and b.nbytes == 48
 
 
+def test_symmetric_bucket_falls_back_without_nvswitch():
+  """GradientBucket(symmetric=True) asks for an NVSwitch multicast mapping of the bucket (gs_multimem_all_reduce);
+  without a CUDA device / NCCL group it must quietly be an ordinary bucket (reducer None), same behaviour otherwise."""
+  p = torch.zeros(8, 3, requires_grad=True)
+  q = torch.zeros(8, requires_grad=True)
+  bucket = GradientBucket([p, q], symmetric=True)
+  assert bucket.reducer is None and bucket.flat.shape == (32,)
+  (p.sum() * 2 + q.sum()).backward()
+  assert bucket.all_reduce() is None
+  assert torch.equal(bucket.flat, torch.cat([torch.full((24,), 2.0), torch.ones(8)]))
+
+
 @pytest.mark.timeout(600)
 def test_view_parallel_gradients_equal_serial_sum(tmp_path):
   world = 2
