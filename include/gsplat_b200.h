@@ -271,7 +271,10 @@ typedef struct GsRasterParams {
                                         timing (benchmarks/variants.py), all tested to the same tolerances
                                         (tests/test_gpu_rasterizer.py test_kernel_variants_agree): bit 0 = narrow backward
                                         reduces every survivor alone (default: pairs), bit 1 = wide backward reduces the
-                                        feature gradient with warp butterflies (default: mma.sync product) */
+                                        feature gradient with warp butterflies (default: mma.sync product), bit 2 = the
+                                        rasterizer kernels launch at the stream's priority (default: the lowest, so that a
+                                        caller's high-priority streams put every other kernel first), bits 3-4 = warps per
+                                        CTA of the wide backward: 0 -> two (default), 1 -> eight, 2 -> four, 3 -> one */
   int64_t num_points;                /* V */
   int64_t num_overlaps;              /* K */
   double clamp_max_alpha, alpha_threshold, saturate_threshold;

@@ -19,7 +19,7 @@ void set_error(const char* fmt, ...) {
 
 extern "C" {
 
-int gs_abi_version(void) { return 4; }
+int gs_abi_version(void) { return 5; }   // 5: *_counted backward / stage / capped emit, multimem all-reduce
 
 const char* gs_last_error_string(void) { return gs::g_error; }
 

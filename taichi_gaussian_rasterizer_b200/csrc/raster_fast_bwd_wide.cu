@@ -224,11 +224,13 @@ struct WideMmaLayout {
   static constexpr int WS = 36;                  // row stride of the weight tile (float2 units): conflict-free A loads
   static constexpr size_t stage_bytes = 2 * kMmaBatch * (32 + FP * 4);
   static constexpr size_t warp_bytes = 32 * GS * 4 + kMmaGroup * WS * 8 + kMmaGroup * 4;
-  static constexpr size_t total = stage_bytes + 8 * warp_bytes;
+  static constexpr size_t total(int warps) { return stage_bytes + warps * warp_bytes; }
 };
 
-template <int FP, bool HEUR>
-__global__ void __launch_bounds__(kWideThreads, 2)   // 118 registers; an 80-register cap (three CTAs) spills: 8.0 vs 6.8 ms
+// WARPS: warps per CTA = 8 (one CTA per tile) or 4 / 2 (two / four CTAs per tile, each staging the tile list for itself:
+// the block barrier of a batch then waits for 4 / 2 warps instead of 8 — 21 % of the stall samples sat there).
+template <int FP, bool HEUR, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)   // 118 registers; an 80-register cap (three CTAs) spills: 8.0 vs 6.8 ms
 raster_bwd_wide_mma_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
                            const float* __restrict__ featP, const int32_t* __restrict__ ranges,
                            const int32_t* __restrict__ o2p, const float* __restrict__ image,
@@ -241,8 +243,10 @@ raster_bwd_wide_mma_kernel(const __grid_constant__ GsRasterParams p, const float
   float4 (*s_r1)[kMmaBatch] = reinterpret_cast<float4 (*)[kMmaBatch]>(smem + 2 * kMmaBatch * 16);
   float (*s_feat)[kMmaBatch][FP] = reinterpret_cast<float (*)[kMmaBatch][FP]>(smem + 2 * kMmaBatch * 32);
 
-  const int tile = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  unsigned char* wbase = smem + L::stage_bytes + (size_t)warp * L::warp_bytes;
+  constexpr int kThreads = WARPS * 32, kParts = 8 / WARPS;
+  const int tile = blockIdx.x / kParts, t = threadIdx.x, lane = t & 31, lwarp = t >> 5;
+  const int warp = (blockIdx.x % kParts) * WARPS + lwarp;   // which 8x4 pixel block of the tile
+  unsigned char* wbase = smem + L::stage_bytes + (size_t)lwarp * L::warp_bytes;
   float* s_G = reinterpret_cast<float*>(wbase);                                    // [32][GS]
   float2* s_W = reinterpret_cast<float2*>(wbase + 32 * L::GS * 4);                 // [16][WS] {hi, lo}
   int* s_idx = reinterpret_cast<int*>(wbase + 32 * L::GS * 4 + kMmaGroup * L::WS * 8);   // [16]
@@ -339,7 +343,7 @@ raster_bwd_wide_mma_kernel(const __grid_constant__ GsRasterParams p, const float
     }
     constexpr int CH = FP / 4;
 #pragma unroll
-    for (int q0 = 0; q0 < kMmaBatch * CH; q0 += kWideThreads) {
+    for (int q0 = 0; q0 < kMmaBatch * CH; q0 += kThreads) {
       const int q = q0 + t;
       const int slot = q / CH, part = q - slot * CH;
       const int v = b * kMmaBatch + slot;
@@ -436,17 +440,31 @@ raster_bwd_wide_mma_kernel(const __grid_constant__ GsRasterParams p, const float
   if (ns > 0) flush_group();
 }
 
-template <int FP, bool HEUR>
-static int launch_wide_mma(const GsRasterParams& p, const RasterArgs& a, const float4* rec, const float* featP, int tiles,
-                           cudaStream_t st) {
+template <int FP, bool HEUR, int WARPS>
+static int launch_wide_mma_w(const GsRasterParams& p, const RasterArgs& a, const float4* rec, const float* featP, int tiles,
+                             cudaStream_t st) {
   using L = WideMmaLayout<FP>;
   // per launch: the attribute belongs to the (function, device) pair and the call costs about a microsecond
-  GS_CUDA(cudaFuncSetAttribute(raster_bwd_wide_mma_kernel<FP, HEUR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)L::total));
-  raster_bwd_wide_mma_kernel<FP, HEUR><<<tiles, kWideThreads, L::total, st>>>(
+  GS_CUDA(cudaFuncSetAttribute(raster_bwd_wide_mma_kernel<FP, HEUR, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)L::total(WARPS)));
+  raster_bwd_wide_mma_kernel<FP, HEUR, WARPS><<<tiles * (8 / WARPS), WARPS * 32, L::total(WARPS), st>>>(
       p, rec, featP, a.tile_ranges, a.overlap_to_point, (const float*)a.image_in, (const float*)a.grad_image,
       (float*)a.grad_gaussians, (float*)a.grad_features, HEUR ? (float*)a.point_heuristic : nullptr);
   return GS_OK;
+}
+
+template <int FP, bool HEUR>
+static int launch_wide_mma(const GsRasterParams& p, const RasterArgs& a, const float4* rec, const float* featP, int tiles,
+                           cudaStream_t st) {
+  // Two warps per CTA (four CTAs per tile).  Measured at config 4 (34 channels, 4K; benchmarks/variants.py
+  // --variants 0,8,16,24 --scene c4): eight warps 7.05 ms, four 7.35, two 6.39, one 6.99.
+  // kernel_variant bits 3-4 (A/B): 0 = two warps per CTA, 1 = eight, 2 = four, 3 = one
+  switch ((p.kernel_variant >> 3) & 3) {
+    case 1: return launch_wide_mma_w<FP, HEUR, 8>(p, a, rec, featP, tiles, st);
+    case 2: return launch_wide_mma_w<FP, HEUR, 4>(p, a, rec, featP, tiles, st);
+    case 3: return launch_wide_mma_w<FP, HEUR, 1>(p, a, rec, featP, tiles, st);
+    default: return launch_wide_mma_w<FP, HEUR, 2>(p, a, rec, featP, tiles, st);
+  }
 }
 
 int raster_bwd_wide(const GsRasterParams& p, const RasterArgs& a, const float4* rec, const float* featP,

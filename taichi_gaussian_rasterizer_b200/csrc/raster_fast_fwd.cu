@@ -176,9 +176,7 @@ raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* _
   const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
   const bool inb = px < p.image_width && py < p.image_height;
   const float pxf = (float)px + 0.5f, pyf = (float)py + 0.5f;
-  const float bx0 = (float)wx0 + 0.5f, bx1 = (float)wx0 + 7.5f, by0 = (float)wy0 + 0.5f, by1 = (float)wy0 + 3.5f;
   const float thr = (float)p.alpha_threshold, cmax = (float)p.clamp_max_alpha;
-  const float l2thr = log2f(thr);
   const float exit_T = (float)p.forward_exit_transmittance;
 
   float acc[FP];

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
   lib = _native.lib()
-  assert lib.gs_abi_version() == 4
+  assert lib.gs_abi_version() == 5
   assert isinstance(lib.gs_last_error_string(), bytes)
 
 

@@ -260,12 +260,13 @@ def test_visibility(cuda_device):
     assert rel_l2(f32.grad[:, 0], r32.visibility) < GRAD_REL_L2
 
 
-@pytest.mark.parametrize("variant,channels", [(1, 3), (2, 34), (2, 12)])
+@pytest.mark.parametrize("variant,channels", [(1, 3), (2, 34), (2, 12), (4, 3), (8, 34), (16, 34), (24, 12)])
 def test_kernel_variants_agree(cuda_device, variant, channels):
   """GsRasterParams.kernel_variant selects alternative instantiations kept for A/B timing (benchmarks/variants.py):
   bit 0 = the narrow backward reduces every survivor on its own (default: in pairs), bit 1 = the wide backward reduces
-  the feature gradient with warp butterflies (default: tensor-core product).  Every variant must pass the same parity
-  check as the default."""
+  the feature gradient with warp butterflies (default: tensor-core product), bit 2 = rasterizer launches at the stream's
+  priority, bits 3-4 = eight / four / one warps per CTA in the wide backward (default: two).  Every variant must pass
+  the same parity check as the default."""
   cfg = RasterConfig(compute_visibility=True, compute_point_heuristic=True)
   set_raster_options(kernel_variant=variant)
   try:
