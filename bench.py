@@ -180,7 +180,8 @@ def run_ours(args):
   # (csrc/multimem_reduce.cu) on the step's streams, inside the step's CUDA graph; --nccl-bucket = ncclAllReduce
   # Measured (gpurun_out/s8_*): 8 GPUs 21.22 ms per step against 21.37 with NCCL; 2 GPUs 21.30 against 20.59 — through
   # the switch (1 + 1/N) x the bucket crosses each link, a two-GPU exchange moves 1 x: used from four ranks up.
-  bucket = GradientBucket(params, symmetric=(world >= 4 and args.symmetric))
+  bucket = GradientBucket(params, symmetric=(world >= args.symmetric_from and args.symmetric))
+  bucket.pipeline_chunks = args.pipeline_chunks
   if world > 1 and args.reduce_early and args.background_ctas > 0:
     from taichi_gaussian_rasterizer_b200.distributed import make_background_group
     bucket.background_group = make_background_group(args.background_ctas)
@@ -580,7 +581,8 @@ def run_ours(args):
                "emulate_stale_tail": True, "forward_exit_transmittance": 0.0,
                "cuda_graph": use_graph, "cuda_graph_error": graph_state["error"],
                "gradient_sum": ("in-switch reduction through a multicast mapping of the bucket (gs_multimem_all_reduce), "
-                                "inside the step's graph" if bucket.reducer is not None else
+                                f"inside the step's graph, pipelined with the SH flush in {args.pipeline_chunks} slices"
+                                if bucket.reducer is not None else
                                 ("ncclAllReduce" if world > 1 else None)),
                "overlap_capacity": graph_state["capacity"] if use_graph else None, "overlap_total_max": overlap_total_max,
                "graph_vs_eager_grad_rel_l2": graph_check,
@@ -780,6 +782,10 @@ def main():
   ap.add_argument("--stream-priority", type=int, default=-1,
                   help="CUDA priority of the view streams (-1 = high: the rasterizer kernels still launch at the lowest)")
   ap.add_argument("--kernel-variant", type=int, default=0, help="set_raster_options(kernel_variant=): A/B switches")
+  ap.add_argument("--symmetric-from", type=int, default=4,
+                  help="smallest world size that sums the bucket with the in-switch kernel (below it: ncclAllReduce)")
+  ap.add_argument("--pipeline-chunks", type=int, default=4,
+                  help="symmetric bucket: slices of the deferred SH flush, each reduced while the next one is formed (1 = off)")
   ap.add_argument("--nccl-bucket", dest="symmetric", action="store_false",
                   help="N > 1: sum the gradient bucket with ncclAllReduce instead of the multimem kernel")
   ap.add_argument("--no-graph", dest="graph", action="store_false",

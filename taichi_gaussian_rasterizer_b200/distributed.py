@@ -35,6 +35,7 @@ class GradientBucket:
     sizes = [p.numel() for p in self.params]
     self.reducer = None
     self.flat = None
+    self.pipeline_chunks = 4   # symmetric bucket: slices of the SH flush reduced while the next one is formed (1 = off)
     if symmetric and device.type == "cuda" and dtype == torch.float32:
       self.reducer = SymmetricBucketReducer.create(sum(sizes), device, group)
       if self.reducer is not None:
@@ -169,6 +170,30 @@ class GradientBucket:
     work = dist.all_reduce(self.flat[split:], op=dist.ReduceOp.SUM, group=self.background_group or group, async_op=True)
     self._early = (split, deferred, work)
 
+  def _all_reduce_pipelined(self, split, d):
+    """The compute step in front of the collective (the flush that forms the SH coefficient rows, HBM bound) and the
+    in-switch reduction (NVLink bound) as a pipeline: the geometry head is reduced while the first slice of rows is
+    formed, and every slice is reduced while the next one is formed — on the reducer's stream, joined at the end."""
+    red = self.reducer
+    cur = torch.cuda.current_stream(self.flat.device)
+    side = red.stream
+    side.wait_stream(cur)                       # every view's backward has been joined into `cur`
+    with torch.cuda.stream(side):
+      red.all_reduce(offset=0, count=split, channel=1)
+    row = d.sink.shape[1] * d.sink.shape[2]
+
+    def after_chunk(lo, hi):
+      formed = torch.cuda.Event()
+      formed.record(cur)
+      side.wait_event(formed)
+      with torch.cuda.stream(side):
+        red.all_reduce(offset=split + lo * row, count=(hi - lo) * row, channel=1)
+
+    if not d.flush(chunks=self.pipeline_chunks, after_chunk=after_chunk):
+      with torch.cuda.stream(side):             # nothing was pending: the rows are final as they are
+        red.all_reduce(offset=split, channel=1)
+    cur.wait_stream(side)
+
   def _finish_early_symmetric(self):
     """After reduce_early() on the symmetric bucket: the geometry head is reduced in the switch, then ONE flush kernel
     adds sum_ranks staged_rank (x) basis(position - camera_rank) to the (already reduced) SH rows, reading every rank's
@@ -246,6 +271,9 @@ class GradientBucket:
       return None
     split, deferred = (None, []) if async_op else self._pending_split()
     if self.reducer is not None and not async_op:
+      if split is not None and split % 4 == 0 and len(deferred) == 1 and self.pipeline_chunks > 1:
+        self._all_reduce_pipelined(split, deferred[0])
+        return None
       self.flush()
       self.reducer.all_reduce()   # on the current stream: in-switch reduction through the multicast mapping
       return None

@@ -24,12 +24,18 @@ def grad_sink(param: torch.Tensor) -> Optional[torch.Tensor]:
 
 
 # ---------------------------------------------------------------------------------------------- deferred SH gradient
-def flush_sh_views(sink: torch.Tensor, points: torch.Tensor, staged, camera_positions, overwrite: bool):
+def flush_sh_views(sink: torch.Tensor, points: torch.Tensor, staged, camera_positions, overwrite: bool, rows=None):
   """sink (N, K, D) (+)= sum_v staged_v (x) basis(points - camera_v): gs_sh_bwd_flush in chunks of MAX_VIEWS views
-  (the first chunk overwrites the rows when ``overwrite``, the others add)."""
+  (the first chunk overwrites the rows when ``overwrite``, the others add).  ``rows = (lo, hi)``: only those gaussians
+  (row slices of every tensor are contiguous)."""
   import ctypes
   from . import _native as N
+  if rows is not None:
+    lo, hi = rows
+    sink, points, staged = sink[lo:hi], points[lo:hi], [t[lo:hi] for t in staged]
   n, k, d = sink.shape
+  if n == 0:
+    return
   for c0 in range(0, len(staged), DeferredSH.MAX_VIEWS):
     chunk_s, chunk_c = staged[c0:c0 + DeferredSH.MAX_VIEWS], camera_positions[c0:c0 + DeferredSH.MAX_VIEWS]
     nv = len(chunk_s)
@@ -94,22 +100,32 @@ class DeferredSH:
     self.pending, self.points, self.hold = [], None, False
     return pending, points
 
-  def flush(self):
+  def flush(self, chunks: int = 1, after_chunk=None):
+    """``chunks`` > 1: the rows are flushed in that many slices and ``after_chunk(lo, hi)`` is called after each
+    slice's kernel has been enqueued (GradientBucket.all_reduce starts reducing a slice while the next one is formed)."""
     if not self.pending and not self.overwrite_next:
       self.points = None
-      return
+      return False
     self._order_after_producers()
-    if len(self.pending) == 0:   # clean sink, nothing staged: the rows become zeros
-      self.sink.zero_()
-    else:
-      flush_sh_views(self.sink, self.points, [p[0] for p in self.pending], [p[1] for p in self.pending],
-                     self.overwrite_next)
+    n = self.sink.shape[0]
+    chunks = max(1, min(int(chunks), n))
+    bounds = [(n * c) // chunks for c in range(chunks + 1)]
+    for c in range(chunks):
+      lo, hi = bounds[c], bounds[c + 1]
+      if len(self.pending) == 0:   # clean sink, nothing staged: the rows become zeros
+        self.sink[lo:hi].zero_()
+      else:
+        flush_sh_views(self.sink, self.points, [p[0] for p in self.pending], [p[1] for p in self.pending],
+                       self.overwrite_next, **({"rows": (lo, hi)} if chunks > 1 else {}))
+      if after_chunk is not None:
+        after_chunk(lo, hi)
     if self.sink.is_cuda:
       self._last_flush = torch.cuda.Event()
       self._last_flush.record(torch.cuda.current_stream(self.sink.device))
     self.overwrite_next = False
     self.pending = []
     self.points = None
+    return True
 
   def _order_after_producers(self):
     """The flushing stream waits for every stream a pending view was staged on and for the previous flush (two

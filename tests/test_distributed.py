@@ -134,9 +134,12 @@ def test_view_parallel_gradients_equal_serial_sum(tmp_path):
 
 
 # ------------------------------------------------------------------------------------- reduce_early (host logic on gloo)
-def _torch_flush(sink, points, staged, camera_positions, overwrite):
+def _torch_flush(sink, points, staged, camera_positions, overwrite, rows=None):
   """What gs_sh_bwd_flush computes, in torch: sink (+)= sum_v staged_v (x) basis(points - camera_v)."""
   from oracle import torch_ref
+  if rows is not None:
+    lo, hi = rows
+    sink, points, staged = sink[lo:hi], points[lo:hi], [t[lo:hi] for t in staged]
   n, k, d = sink.shape
   degree = int(round(d ** 0.5)) - 1
   total = torch.zeros_like(sink)
@@ -147,6 +150,31 @@ def _torch_flush(sink, points, staged, camera_positions, overwrite):
     sink.copy_(total)
   else:
     sink.add_(total)
+
+
+def test_deferred_flush_in_slices_equals_one_flush(monkeypatch):
+  """DeferredSH.flush(chunks=, after_chunk=): the slices cover every row exactly once, in order, and give the rows of
+  a single flush (GradientBucket._all_reduce_pipelined reduces a slice while the next one is formed)."""
+  from taichi_gaussian_rasterizer_b200 import grad_sinks
+  monkeypatch.setattr(grad_sinks, "flush_sh_views", _torch_flush)
+  g = torch.Generator().manual_seed(5)
+  n = 37
+  points = torch.randn(n, 3, generator=g)
+  views = [(torch.randn(n, 3, generator=g), torch.randn(3, generator=g)) for _ in range(3)]
+  results = []
+  for chunks in (1, 4):
+    sink = torch.full((n, 3, 4), 7.0)
+    d = grad_sinks.DeferredSH(sink)
+    d.mark_clean()
+    for staged, cam in views:
+      d.add(staged, cam, points)
+    seen = []
+    assert d.flush(chunks=chunks, after_chunk=lambda lo, hi: seen.append((lo, hi)))
+    assert seen[0][0] == 0 and seen[-1][1] == n and all(a[1] == b[0] for a, b in zip(seen, seen[1:]))
+    assert len(seen) == chunks and not d.pending
+    results.append(sink)
+  assert torch.equal(results[0], results[1])
+  assert not grad_sinks.DeferredSH(torch.zeros(2, 3, 4)).flush(chunks=2)   # nothing pending
 
 
 def _early_worker(rank, world, port, out_dir):
