@@ -637,11 +637,11 @@ def run_configs(device, steps=5):
   sys.path.insert(0, str(ROOT / "benchmarks"))
   import configs as cfgs
   res = {}
-  for name in ("c1", "c1_graph", "c2", "c3", "c4", "c5"):
+  for name in ("c1", "c1_graph", "c2", "c3", "c3_graph", "c4", "c5"):
     try:
       maker = cfgs.CONFIGS.get(name) or cfgs.EXTRA[name]
       step = maker(device)
-      ms, stages, info = cfgs.timed(step, steps if name != "c1_graph" else 50)
+      ms, stages, info = cfgs.timed(step, steps if not name.endswith("_graph") else (50 if name == "c1_graph" else 10))
       res[name] = {"ms_per_frame": round(ms, 3), "what": " ".join(maker.__doc__.split()), **info,
                    "raster_fwd_ms": stages.get("gs_raster_fwd"), "raster_bwd_ms": stages.get("gs_raster_bwd")}
     except Exception as e:   # noqa: BLE001 - report and continue

@@ -139,6 +139,68 @@ def render_step(g, cam, cfg, **kw):
   return step
 
 
+def render_step_graph(g, cam, cfg, **kw):
+  """render_step with the view going through render_gaussians(..., overlap_capacity=) — nothing is read back — and the
+  whole step (forward, loss, backward) replayed from ONE CUDA graph.  The gradients are assigned, not accumulated: they
+  are None when the graph is captured, so every replay rewrites the tensors the capture allocated."""
+  V, K = count_overlaps(g, cam, cfg)
+  capacity = int(K * 1.25) + 4096
+  params = (g.position, g.log_scaling, g.rotation, g.alpha_logit, g.feature)
+  total = torch.zeros(1, dtype=torch.int32, device=g.position.device)
+  dev = g.position.device
+
+  def body():
+    r = render_gaussians(g, cam, cfg, overlap_capacity=capacity, overlap_total_out=total, **kw)
+    loss = r.image.abs().mean()
+    if r.depth is not None:
+      loss = loss + r.depth.mean() * 1e-3
+    loss.backward()
+
+  side = torch.cuda.Stream(device=dev)
+  side.wait_stream(torch.cuda.current_stream(dev))
+  with torch.cuda.stream(side):
+    for _ in range(2):
+      for t in params:
+        t.grad = None
+      body()
+  torch.cuda.current_stream(dev).wait_stream(side)
+  for t in params:
+    t.grad = None
+  graph = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(graph):
+    body()
+
+  def step():
+    graph.replay()
+    return {"V": V, "K": K, "capacity": capacity}
+  step.graph_state = dict(params=params, total=total, keep_alive=(g, cam, graph, body))
+  return step
+
+
+def c2_graph(dev):
+  """config 2 as one CUDA graph per frame (read-back free render_gaussians)."""
+  g, cam = scene3d("c2", dev)
+  return render_step_graph(g, cam, RasterConfig(), use_sh=True)
+
+
+def c3_graph(dev):
+  """config 3 (6M gaussians, visibility + split/prune stats) as one CUDA graph per frame (read-back free render_gaussians)."""
+  g, cam = scene3d("c3", dev)
+  return render_step_graph(g, cam, RasterConfig(compute_visibility=True, compute_point_heuristic=True), use_sh=True)
+
+
+def c4_graph(dev):
+  """config 4 (34 channels, 4K) as one CUDA graph per frame (read-back free render_gaussians)."""
+  g, cam = scene3d("c4", dev)
+  return render_step_graph(g, cam, RasterConfig(), use_sh=False, render_depth=True)
+
+
+def c5_graph(dev):
+  """one view of config 5 as one CUDA graph per frame (read-back free render_gaussians)."""
+  g, cam = scene3d("c5", dev)
+  return render_step_graph(g, cam, RasterConfig(), use_sh=True)
+
+
 def c2(dev):
   """render_gaussians 3D: 1M gaussians, SH degree 3, 1920x1080."""
   g, cam = scene3d("c2", dev)
@@ -164,7 +226,8 @@ def c5(dev):
 
 
 CONFIGS = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5}
-EXTRA = {"c1_graph": c1_graph}   # not part of the default list: python benchmarks/configs.py --only c1,c1_graph
+# not part of the default list: python benchmarks/configs.py --only c1,c1_graph,c3,c3_graph
+EXTRA = {"c1_graph": c1_graph, "c2_graph": c2_graph, "c3_graph": c3_graph, "c4_graph": c4_graph, "c5_graph": c5_graph}
 
 
 def main():

@@ -9,7 +9,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 python bench.py > $OUT/bench_$TAG.log 2>&1; echo "bench rc=$?"; tail -1 $OUT/bench_$TAG.log | cut -c1-400
 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref_$TAG.log 2>&1; echo "reference arm rc=$?"; tail -1 $OUT/bench_ref_$TAG.log | cut -c1-300
-python benchmarks/configs.py --only c1,c1_graph,c2,c3,c4,c5 > $OUT/configs_$TAG.log 2>&1; echo "configs rc=$?"
+python benchmarks/configs.py --only c1,c1_graph,c2,c2_graph,c3,c3_graph,c4,c4_graph,c5,c5_graph > $OUT/configs_$TAG.log 2>&1; echo "configs rc=$?"
 python benchmarks/timeline.py > $OUT/timeline_$TAG.log 2>&1; echo "timeline rc=$?"
 SMALL="python bench.py --no-cpu-baseline --no-configs --no-stock --steps 2 --warmup 1 --views-per-rank 2"
 $SMALL > $OUT/plain_$TAG.log 2>&1; echo "plain rc=$?"
