@@ -346,35 +346,14 @@ def run_ours(args):
   # ---- the step as ONE CUDA graph (default): every view runs through render_gaussians(..., overlap_capacity=), which
   # reads nothing back, so the ~370 launches of a step (two view streams as parallel branches, H2D copies included in
   # the end-to-end variant) are replayed by one cudaGraphLaunch; the gradient all-reduce (N > 1) follows the replay.
-  def overlap_capacity():
-    from taichi_gaussian_rasterizer_b200 import map_to_tiles
-    from taichi_gaussian_rasterizer_b200.perspective.projection import project_to_image
-    from taichi_gaussian_rasterizer_b200.torch_lib.projection import ndc_depth
-    worst = 0
-    with torch.no_grad():
-      for c in dev_cams:
-        g2d, depths, _ = project_to_image(gaussians, c, config)
-        worst = max(worst, int(map_to_tiles(g2d, ndc_depth(depths, c.near_plane, c.far_plane), c.image_size,
-                                            config)[0].shape[0]))
-    return int(worst * 1.25) + 4096
-
   def capture(from_host: bool):
-    side = torch.cuda.Stream(device=device)
-    side.wait_stream(torch.cuda.current_stream(device))
-    with torch.cuda.stream(side):   # warm-up on a side stream, as graph capture requires
-      for _ in range(2):
-        step(from_host, static=True, collective=in_graph_collective)
-    torch.cuda.current_stream(device).wait_stream(side)
-    torch.cuda.synchronize()
-    holder = {}
-    g = torch.cuda.CUDAGraph()
-    graph_state["capturing"] = True
+    from taichi_gaussian_rasterizer_b200 import CapturedStep
+    graph_state["capturing"] = True    # _step: no waits on events of earlier eager steps (also during the warm-up runs)
     try:
-      with torch.cuda.graph(g):
-        holder["total"] = step(from_host, static=True, collective=in_graph_collective)
+      captured = CapturedStep(lambda: step(from_host, static=True, collective=in_graph_collective), device=device)
     finally:
       graph_state["capturing"] = False
-    return g, holder
+    return captured.graph, {"total": captured.result, "captured": captured}
 
   def graph_step(from_host: bool):
     g, holder = graph_state["graphs"][from_host]
@@ -397,7 +376,8 @@ def run_ours(args):
   use_graph, graph_check = False, None
   if args.graph:
     try:
-      graph_state["capacity"] = overlap_capacity()
+      from taichi_gaussian_rasterizer_b200 import overlap_capacity_for
+      graph_state["capacity"] = overlap_capacity_for(gaussians, dev_cams, config)
       graph_state["totals"] = [torch.zeros(1, dtype=torch.int32, device=device) for _ in range(views)]
       step(False)
       eager_flat = bucket.flat.clone()

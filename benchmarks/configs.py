@@ -143,11 +143,11 @@ def render_step_graph(g, cam, cfg, **kw):
   """render_step with the view going through render_gaussians(..., overlap_capacity=) — nothing is read back — and the
   whole step (forward, loss, backward) replayed from ONE CUDA graph.  The gradients are assigned, not accumulated: they
   are None when the graph is captured, so every replay rewrites the tensors the capture allocated."""
+  from taichi_gaussian_rasterizer_b200 import CapturedStep, overlap_capacity_for
   V, K = count_overlaps(g, cam, cfg)
-  capacity = int(K * 1.25) + 4096
+  capacity = overlap_capacity_for(g, [cam], cfg)
   params = (g.position, g.log_scaling, g.rotation, g.alpha_logit, g.feature)
   total = torch.zeros(1, dtype=torch.int32, device=g.position.device)
-  dev = g.position.device
 
   def body():
     r = render_gaussians(g, cam, cfg, overlap_capacity=capacity, overlap_total_out=total, **kw)
@@ -156,24 +156,15 @@ def render_step_graph(g, cam, cfg, **kw):
       loss = loss + r.depth.mean() * 1e-3
     loss.backward()
 
-  side = torch.cuda.Stream(device=dev)
-  side.wait_stream(torch.cuda.current_stream(dev))
-  with torch.cuda.stream(side):
-    for _ in range(2):
-      for t in params:
-        t.grad = None
-      body()
-  torch.cuda.current_stream(dev).wait_stream(side)
-  for t in params:
-    t.grad = None
-  graph = torch.cuda.CUDAGraph()
-  with torch.cuda.graph(graph):
-    body()
+  def no_grads():
+    for t in params:
+      t.grad = None
+  captured = CapturedStep(body, device=g.position.device, before_capture=no_grads)
 
   def step():
-    graph.replay()
+    captured.replay()
     return {"V": V, "K": K, "capacity": capacity}
-  step.graph_state = dict(params=params, total=total, keep_alive=(g, cam, graph, body))
+  step.graph_state = dict(params=params, total=total, keep_alive=(g, cam, captured))
   return step
 
 

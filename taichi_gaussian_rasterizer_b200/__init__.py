@@ -21,6 +21,7 @@ from .rasterizer import rasterize, rasterize_with_tiles, set_raster_options
 # composition
 from .rendering import Rendering
 from .renderer import render_gaussians, render_projected, viewspace_gradient
+from .graphs import CapturedStep, overlap_capacity_for
 # launch-queue compatibility shim (the Taichi runtime it guarded does not exist here)
 from .taichi_queue import TaichiQueue, taichi_queue
 
@@ -28,5 +29,6 @@ __all__ = [
   "Gaussians2D", "Gaussians3D", "RasterConfig", "CameraParams", "perspective",
   "evaluate_sh_at", "evaluate_sh_views", "map_to_tiles", "pad_to_tile", "cuda_lib", "rasterize", "rasterize_with_tiles",
   "set_raster_options", "Rendering", "render_gaussians", "render_projected", "viewspace_gradient",
+  "CapturedStep", "overlap_capacity_for",
   "TaichiQueue", "taichi_queue",
 ]

@@ -6,7 +6,8 @@ ONE CUDA graph and replayed, alone and inside GradientBucket.fused_accumulation 
 import pytest
 import torch
 
-from taichi_gaussian_rasterizer_b200 import RasterConfig, evaluate_sh_views, render_gaussians
+from taichi_gaussian_rasterizer_b200 import (CapturedStep, RasterConfig, evaluate_sh_views, overlap_capacity_for,
+                                             render_gaussians)
 from taichi_gaussian_rasterizer_b200.distributed import GradientBucket, run_views
 from util import rel_l2, scene3d
 
@@ -166,13 +167,16 @@ def test_static_multi_view_bucket_graph(cuda_device):
   bucket = GradientBucket(params)
   streams = [torch.cuda.Stream(device=cuda_device) for _ in range(2)]
 
+  capacity = overlap_capacity_for(g, cams, cfg)
+  assert 4096 < capacity < 10_000_000
+
   def step(static):
     with bucket.fused_accumulation():
       bucket.zero_()
       colors = evaluate_sh_views(g.feature, g.position, [c.camera_position for c in cams])
 
       def view(i):
-        kw = dict(overlap_capacity=300_000) if static else {}
+        kw = dict(overlap_capacity=capacity) if static else {}
         out = render_gaussians(g, cams[i], cfg, use_sh=True, sh_colors=colors[i], **kw)
         loss = torch.nn.functional.l1_loss(out.image, targets[i])
         loss.backward()
@@ -184,19 +188,16 @@ def test_static_multi_view_bucket_graph(cuda_device):
   ref_loss = step(False).item()
   ref = bucket.flat.clone()
 
-  side = torch.cuda.Stream(device=cuda_device)
-  side.wait_stream(torch.cuda.current_stream(cuda_device))
-  with torch.cuda.stream(side):
-    step(True)
-  torch.cuda.current_stream(cuda_device).wait_stream(side)
+  assert not CapturedStep.capturing()
+  captured = CapturedStep(lambda: step(True), device=cuda_device)   # warm-up runs on a side stream, then the capture
   torch.cuda.synchronize()
-  assert rel_l2(bucket.flat, ref) < 2e-6
-  holder = {}
-  graph = torch.cuda.CUDAGraph()
-  with torch.cuda.graph(graph):
-    holder["loss"] = step(True)
   bucket.flat.fill_(7.0)   # the replay must rebuild every gradient
-  graph.replay()
+  loss = captured.replay()
   torch.cuda.synchronize()
   assert rel_l2(bucket.flat, ref) < 2e-6, rel_l2(bucket.flat, ref)
-  assert abs(holder["loss"].item() - ref_loss) <= 1e-6 * abs(ref_loss)
+  assert abs(loss.item() - ref_loss) <= 1e-6 * abs(ref_loss)
+  with torch.no_grad():   # parameters change in place between replays, as an optimizer step does
+    g.alpha_logit.sub_(0.2)
+  loss2 = captured.replay().item()
+  moved = step(False).item()
+  assert abs(loss2 - moved) <= 1e-6 * abs(moved) and loss2 != ref_loss
