@@ -75,6 +75,46 @@ def test_static_equals_default(cuda_device, use_sh, render_depth, stats):
     assert rel_l2(g_out[n], g_ref[n]) < 2e-6, (n, rel_l2(g_out[n], g_ref[n]))
 
 
+@pytest.mark.parametrize("case", ["depth16", "median_depth", "antialias", "tile8", "tile32"])
+def test_static_options_equal_default(cuda_device, case):
+  """The options that change kernels or sort keys under the read-back free path: 16 bit depth keys, the quantile
+  (median depth) pass, antialiased rendering, the generic kernels (tile 8 / 32).  Forward bit-identical to the default
+  path, gradients to the order of the atomic additions."""
+  kw, cfg_kw = {}, {}
+  if case == "depth16":
+    kw = dict(use_depth16=True)
+  elif case == "median_depth":
+    kw = dict(render_median_depth=True)
+  elif case == "antialias":
+    cfg_kw = dict(antialias=True, blur_cov=0.0)
+  elif case == "tile8":
+    cfg_kw = dict(tile_size=8, pixel_stride=(1, 1))
+  elif case == "tile32":
+    cfg_kw = dict(tile_size=32)
+  cfg = RasterConfig(**cfg_kw)
+  g, cam = _scene(cuda_device, n=4000)
+  torch.manual_seed(2)
+  gi = torch.rand(cam.image_size[1], cam.image_size[0], 3, device=cuda_device) - 0.3
+
+  def run(**extra):
+    for p in _params(g):
+      p.grad = None
+    out = render_gaussians(g, cam, cfg, use_sh=True, **kw, **extra)
+    loss = (out.image * gi).sum()
+    if out.median_depth is not None:
+      loss = loss + out.median_depth.mean()
+    loss.backward()
+    return out, _grads(g)
+
+  ref, g_ref = run()
+  out, g_out = run(overlap_capacity=500_000)
+  assert torch.equal(out.image, ref.image) and torch.equal(out.image_weight, ref.image_weight)
+  if case == "median_depth":
+    assert torch.equal(out.median_depth, ref.median_depth)
+  for n in NAMES:
+    assert rel_l2(g_out[n], g_ref[n]) < 2e-6, (n, rel_l2(g_out[n], g_ref[n]))
+
+
 def test_static_drops_overlaps_beyond_capacity(cuda_device):
   """A capacity below K must not overrun anything: K is still reported, the image is simply missing gaussians."""
   cfg = RasterConfig()
