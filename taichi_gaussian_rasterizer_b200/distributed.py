@@ -332,7 +332,9 @@ class SymmetricBucketReducer:
         return None
       buf.zero_()
       return cls(buf, handle, flags, flags_handle, group, blocks)
-    except Exception:   # noqa: BLE001 - no symmetric memory in this torch / on this box: the caller uses NCCL
+    except Exception as e:   # noqa: BLE001 - no symmetric memory in this torch / on this box: the caller uses NCCL
+      import warnings
+      warnings.warn(f"symmetric gradient bucket unavailable ({type(e).__name__}: {e}); falling back to ncclAllReduce")
       return None
 
   def all_reduce(self, offset: int = 0, count: Optional[int] = None, channel: int = 0):

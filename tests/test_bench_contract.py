@@ -33,6 +33,10 @@ def test_bench_line_has_the_contract_keys(cuda_device):
   assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port"
   assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
   assert "workload" in d["config"] and "model" not in d["config"]
+  # the timed step is the CUDA-graph replay of the read-back free path, checked against the eager default path
+  assert d["config"]["cuda_graph"] is True, d["config"].get("cuda_graph_error")
+  assert d["config"]["graph_vs_eager_grad_rel_l2"] < 1e-5
+  assert d["config"]["overlap_total_max"] <= d["config"]["overlap_capacity"]
 
 
 def test_reference_arm_line(monkeypatch):
