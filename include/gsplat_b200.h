@@ -157,6 +157,17 @@ int gs_sh_fwd_views(const GsSHParams* p, int32_t num_views, const void* params, 
 int gs_gather_rows_counted(int64_t capacity, int32_t row_floats, const void* src, const int64_t* indexes,
                            const int32_t* count_dev, void* out, void* stream);
 
+/* Plain (non-SH) features of the visible set: replaces `features = gaussians.feature[indexes]` of render_gaussians
+ * (renderer.py:152-153) and the index_put of its backward.  Rows of row_floats f32, any width; the gathered rows may
+ * land inside wider rows (out_stride / out_offset, in floats: e.g. behind the two depth channels of render_depth);
+ * `indexes` are unique (the visible set), so the scatter writes without atomics after zero-filling dst (dst_rows rows).
+ * count_dev (optional): the number of valid indexes still on the device, capacity = rows of `indexes`. */
+int gs_gather_rows_strided(int64_t capacity, int32_t row_floats, const float* src, const int64_t* indexes,
+                           const int32_t* count_dev, float* out, int32_t out_stride, int32_t out_offset, void* stream);
+int gs_scatter_rows_strided(int64_t capacity, int32_t row_floats, const float* src, int32_t src_stride,
+                            int32_t src_offset, const int64_t* indexes, const int32_t* count_dev, int64_t dst_rows,
+                            float* dst, void* stream);
+
 /* ------------------------------------------------------------------ tile mapper (f32)
  * replaces tile_overlaps_kernel / generate_sort_keys_kernel / find_ranges_kernel
  * (mapper/tile_mapper.py:73-84, :112-144, :90-110) with the OBB query of

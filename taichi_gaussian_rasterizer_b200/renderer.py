@@ -83,6 +83,7 @@ def render_gaussians(
                                                   after_launch=early_work if order_early else None)
 
   fill_features = None
+  depth_in_features = False
   if use_sh and sh_early:
     # The colours do not depend on the tile map: their kernel (the SH evaluation, or the gather of this view's rows of
     # a batch evaluation) is enqueued by the tile mapper right before it waits for the overlap total, to keep the GPU
@@ -103,13 +104,18 @@ def render_gaussians(
     features = evaluate_sh_at(gaussians.feature, gaussians.position.detach(), indexes,
                               camera_position, indexes_sorted_unique=True)
   else:
-    features = gaussians.feature[indexes]
-    assert len(features.shape) == 2, f"Features must be (N, C) if use_sh=False, got {features.shape}"
+    assert len(gaussians.feature.shape) == 2, f"Features must be (N, C) if use_sh=False, got {gaussians.feature.shape}"
+    # one gather kernel, the two depth channels of render_depth assembled in front of the rows by the same call
+    features = _visible_features(gaussians.feature, indexes, None, depths if render_depth else None)
+    if features is not None:
+      depth_in_features = render_depth
+    else:
+      features = gaussians.feature[indexes]
 
   return render_projected(indexes, gaussians2d, features, depths, camera_params, config,
                           render_depth=render_depth, use_depth16=use_depth16,
                           render_median_depth=render_median_depth, mapper_front=early.get("front"),
-                          before_total_sync=fill_features)
+                          before_total_sync=fill_features, features_include_depth=depth_in_features)
 
 
 def _render_gaussians_static(gaussians, camera_params, config, use_sh, render_depth, use_depth16, render_median_depth,
@@ -139,8 +145,9 @@ def _render_gaussians_static(gaussians, camera_params, config, use_sh, render_de
   else:
     assert sh_colors is None
     assert len(gaussians.feature.shape) == 2, f"Features must be (N, C) if use_sh=False, got {gaussians.feature.shape}"
-    features = _GatherCounted.apply(gaussians.feature, indexes, count)
-  if render_depth:
+    features = _visible_features(gaussians.feature, indexes, count, depths if render_depth else None)
+    assert features is not None, "overlap_capacity without SH: dense contiguous float32 features"
+  if render_depth and use_sh:
     features = torch.cat([depths, depths ** 2, features], dim=1)
   overlap_to_point, tile_ranges = map_front_to_tiles_capped(gaussians2d, count, front, size, config, overlap_capacity,
                                                             overlap_total_out)
@@ -149,8 +156,8 @@ def _render_gaussians_static(gaussians, camera_params, config, use_sh, render_de
                                 image_size=size, config=config)
   image, depth_image, depth_var = raster.image, None, None
   if render_depth:
-    depth_image, depth_var = compute_depth_variance(image[..., :2], raster.image_weight)
-    image = image[..., 2:]
+    depth2, image = _SplitDepthChannels.apply(image)
+    depth_image, depth_var = compute_depth_variance(depth2, raster.image_weight)
   return Rendering(
     image=image, image_weight=raster.image_weight, depth=depth_image, depth_var=depth_var,
     median_depth=(_median_depth(gaussians2d, depths, overlap_to_point, ranges, camera_params, config)
@@ -161,25 +168,84 @@ def _render_gaussians_static(gaussians, camera_params, config, use_sh, render_de
     camera=camera_params, config=config, points_in_view_count=count)
 
 
-class _GatherCounted(torch.autograd.Function):
-  """features[indexes[:count]] into a capacity-sized buffer (rows past the count: zeros), count on the device; the
-  backward scatters the first count gradient rows back (indexes are unique).  Plain torch indexing with a
-  device-side row limit: the rows past the count are masked instead of sliced off."""
+class _VisibleFeatures(torch.autograd.Function):
+  """The plain (non-SH) feature rows of the visible set, optionally behind the two depth channels of render_depth:
+  ``[depth, depth^2, feature[indexes]]`` assembled by ONE gather kernel (gs_gather_rows_strided) instead of
+  ``feature[indexes]`` + ``torch.cat`` (renderer.py:152-153, 199-200 of the reference), the backward ONE scatter
+  (gs_scatter_rows_strided: the indexes are unique, no atomics, no sort) instead of index_put with accumulate + the
+  slices of the cat.  ``count`` (optional, (1,) int32 on the device): only the first count[0] rows of ``indexes`` are
+  valid (read-back free path); rows past it are left uninitialised / ignored."""
 
   @staticmethod
-  def forward(ctx, features, indexes, count):
-    valid = torch.arange(indexes.shape[0], device=indexes.device) < count
-    safe = torch.where(valid, indexes, torch.zeros_like(indexes))
-    ctx.save_for_backward(safe, valid)
-    ctx.rows = features.shape[0]
-    return features[safe] * valid.unsqueeze(1).to(features.dtype)
+  def forward(ctx, feature, indexes, count, depths):
+    import ctypes
+    from . import _native as N
+    v, c = indexes.shape[0], feature.shape[1]
+    extra = 0 if depths is None else 2
+    out = torch.empty((v, c + extra), dtype=feature.dtype, device=feature.device)
+    N.call("gs_gather_rows_strided", ctypes.c_int64(v), ctypes.c_int32(c), N.ptr(feature), N.ptr(indexes),
+           N.ptr(count), N.ptr(out), ctypes.c_int32(c + extra), ctypes.c_int32(extra), N.stream_ptr(feature.device))
+    if depths is not None:
+      out[:, 0:1] = depths
+      out[:, 1:2] = depths * depths
+    ctx.rows, ctx.extra = feature.shape[0], extra
+    ctx.save_for_backward(indexes, count, depths)
+    return out
 
   @staticmethod
-  def backward(ctx, grad):
-    safe, valid = ctx.saved_tensors
-    out = grad.new_zeros((ctx.rows, grad.shape[1]))
-    out.index_add_(0, safe, grad * valid.unsqueeze(1).to(grad.dtype))
-    return out, None, None
+  def backward(ctx, g):
+    import ctypes
+    from . import _native as N
+    indexes, count, depths = ctx.saved_tensors
+    g = g.contiguous()
+    v, width = g.shape
+    c = width - ctx.extra
+    g_feature = g_depths = None
+    if ctx.needs_input_grad[0]:
+      g_feature = torch.empty((ctx.rows, c), dtype=g.dtype, device=g.device)
+      N.call("gs_scatter_rows_strided", ctypes.c_int64(v), ctypes.c_int32(c), N.ptr(g), ctypes.c_int32(width),
+             ctypes.c_int32(ctx.extra), N.ptr(indexes), N.ptr(count), ctypes.c_int64(ctx.rows), N.ptr(g_feature),
+             N.stream_ptr(g.device))
+    if depths is not None and ctx.needs_input_grad[3]:
+      g_depths = g[:, 0:1] + 2.0 * depths * g[:, 1:2]
+    return g_feature, None, None, g_depths
+
+
+def _visible_features(feature, indexes, count=None, depths=None):
+  """feature[indexes] (with the depth channels in front when ``depths`` is given) through the kernels above when the
+  features are dense contiguous float32 on the GPU; None otherwise (the caller indexes with torch)."""
+  if feature.is_cuda and feature.dtype == torch.float32 and feature.ndim == 2 and feature.is_contiguous() and \
+      (depths is None or depths.dtype == torch.float32):
+    return _VisibleFeatures.apply(feature, indexes.contiguous(), count, depths)
+  return None
+
+
+class _SplitDepthChannels(torch.autograd.Function):
+  """(H, W, 2 + C) blended [depth, depth^2, features] -> contiguous (H, W, 2) and (H, W, C).
+
+  The reference slices (renderer.py:215-222): two strided views of one tensor, every later elementwise operation of the
+  caller (a loss over a 34-channel 4K image, say) then runs on a strided view, and autograd's backward of the two slices
+  is two zero-filled full-size tensors plus their sum — at config 4 that glue cost 7 ms of a 16.6 ms frame.  Here the two
+  parts are copied out once (same values) and the backward writes both gradients into ONE uninitialised full-size
+  tensor: each element exactly once, no zero fill, no add."""
+
+  @staticmethod
+  def forward(ctx, image):
+    ctx.shape, ctx.opts = image.shape, dict(dtype=image.dtype, device=image.device)
+    return image[..., :2].contiguous(), image[..., 2:].contiguous()
+
+  @staticmethod
+  def backward(ctx, g_depth, g_feat):
+    g = torch.empty(ctx.shape, **ctx.opts)
+    if g_depth is None:
+      g[..., :2].zero_()
+    else:
+      g[..., :2].copy_(g_depth)
+    if g_feat is None:
+      g[..., 2:].zero_()
+    else:
+      g[..., 2:].copy_(g_feat)
+    return g
 
 
 def compute_depth_variance(depth_depthsq, weight, eps=1e-6):
@@ -208,16 +274,17 @@ def render_projected(indexes: torch.Tensor, gaussians2d: torch.Tensor,
                      camera_params: CameraParams, config: RasterConfig,
                      render_depth: bool = False, use_depth16: bool = False,
                      render_median_depth: bool = False, use_ndc_depth: bool = False,
-                     mapper_front=None, before_total_sync=None):
+                     mapper_front=None, before_total_sync=None, features_include_depth: bool = False):
   """Tile-map and rasterize gaussians that are already projected (renderer.py:183-231 of the reference).
   Gaussians are ordered by NDC depth inside every tile; depth features stay linear unless use_ndc_depth.
   ``mapper_front`` (extension): the front half of the tile mapping of exactly these gaussians when render_gaussians has
   already enqueued it (mapper.tile_mapper.launch_mapper_front_counted); ``before_total_sync``: see _map_to_tiles (called exactly
-  once before the rasterizer is enqueued)."""
+  once before the rasterizer is enqueued); ``features_include_depth``: the caller has already put the two depth channels
+  in front of the feature rows (render_gaussians' plain-feature path assembles them with its gather kernel)."""
   size = camera_params.image_size
   ndc_range = (camera_params.near_plane, camera_params.far_plane)
 
-  if render_depth:   # two extra leading channels: depth and depth^2, blended like any other feature
+  if render_depth and not features_include_depth:   # two extra leading channels: depth and depth^2, blended like any other feature
     if before_total_sync is not None:   # the features are read right here: their kernel cannot wait for the mapper
       before_total_sync()
       before_total_sync = None
@@ -240,8 +307,8 @@ def render_projected(indexes: torch.Tensor, gaussians2d: torch.Tensor,
 
   image, depth_image, depth_var = raster.image, None, None
   if render_depth:
-    depth_image, depth_var = compute_depth_variance(image[..., :2], raster.image_weight)
-    image = image[..., 2:]
+    depth2, image = _SplitDepthChannels.apply(image)
+    depth_image, depth_var = compute_depth_variance(depth2, raster.image_weight)
 
   return Rendering(
     image=image, image_weight=raster.image_weight, depth=depth_image, depth_var=depth_var,

@@ -48,7 +48,7 @@ def oracle_render(g, cam, cfg, use_sh, render_depth, out):
   return raster, idx, o2p, g64, (img32, w32, vis32)
 
 
-@pytest.mark.parametrize("use_sh,render_depth", [(False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("use_sh,render_depth", [(False, False), (True, False), (True, True), (False, True)])
 def test_render_gaussians_vs_oracle(cuda_device, use_sh, render_depth):
   cfg = RasterConfig(compute_visibility=True, compute_point_heuristic=True)
   g, cam = scene3d(3, 6000, image_size=(320, 240), scale_factor=0.5, sh_degree=3 if use_sh else None)

@@ -31,7 +31,7 @@ def _grads(g):
   return {n: getattr(g, n).grad.clone() for n in NAMES}
 
 
-@pytest.mark.parametrize("use_sh,render_depth,stats", [(True, False, False), (False, False, True), (True, True, True)])
+@pytest.mark.parametrize("use_sh,render_depth,stats", [(True, False, False), (False, False, True), (True, True, True), (False, True, False)])
 def test_static_equals_default(cuda_device, use_sh, render_depth, stats):
   cfg = RasterConfig(compute_visibility=stats, compute_point_heuristic=stats)
   g, cam = _scene(cuda_device, sh=use_sh)
