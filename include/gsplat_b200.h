@@ -168,6 +168,14 @@ int gs_scatter_rows_strided(int64_t capacity, int32_t row_floats, const float* s
                             int32_t src_offset, const int64_t* indexes, const int32_t* count_dev, int64_t dst_rows,
                             float* dst, void* stream);
 
+/* render_depth: the rendered (P, channels) image split into its first `split` channels (depth, depth^2) and the rest,
+ * and the inverse for the backward (a NULL part stands for zeros) — replaces the two strided slices of
+ * renderer.py:215-222 and autograd's zero-padded slice backward of each.  f32, contiguous rows. */
+int gs_split_channels(int64_t rows, int32_t channels, int32_t split, const float* src, float* first, float* rest,
+                      void* stream);
+int gs_merge_channels(int64_t rows, int32_t channels, int32_t split, const float* first, const float* rest, float* dst,
+                      void* stream);
+
 /* ------------------------------------------------------------------ tile mapper (f32)
  * replaces tile_overlaps_kernel / generate_sort_keys_kernel / find_ranges_kernel
  * (mapper/tile_mapper.py:73-84, :112-144, :90-110) with the OBB query of

@@ -17,7 +17,7 @@ GS_F32, GS_F64 = 0, 1
 EXPORTS = [
   "gs_abi_version", "gs_last_error_string",
   "gs_project_fwd_workspace_bytes", "gs_project_fwd", "gs_project_bwd", "gs_project_bwd_counted",
-  "gs_sh_fwd", "gs_sh_fwd_counted", "gs_sh_bwd", "gs_sh_bwd_stage", "gs_sh_bwd_stage_counted", "gs_sh_bwd_flush", "gs_sh_fwd_views", "gs_gather_rows_counted", "gs_gather_rows_strided", "gs_scatter_rows_strided",
+  "gs_sh_fwd", "gs_sh_fwd_counted", "gs_sh_bwd", "gs_sh_bwd_stage", "gs_sh_bwd_stage_counted", "gs_sh_bwd_flush", "gs_sh_fwd_views", "gs_gather_rows_counted", "gs_gather_rows_strided", "gs_scatter_rows_strided", "gs_split_channels", "gs_merge_channels",
   "gs_tile_count", "gs_full_cumsum_workspace_bytes", "gs_full_cumsum", "gs_full_cumsum_counted", "gs_tile_emit_keys",
   "gs_radix_sort_pairs_workspace_bytes", "gs_radix_sort_pairs", "gs_radix_sort_pairs_counted", "gs_find_ranges",
   "gs_depth_keys", "gs_depth_keys_counted", "gs_tile_count_perm", "gs_tile_count_perm_counted", "gs_tile_emit_tiles", "gs_find_ranges_tiles",

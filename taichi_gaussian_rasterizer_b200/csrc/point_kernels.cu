@@ -488,6 +488,36 @@ scatter_rows_strided_kernel(int64_t capacity, int row, const float* __restrict__
   dst[indexes[j] * row + c] = src[j * src_stride + src_offset + c];
 }
 
+// Channel split / merge of the rendered image for render_depth: (P, F) rows -> (P, S) and (P, F - S), and back.
+// The reference slices (renderer.py:215-222); as strided views every later elementwise pass over the 34-channel 4K
+// image and autograd's zero-padded slice backward run at a fraction of the bandwidth (ATen's generic strided copy:
+// four passes of 0.5 ms at config 4).  VEC floats per thread (2 when F and S are even: all three row starts 8 B aligned).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+split_channels_kernel(int64_t total, int F, int S, const float* __restrict__ src, float* __restrict__ a,
+                      float* __restrict__ b) {
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (e >= total) return;
+  const int64_t row = e / F;
+  const int c = (int)(e - row * F);
+  float* dst = c < S ? a + row * S + c : b + row * (F - S) + (c - S);
+  if (VEC == 2) *reinterpret_cast<float2*>(dst) = *reinterpret_cast<const float2*>(src + e);
+  else *dst = src[e];
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+merge_channels_kernel(int64_t total, int F, int S, const float* __restrict__ a, const float* __restrict__ b,
+                      float* __restrict__ dst) {
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (e >= total) return;
+  const int64_t row = e / F;
+  const int c = (int)(e - row * F);
+  const float* src = c < S ? (a ? a + row * S + c : nullptr) : (b ? b + row * (F - S) + (c - S) : nullptr);
+  if (VEC == 2) *reinterpret_cast<float2*>(dst + e) = src ? *reinterpret_cast<const float2*>(src) : make_float2(0.f, 0.f);
+  else dst[e] = src ? *src : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------------ projection bwd
 constexpr int kPBwdBlock = 128;
 
@@ -933,6 +963,38 @@ int gs_scatter_rows_strided(int64_t capacity, int32_t row_floats, const float* s
   GS_CHECK_ARG(src && indexes, "gs_scatter_rows_strided: null tensor");
   scatter_rows_strided_kernel<<<(unsigned)ceil_div(capacity * row_floats, 256), 256, 0, st>>>(
       capacity, row_floats, src, src_stride, src_offset, indexes, count_dev, dst);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+int gs_split_channels(int64_t rows, int32_t channels, int32_t split, const float* src, float* first, float* rest,
+                      void* stream) {
+  GS_CHECK_ARG(rows >= 0 && channels > 0 && split > 0 && split < channels, "gs_split_channels: bad sizes");
+  if (rows == 0) return GS_OK;
+  GS_CHECK_ARG(src && first && rest, "gs_split_channels: null tensor");
+  const int64_t total = rows * channels;
+  if (channels % 2 == 0 && split % 2 == 0)
+    split_channels_kernel<2><<<(unsigned)ceil_div(total / 2, 256), 256, 0, (cudaStream_t)stream>>>(total, channels, split,
+                                                                                                   src, first, rest);
+  else
+    split_channels_kernel<1><<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(total, channels, split, src,
+                                                                                               first, rest);
+  GS_LAUNCH_CHECK();
+  return GS_OK;
+}
+
+int gs_merge_channels(int64_t rows, int32_t channels, int32_t split, const float* first, const float* rest, float* dst,
+                      void* stream) {
+  GS_CHECK_ARG(rows >= 0 && channels > 0 && split > 0 && split < channels, "gs_merge_channels: bad sizes");
+  if (rows == 0) return GS_OK;
+  GS_CHECK_ARG(dst != nullptr, "gs_merge_channels: null destination");
+  const int64_t total = rows * channels;
+  if (channels % 2 == 0 && split % 2 == 0)
+    merge_channels_kernel<2><<<(unsigned)ceil_div(total / 2, 256), 256, 0, (cudaStream_t)stream>>>(total, channels, split,
+                                                                                                   first, rest, dst);
+  else
+    merge_channels_kernel<1><<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(total, channels, split,
+                                                                                               first, rest, dst);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }

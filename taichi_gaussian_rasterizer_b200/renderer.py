@@ -232,11 +232,29 @@ class _SplitDepthChannels(torch.autograd.Function):
   @staticmethod
   def forward(ctx, image):
     ctx.shape, ctx.opts = image.shape, dict(dtype=image.dtype, device=image.device)
-    return image[..., :2].contiguous(), image[..., 2:].contiguous()
+    ctx.native = image.is_cuda and image.dtype == torch.float32 and image.is_contiguous()
+    if not ctx.native:
+      return image[..., :2].contiguous(), image[..., 2:].contiguous()
+    import ctypes
+    from . import _native as N
+    h, w, f = image.shape
+    depth2 = torch.empty((h, w, 2), **ctx.opts)
+    rest = torch.empty((h, w, f - 2), **ctx.opts)
+    N.call("gs_split_channels", ctypes.c_int64(h * w), ctypes.c_int32(f), ctypes.c_int32(2), N.ptr(image), N.ptr(depth2),
+           N.ptr(rest), N.stream_ptr(image.device))
+    return depth2, rest
 
   @staticmethod
   def backward(ctx, g_depth, g_feat):
     g = torch.empty(ctx.shape, **ctx.opts)
+    if ctx.native:
+      import ctypes
+      from . import _native as N
+      h, w, f = ctx.shape
+      N.call("gs_merge_channels", ctypes.c_int64(h * w), ctypes.c_int32(f), ctypes.c_int32(2),
+             N.ptr(None if g_depth is None else g_depth.contiguous()),
+             N.ptr(None if g_feat is None else g_feat.contiguous()), N.ptr(g), N.stream_ptr(g.device))
+      return g
     if g_depth is None:
       g[..., :2].zero_()
     else:
