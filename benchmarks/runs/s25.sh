@@ -8,3 +8,6 @@ for l in open('gpurun_out/s25_c4.log'):
     if l.startswith('{'):
         d=json.loads(l); print(d['config'], d.get('ms_per_frame_fwd_bwd'), d.get('error','')[:200], d.get('peak_mem_gb'))
 P
+mkdir -p gpurun_out
+python benchmarks/profile_config.py c4 --top 30 > gpurun_out/s26_c4_profile.log 2>&1; echo rc=$?
+grep -v Warning gpurun_out/s26_c4_profile.log | tail -32 | cut -c1-170

@@ -464,27 +464,32 @@ gather_rows_counted_kernel(int64_t capacity, const float* __restrict__ src, cons
 // scatter needs no atomics; the count may still be on the device.
 //   gather : out[j * out_stride + out_offset + c] = src[indexes[j] * row + c]
 //   scatter: dst[indexes[j] * row + c] = src[j * src_stride + src_offset + c]      (dst zero-filled by the caller)
+// IdxT: uint32_t when the element count fits (a 64 bit division per thread costs more than the copy)
+template <typename IdxT>
 __global__ void __launch_bounds__(256)
 gather_rows_strided_kernel(int64_t capacity, int row, const float* __restrict__ src, const int64_t* __restrict__ indexes,
                            const int32_t* __restrict__ count_dev, float* __restrict__ out, int out_stride,
                            int out_offset) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const IdxT e = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nv = count_dev ? min(capacity, (int64_t)*count_dev) : capacity;
-  const int64_t j = e / row;
+  const IdxT jq = e / (IdxT)row;
+  const int64_t j = (int64_t)jq;
   if (j >= nv) return;
-  const int c = (int)(e - j * row);
+  const int c = (int)(e - jq * (IdxT)row);
   out[j * out_stride + out_offset + c] = src[indexes[j] * row + c];
 }
 
+template <typename IdxT>
 __global__ void __launch_bounds__(256)
 scatter_rows_strided_kernel(int64_t capacity, int row, const float* __restrict__ src, int src_stride, int src_offset,
                             const int64_t* __restrict__ indexes, const int32_t* __restrict__ count_dev,
                             float* __restrict__ dst) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const IdxT e = (IdxT)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nv = count_dev ? min(capacity, (int64_t)*count_dev) : capacity;
-  const int64_t j = e / row;
+  const IdxT jq = e / (IdxT)row;
+  const int64_t j = (int64_t)jq;
   if (j >= nv) return;
-  const int c = (int)(e - j * row);
+  const int c = (int)(e - jq * (IdxT)row);
   dst[indexes[j] * row + c] = src[j * src_stride + src_offset + c];
 }
 
@@ -492,27 +497,31 @@ scatter_rows_strided_kernel(int64_t capacity, int row, const float* __restrict__
 // The reference slices (renderer.py:215-222); as strided views every later elementwise pass over the 34-channel 4K
 // image and autograd's zero-padded slice backward run at a fraction of the bandwidth (ATen's generic strided copy:
 // four passes of 0.5 ms at config 4).  VEC floats per thread (2 when F and S are even: all three row starts 8 B aligned).
-template <int VEC>
+template <int VEC, typename IdxT>
 __global__ void __launch_bounds__(256)
 split_channels_kernel(int64_t total, int F, int S, const float* __restrict__ src, float* __restrict__ a,
                       float* __restrict__ b) {
-  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  const IdxT eq = ((IdxT)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  const int64_t e = (int64_t)eq;
   if (e >= total) return;
-  const int64_t row = e / F;
-  const int c = (int)(e - row * F);
+  const IdxT rq = eq / (IdxT)F;
+  const int64_t row = (int64_t)rq;
+  const int c = (int)(eq - rq * (IdxT)F);
   float* dst = c < S ? a + row * S + c : b + row * (F - S) + (c - S);
   if (VEC == 2) *reinterpret_cast<float2*>(dst) = *reinterpret_cast<const float2*>(src + e);
   else *dst = src[e];
 }
 
-template <int VEC>
+template <int VEC, typename IdxT>
 __global__ void __launch_bounds__(256)
 merge_channels_kernel(int64_t total, int F, int S, const float* __restrict__ a, const float* __restrict__ b,
                       float* __restrict__ dst) {
-  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  const IdxT eq = ((IdxT)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  const int64_t e = (int64_t)eq;
   if (e >= total) return;
-  const int64_t row = e / F;
-  const int c = (int)(e - row * F);
+  const IdxT rq = eq / (IdxT)F;
+  const int64_t row = (int64_t)rq;
+  const int c = (int)(eq - rq * (IdxT)F);
   const float* src = c < S ? (a ? a + row * S + c : nullptr) : (b ? b + row * (F - S) + (c - S) : nullptr);
   if (VEC == 2) *reinterpret_cast<float2*>(dst + e) = src ? *reinterpret_cast<const float2*>(src) : make_float2(0.f, 0.f);
   else dst[e] = src ? *src : 0.f;
@@ -944,8 +953,13 @@ int gs_gather_rows_strided(int64_t capacity, int32_t row_floats, const float* sr
                "gs_gather_rows_strided: bad sizes");
   if (capacity == 0) return GS_OK;
   GS_CHECK_ARG(src && indexes && out, "gs_gather_rows_strided: null tensor");
-  gather_rows_strided_kernel<<<(unsigned)ceil_div(capacity * row_floats, 256), 256, 0, (cudaStream_t)stream>>>(
-      capacity, row_floats, src, indexes, count_dev, out, out_stride, out_offset);
+  const int64_t total = capacity * row_floats;
+  if (total + 256 < (1ll << 32))
+    gather_rows_strided_kernel<uint32_t><<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        capacity, row_floats, src, indexes, count_dev, out, out_stride, out_offset);
+  else
+    gather_rows_strided_kernel<uint64_t><<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        capacity, row_floats, src, indexes, count_dev, out, out_stride, out_offset);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }
@@ -961,8 +975,13 @@ int gs_scatter_rows_strided(int64_t capacity, int32_t row_floats, const float* s
   GS_CUDA(cudaMemsetAsync(dst, 0, (size_t)dst_rows * row_floats * sizeof(float), st));   // rows outside the visible set
   if (capacity == 0) return GS_OK;
   GS_CHECK_ARG(src && indexes, "gs_scatter_rows_strided: null tensor");
-  scatter_rows_strided_kernel<<<(unsigned)ceil_div(capacity * row_floats, 256), 256, 0, st>>>(
-      capacity, row_floats, src, src_stride, src_offset, indexes, count_dev, dst);
+  const int64_t total = capacity * row_floats;
+  if (total + 256 < (1ll << 32))
+    scatter_rows_strided_kernel<uint32_t><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(
+        capacity, row_floats, src, src_stride, src_offset, indexes, count_dev, dst);
+  else
+    scatter_rows_strided_kernel<uint64_t><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(
+        capacity, row_floats, src, src_stride, src_offset, indexes, count_dev, dst);
   GS_LAUNCH_CHECK();
   return GS_OK;
 }
@@ -973,12 +992,16 @@ int gs_split_channels(int64_t rows, int32_t channels, int32_t split, const float
   if (rows == 0) return GS_OK;
   GS_CHECK_ARG(src && first && rest, "gs_split_channels: null tensor");
   const int64_t total = rows * channels;
-  if (channels % 2 == 0 && split % 2 == 0)
-    split_channels_kernel<2><<<(unsigned)ceil_div(total / 2, 256), 256, 0, (cudaStream_t)stream>>>(total, channels, split,
-                                                                                                   src, first, rest);
-  else
-    split_channels_kernel<1><<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(total, channels, split, src,
-                                                                                               first, rest);
+  const bool small = total + 512 < (1ll << 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g2 = (unsigned)ceil_div(total / 2, 256), g1 = (unsigned)ceil_div(total, 256);
+  if (channels % 2 == 0 && split % 2 == 0) {
+    if (small) split_channels_kernel<2, uint32_t><<<g2, 256, 0, st>>>(total, channels, split, src, first, rest);
+    else split_channels_kernel<2, uint64_t><<<g2, 256, 0, st>>>(total, channels, split, src, first, rest);
+  } else {
+    if (small) split_channels_kernel<1, uint32_t><<<g1, 256, 0, st>>>(total, channels, split, src, first, rest);
+    else split_channels_kernel<1, uint64_t><<<g1, 256, 0, st>>>(total, channels, split, src, first, rest);
+  }
   GS_LAUNCH_CHECK();
   return GS_OK;
 }
@@ -989,12 +1012,16 @@ int gs_merge_channels(int64_t rows, int32_t channels, int32_t split, const float
   if (rows == 0) return GS_OK;
   GS_CHECK_ARG(dst != nullptr, "gs_merge_channels: null destination");
   const int64_t total = rows * channels;
-  if (channels % 2 == 0 && split % 2 == 0)
-    merge_channels_kernel<2><<<(unsigned)ceil_div(total / 2, 256), 256, 0, (cudaStream_t)stream>>>(total, channels, split,
-                                                                                                   first, rest, dst);
-  else
-    merge_channels_kernel<1><<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(total, channels, split,
-                                                                                               first, rest, dst);
+  const bool small = total + 512 < (1ll << 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g2 = (unsigned)ceil_div(total / 2, 256), g1 = (unsigned)ceil_div(total, 256);
+  if (channels % 2 == 0 && split % 2 == 0) {
+    if (small) merge_channels_kernel<2, uint32_t><<<g2, 256, 0, st>>>(total, channels, split, first, rest, dst);
+    else merge_channels_kernel<2, uint64_t><<<g2, 256, 0, st>>>(total, channels, split, first, rest, dst);
+  } else {
+    if (small) merge_channels_kernel<1, uint32_t><<<g1, 256, 0, st>>>(total, channels, split, first, rest, dst);
+    else merge_channels_kernel<1, uint64_t><<<g1, 256, 0, st>>>(total, channels, split, first, rest, dst);
+  }
   GS_LAUNCH_CHECK();
   return GS_OK;
 }
