@@ -151,7 +151,7 @@ int raster_cull_mask(const GsRasterParams& p, const RasterArgs& a, cudaStream_t 
 // BATCH = staged tile-list entries per buffer: 128 for narrow features, 64 for FP >= 16 (shared memory budget).
 // FOURTH: with FP = 4 the fourth accumulator is only needed when F = 4 (it is padding for F <= 3).
 template <int FP, bool VIS, int BATCH, bool FOURTH = true, bool AA = false>
-__global__ void __launch_bounds__(kFwdThreads, FP <= 8 ? 8 : (FP <= 36 ? 4 : 2))   // 32 / 64 / 128 registers
+__global__ void __launch_bounds__(kFwdThreads, FP <= 8 ? 0 : (FP <= 36 ? 4 : 2))   // narrow: no occupancy target (the compiler settles on 30 registers = 8 CTAs per SM by itself; forcing 8 lengthened the VIS walk); 64 / 128 registers for the wide ones
 raster_fwd_fast_kernel(const __grid_constant__ GsRasterParams p, const float4* __restrict__ rec,
                        const float* __restrict__ featP, const int32_t* __restrict__ ranges,
                        const int32_t* __restrict__ o2p, float* __restrict__ image, float* __restrict__ image_alpha,
