@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
 NP=${1:-4}
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $NP --steps 20 --warmup 5 > gpurun_out/s28_default_n$NP.log 2> gpurun_out/s28_default_n$NP.err; echo default rc=$?
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $NP --steps 10 --warmup 3 > gpurun_out/s28_default_n$NP.log 2> gpurun_out/s28_default_n$NP.err; echo default rc=$?
 grep -v "^\*\|OMP_NUM\|^$" gpurun_out/s28_default_n$NP.err | tail -4 | cut -c1-300
 python - <<P
 import json
